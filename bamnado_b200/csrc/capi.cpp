@@ -1,0 +1,207 @@
+// capi.cpp — the extern "C" boundary declared in include/bamnado_b200.h, a thin shell over bnd::Pileup.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bamnado_b200.h"
+#include "engine.h"
+#include "outputs.h"
+
+namespace {
+thread_local std::string g_err;
+thread_local int g_err_class = BND_OK;
+
+template <class Fn>
+int guarded(Fn fn) {
+  try {
+    fn();
+    g_err_class = BND_OK;
+    return 0;
+  } catch (const bnd::Error &e) {
+    g_err = e.what();
+    g_err_class = e.cls;
+    return e.cls;
+  } catch (const std::bad_alloc &) {
+    g_err = "out of host memory";
+    g_err_class = BND_ERR_RUNTIME;
+    return BND_ERR_RUNTIME;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    g_err_class = BND_ERR_RUNTIME;
+    return BND_ERR_RUNTIME;
+  }
+}
+
+bnd::Pileup *P(bnd_pileup *p) {
+  if (!p) bnd::fail("null pileup handle", bnd::ERR_INVALID);
+  return reinterpret_cast<bnd::Pileup *>(p);
+}
+
+static_assert(sizeof(bnd::RunRow) == sizeof(bnd_run), "row layout must match the C ABI");
+static_assert(bnd::ST_N_COUNTERS == BND_N_COUNTERS, "counter layout must match the C ABI");
+
+void rows_out(std::vector<bnd::RunRow> &rows, bnd_run **runs, uint64_t *n_runs) {
+  *n_runs = rows.size();
+  *runs = (bnd_run *)malloc(std::max<size_t>(rows.size(), 1) * sizeof(bnd_run));
+  if (!*runs) throw std::bad_alloc();
+  if (!rows.empty()) memcpy(*runs, rows.data(), rows.size() * sizeof(bnd_run));
+}
+}  // namespace
+
+extern "C" {
+
+const char *bnd_last_error(void) { return g_err.c_str(); }
+int bnd_last_error_class(void) { return g_err_class; }
+void bnd_free(void *p) { free(p); }
+int bnd_abi_version(void) { return BND_ABI_VERSION; }
+int bnd_device_count(void) { return bnd::device_count(); }
+
+bnd_pileup *bnd_pileup_create(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter) {
+  bnd::Pileup *p = nullptr;
+  int rc = guarded([&] { p = new bnd::Pileup(cfg, filter); });
+  return rc == 0 ? reinterpret_cast<bnd_pileup *>(p) : nullptr;
+}
+void bnd_pileup_destroy(bnd_pileup *p) { delete reinterpret_cast<bnd::Pileup *>(p); }
+
+int bnd_pileup_to_bedgraph(bnd_pileup *p, const char *out_path) {
+  return guarded([&] { P(p)->to_bedgraph(out_path); });
+}
+int bnd_pileup_to_bigwig(bnd_pileup *p, const char *out_path) {
+  return guarded([&] { bnd::pileup_to_bigwig(*P(p), out_path); });
+}
+int bnd_pileup_chromosome(bnd_pileup *p, const char *chrom, bnd_run **runs, uint64_t *n_runs) {
+  return guarded([&] {
+    std::vector<bnd::RunRow> rows;
+    P(p)->chromosome(chrom, rows);
+    rows_out(rows, runs, n_runs);
+  });
+}
+int bnd_pileup_runs(bnd_pileup *p, bnd_run **runs, uint64_t *n_runs) {
+  return guarded([&] {
+    std::vector<bnd::RunRow> rows;
+    P(p)->runs(rows);
+    rows_out(rows, runs, n_runs);
+  });
+}
+int bnd_pileup_norm_factor(bnd_pileup *p, double *factor) {
+  return guarded([&] { *factor = P(p)->norm_factor(); });
+}
+int bnd_pileup_stats(bnd_pileup *p, uint64_t stats[BND_N_COUNTERS]) {
+  return guarded([&] { P(p)->stats(stats); });
+}
+int bnd_pileup_accumulate(bnd_pileup *p) {
+  return guarded([&] { P(p)->accumulate(); });
+}
+int bnd_pileup_stage(bnd_pileup *p) {
+  return guarded([&] { P(p)->stage(); });
+}
+int bnd_pileup_accumulate_resident(bnd_pileup *p) {
+  return guarded([&] { P(p)->accumulate_resident(); });
+}
+int bnd_pileup_set_total_stats(bnd_pileup *p, const uint64_t stats[BND_N_COUNTERS]) {
+  return guarded([&] { P(p)->set_total_stats(stats); });
+}
+int bnd_pileup_finalize(bnd_pileup *p, uint64_t *n_runs) {
+  return guarded([&] {
+    uint64_t n = P(p)->finalize();
+    if (n_runs) *n_runs = n;
+  });
+}
+int bnd_pileup_bedgraph_text(bnd_pileup *p, char **text, uint64_t *n_bytes) {
+  return guarded([&] {
+    std::string s;
+    P(p)->bedgraph_text(s);
+    *n_bytes = s.size();
+    *text = (char *)malloc(s.size() + 1);
+    if (!*text) throw std::bad_alloc();
+    memcpy(*text, s.data(), s.size());
+    (*text)[s.size()] = 0;
+  });
+}
+int bnd_pileup_timings(bnd_pileup *p, double ms[8]) {
+  return guarded([&] {
+    const bnd::Timings &t = P(p)->timings();
+    ms[0] = t.inflate_ms, ms[1] = t.index_ms, ms[2] = t.pileup_ms, ms[3] = t.finalize_ms;
+    ms[4] = t.h2d_ms, ms[5] = t.text_ms, ms[6] = t.wall_ms, ms[7] = t.read_ms;
+  });
+}
+int bnd_pileup_shape(bnd_pileup *p, uint64_t shape[8]) {
+  return guarded([&] {
+    const bnd::Shape &s = P(p)->shape();
+    shape[0] = s.records, shape[1] = s.comp_bytes, shape[2] = s.inflated_bytes, shape[3] = s.blocks;
+    shape[4] = s.bins, shape[5] = s.launches, shape[6] = s.chunk_len, shape[7] = s.n_chunks;
+  });
+}
+
+int bnd_signal_for_chromosome(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter, const char *chrom, float **signal,
+                              uint64_t *n) {
+  return guarded([&] {
+    // get_signal_for_chromosome builds BamPileup::new(.., Raw, scale, use_fragment, filter, collapse = true, ..)
+    bnd_pileup_cfg c = *cfg;
+    c.norm_method = 0;
+    c.collapse = 1;
+    c.has_shift = 0;
+    c.has_truncate = 0;
+    c.shard_world = 0;
+    bnd::Pileup pile(&c, filter);
+    std::vector<float> v;
+    pile.signal(chrom, v);
+    *n = v.size();
+    *signal = (float *)malloc(std::max<size_t>(v.size(), 1) * sizeof(float));
+    if (!*signal) throw std::bad_alloc();
+    if (!v.empty()) memcpy(*signal, v.data(), v.size() * sizeof(float));
+  });
+}
+
+int bnd_multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int32_t n_bams, const char *out_path) {
+  return guarded([&] { bnd::multi_to_tsv(cfgs, filters, n_bams, out_path); });
+}
+
+int bnd_collapse_bedgraph(const char *in_path, const char *out_path) {
+  return guarded([&] { bnd::collapse_bedgraph_file(in_path, out_path); });
+}
+
+double bnd_scale_factor(int32_t method, float base_scale, uint64_t bin_size, uint64_t n_reads) {
+  // NormalizationMethod::scale_factor (signal_normalization.rs:50-74); method: 0 raw, 1 rpkm, 2 cpm
+  const double base = (double)base_scale;
+  if (method == 0) return base;
+  if (n_reads == 0) return 0.0;
+  const double rpm = 1000000.0 / (double)n_reads;
+  if (method == 2) return base * rpm;
+  const double per_kb = 1000.0 / (double)bin_size;
+  return base * rpm * per_kb;
+}
+
+int bnd_bam_stats(const char *bam_path, uint64_t bin_size, uint64_t out[6]) {
+  return guarded([&] {
+    bnd_pileup_cfg c;
+    memset(&c, 0, sizeof c);
+    c.bam_path = bam_path;
+    c.bin_size = bin_size;
+    c.scale_factor = 1.f;
+    c.device = -1;
+    bnd::Pileup pile(&c, nullptr);
+    const bnd::Geometry &g = pile.geometry();
+    out[0] = g.n_mapped, out[1] = g.n_unmapped, out[2] = g.genome_len, out[3] = g.L, out[4] = g.total_chunks();
+    out[5] = pile.header().names.size();
+  });
+}
+
+int bnd_cli_main(int argc, const char *const *argv) { return bnd::cli_main(argc, argv); }
+
+int bnd_bgzf_inflate(const uint8_t *bgzf, uint64_t n_bytes, uint8_t *out, uint64_t out_cap, uint64_t *out_len, int32_t *status,
+                     uint64_t status_cap, uint64_t *n_blocks) {
+  return guarded([&] {
+    std::vector<uint8_t> o;
+    std::vector<int32_t> st;
+    bnd::device_inflate(bgzf, n_bytes, o, st, -1);
+    if (o.size() > out_cap || st.size() > status_cap) bnd::fail("output buffer too small", bnd::ERR_INVALID);
+    if (!o.empty()) memcpy(out, o.data(), o.size());
+    if (!st.empty()) memcpy(status, st.data(), st.size() * sizeof(int32_t));
+    *out_len = o.size();
+    *n_blocks = st.size();
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// common.cuh — shared device helpers for the sm_100a kernels of the BamNado coverage path.
+//
+// Everything here is byte/integer plumbing (unaligned little-endian loads, sub-warp tiles, launch macro).  The
+// path has no GEMM-shaped work, so nothing goes through tensor cores; the rules that matter are coalescing,
+// shared-memory staging and keeping enough independent warps in flight.
+#pragma once
+#include <stdint.h>
+#if defined(BND_EMUL)
+#include "cuda_emul.h"  // tests/emul: CPU SIMT emulator, test infrastructure only
+#define BND_LAUNCH(kern, grid, block, smem, stream, ...) \
+  emul::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
+#define BND_DYN_SMEM(name) unsigned char *name = emul::dyn_smem()
+#else
+#include <cuda_runtime.h>
+#define BND_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define BND_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+namespace bnd {
+
+template <class T>
+__host__ __device__ __forceinline__ T tmin(T a, T b) {
+  return a < b ? a : b;
+}
+template <class T>
+__host__ __device__ __forceinline__ T tmax(T a, T b) {
+  return a > b ? a : b;
+}
+
+// A power-of-two group of G consecutive lanes inside one warp, driven with raw warp intrinsics.
+template <int G>
+struct Tile {
+  static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "tile width must be a power of two <= 32");
+  unsigned mask;
+  int lane;   // rank inside the tile
+  int shift;  // first warp lane of the tile
+  __device__ __forceinline__ Tile() {
+    int wl = (int)(threadIdx.x & 31u);
+    lane = wl & (G - 1);
+    shift = wl - lane;
+    mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << shift);
+  }
+  template <class T>
+  __device__ __forceinline__ T shfl(T v, int src) const {
+    return __shfl_sync(mask, v, src, G);
+  }
+  template <class T>
+  __device__ __forceinline__ T shfl_up(T v, unsigned d) const {
+    return __shfl_up_sync(mask, v, d, G);
+  }
+  template <class T>
+  __device__ __forceinline__ T shfl_down(T v, unsigned d) const {
+    return __shfl_down_sync(mask, v, d, G);
+  }
+  template <class T>
+  __device__ __forceinline__ T shfl_xor(T v, int d) const {
+    return __shfl_xor_sync(mask, v, d, G);
+  }
+  __device__ __forceinline__ unsigned ballot(int pred) const { return (__ballot_sync(mask, pred) & mask) >> shift; }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
+// ---- unaligned little-endian loads (BAM records sit at arbitrary byte offsets) ---------------------------------
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) {
+  uintptr_t a = (uintptr_t)p;
+  const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+  unsigned sh = (unsigned)(a & 3) * 8;
+  uint32_t lo = w[0];
+  if (sh == 0) return lo;
+  uint32_t hi = w[1];
+  return __funnelshift_r(lo, hi, sh);
+}
+__device__ __forceinline__ uint32_t ld_u16_unaligned(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+// warp-wide inclusive scan (all 32 lanes participate)
+template <class T>
+__device__ __forceinline__ T warp_inclusive_scan(T v) {
+  const int lane = (int)(threadIdx.x & 31u);
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+template <class T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// CTA-wide exclusive scan for THREADS threads; `total` receives the CTA sum.  scratch: THREADS/32 + 1 entries.
+template <int THREADS, class T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T *scratch, T &total) {
+  constexpr int NW = THREADS / 32;
+  const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+  T inc = warp_inclusive_scan(v);
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < NW ? scratch[lane] : T(0);
+    T wi = warp_inclusive_scan(w);
+    if (lane < NW) scratch[lane] = wi - w;
+    if (lane == NW - 1) scratch[NW] = wi;
+  }
+  __syncthreads();
+  T out = scratch[warp] + inc - v;
+  total = scratch[NW];
+  __syncthreads();
+  return out;
+}
+
+}  // namespace bnd

@@ -1,0 +1,1173 @@
+// engine.cpp — see engine.h.
+#include "engine.h"
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <thread>
+
+#include "cuda_rt.h"
+#include "kernels.h"
+
+namespace bnd {
+
+namespace {
+
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) fail(std::string("CUDA error: ") + cudaGetErrorString(e_) + " in " #call);     \
+  } while (0)
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+uint64_t env_u64(const char *name, uint64_t dflt) {
+  const char *e = getenv(name);
+  if (!e || !*e) return dflt;
+  return strtoull(e, nullptr, 10);
+}
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  // grows (never shrinks); the caller guarantees no kernel still uses the old allocation
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) CU(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 256;
+    CU(cudaMalloc(&p, want));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+constexpr int NSET = 3;
+
+struct SegSet {
+  cudaStream_t stream = nullptr;
+  DevBuf comp, coff, uoff, infl, t_entry, t_exit, t_count, t_base, t_slots, rec_off;
+  SegState *st = nullptr;
+  uint32_t *work = nullptr;
+  cudaEvent_t ev_idx = nullptr, ev_carry = nullptr;
+  bool carry_pending = false;  // ev_carry was recorded for the segment that followed this set's last use
+};
+
+struct StageSlot {
+  uint8_t *pin = nullptr;
+  size_t cap = 0;
+  BlockTable tab;
+  cudaEvent_t ev_h2d = nullptr;
+  bool h2d_pending = false;
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (pin) CU(cudaFreeHost(pin));
+    pin = nullptr;
+    cap = 0;
+    CU(cudaHostAlloc((void **)&pin, n, cudaHostAllocDefault));
+    cap = n;
+  }
+};
+
+}  // namespace
+
+struct DeviceCtx {
+  int device = 0;
+  int sm_count = 1;
+  CrcTables *d_crc = nullptr;
+  SegSet sets[NSET];
+  std::vector<StageSlot> slots;
+  uint64_t seg_bytes = 0, carry_cap = 0;
+  int n_readers = 4;
+  std::mutex mu;  // one pass at a time per device context
+};
+
+namespace {
+
+std::mutex g_ctx_mu;
+std::map<int, std::unique_ptr<DeviceCtx>> g_ctx;
+
+DeviceCtx &ctx_for(int device) {
+  std::lock_guard<std::mutex> g(g_ctx_mu);
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    fail("bamnado_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback");
+  if (device < 0) CU(cudaGetDevice(&device));
+  if (device >= n) fail("CUDA device ordinal out of range", ERR_INVALID);
+  auto it = g_ctx.find(device);
+  if (it != g_ctx.end()) {
+    CU(cudaSetDevice(device));
+    return *it->second;
+  }
+  CU(cudaSetDevice(device));
+  auto c = std::make_unique<DeviceCtx>();
+  c->device = device;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
+  c->seg_bytes = env_u64("BND_SEGMENT_BYTES", 96ull << 20);
+  c->carry_cap = env_u64("BND_CARRY_BYTES", 8ull << 20);
+  c->carry_cap = (c->carry_cap + REC_TILE - 1) / REC_TILE * REC_TILE;
+  c->n_readers = (int)env_u64("BND_READERS", 4);
+  int n_slots = (int)env_u64("BND_STAGES", 4);
+  if (n_slots < 2) n_slots = 2;
+  c->slots.resize(n_slots);
+  for (auto &s : c->slots) CU(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+  CrcTables host_crc;
+  make_crc_tables(&host_crc);
+  CU(cudaMalloc((void **)&c->d_crc, sizeof(CrcTables)));
+  CU(cudaMemcpy(c->d_crc, &host_crc, sizeof(CrcTables), cudaMemcpyHostToDevice));
+  for (auto &s : c->sets) {
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaMalloc((void **)&s.st, sizeof(SegState)));
+    CU(cudaMalloc((void **)&s.work, 256));
+    CU(cudaEventCreateWithFlags(&s.ev_idx, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_carry, cudaEventDisableTiming));
+  }
+  DeviceCtx &ref = *c;
+  g_ctx[device] = std::move(c);
+  return ref;
+}
+
+struct Segment {
+  uint64_t begin, end;  // file offsets (BGZF block starts)
+};
+
+// ---- reader pool: file bytes -> pinned staging slots, plus the BGZF block table of each segment --------------------
+struct ReaderPool {
+  struct Job {
+    size_t seg;
+    int slot;
+  };
+  int fd;
+  DeviceCtx &ctx;
+  const std::vector<Segment> &segs;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  std::deque<Job> jobs;
+  std::vector<char> done;  // per segment
+  std::string error;
+  bool stop = false;
+  std::vector<std::thread> threads;
+  double read_ms = 0;
+
+  ReaderPool(int fd_, DeviceCtx &c, const std::vector<Segment> &s, int n_threads) : fd(fd_), ctx(c), segs(s) {
+    for (int i = 0; i < n_threads; i++) threads.emplace_back([this] { work(); });
+  }
+  ~ReaderPool() {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      stop = true;
+    }
+    cv_job.notify_all();
+    for (auto &t : threads) t.join();
+  }
+  void submit(size_t seg, int slot) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (done.size() <= seg) done.resize(seg + 1, 0);
+      jobs.push_back(Job{seg, slot});
+    }
+    cv_job.notify_one();
+  }
+  void wait(size_t seg) {
+    std::unique_lock<std::mutex> g(mu);
+    cv_done.wait(g, [&] { return !error.empty() || (done.size() > seg && done[seg]); });
+    if (!error.empty()) fail(error);
+  }
+  void work() {
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> g(mu);
+        cv_job.wait(g, [&] { return stop || !jobs.empty(); });
+        if (stop && jobs.empty()) return;
+        j = jobs.front();
+        jobs.pop_front();
+      }
+      std::string err;
+      double t0 = now_ms();
+      try {
+        const Segment &s = segs[j.seg];
+        StageSlot &slot = ctx.slots[j.slot];
+        const uint64_t len = s.end - s.begin;
+        uint64_t got = 0;
+        while (got < len) {
+          ssize_t r = pread(fd, slot.pin + got, len - got, (off_t)(s.begin + got));
+          if (r < 0) fail("read error on BAM file");
+          if (r == 0) fail("unexpected end of BAM file");
+          got += (uint64_t)r;
+        }
+        scan_bgzf_blocks(slot.pin, len, slot.tab);
+        if (slot.tab.coff.back() != len) fail("BAM segment does not end on a BGZF block boundary (corrupt file or index)");
+      } catch (const std::exception &e) {
+        err = e.what();
+      }
+      {
+        std::lock_guard<std::mutex> g(mu);
+        if (!err.empty() && error.empty()) error = err;
+        done[j.seg] = 1;
+        read_ms += now_ms() - t0;
+      }
+      cv_done.notify_all();
+    }
+  }
+};
+
+}  // namespace
+
+// ---- Pileup::Impl: device state of one pileup ------------------------------------------------------------------------
+struct Pileup::Impl {
+  DeviceCtx *ctx = nullptr;
+  int fd = -1;
+  std::vector<uint64_t> cut_points;  // sorted BGZF block starts known from the index
+  // geometry + filter tables on the device
+  DevBuf d_ref_len, d_first_bin, d_first_chunk;
+  DevBuf d_rg, d_tagv, d_bl_off, d_bl_starts, d_bl_stops, d_bc_table, d_bc_off, d_bc_pool;
+  FilterDev fdev{};
+  PileDev pdev{};
+  GeomDev gdev{};
+  // accumulators
+  DevBuf d_diff, d_stats, d_probe, d_err;
+  // finalize products
+  DevBuf d_tile_sum, d_tile_heads, d_run_bin, d_run_val, d_counts, d_fs;
+  uint64_t n_runs = 0;
+  uint32_t max_val = 0;
+  uint64_t fin_bins = 0;
+  // resident copy of the shard's compressed bytes
+  DevBuf d_resident;
+  std::vector<Segment> res_segs;
+  std::vector<BlockTable> res_tabs;
+  ~Impl() {
+    if (fd >= 0) close(fd);
+    for (DevBuf *b : {&d_ref_len, &d_first_bin, &d_first_chunk, &d_rg, &d_tagv, &d_bl_off, &d_bl_starts, &d_bl_stops, &d_bc_table,
+                      &d_bc_off, &d_bc_pool, &d_diff, &d_stats, &d_probe, &d_err, &d_tile_sum, &d_tile_heads, &d_run_bin, &d_run_val,
+                      &d_counts, &d_fs, &d_resident})
+      b->release();
+  }
+};
+
+namespace {
+template <class T>
+void upload(DevBuf &b, const T *src, size_t n) {
+  b.ensure(std::max<size_t>(n * sizeof(T), 16));
+  if (n) CU(cudaMemcpy(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+}
+}  // namespace
+
+int device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void device_inflate(const uint8_t *bgzf, uint64_t n_bytes, std::vector<uint8_t> &out, std::vector<int32_t> &status, int device) {
+  DeviceCtx &ctx = ctx_for(device);
+  std::lock_guard<std::mutex> g(ctx.mu);
+  BlockTable tab;
+  scan_bgzf_blocks(bgzf, n_bytes, tab);
+  const uint64_t nblk = tab.coff.size() - 1;
+  out.assign(tab.uoff.back(), 0);
+  status.assign(nblk, 0);
+  if (nblk == 0) return;
+  DevBuf comp, coff, uoff, infl, st, err, work;
+  try {
+    comp.ensure(tab.coff.back() + 64);
+    CU(cudaMemcpy(comp.p, bgzf, tab.coff.back(), cudaMemcpyHostToDevice));
+    upload(coff, tab.coff.data(), tab.coff.size());
+    upload(uoff, tab.uoff.data(), tab.uoff.size());
+    infl.ensure(tab.uoff.back() + 64);
+    st.ensure(nblk * 4);
+    err.ensure(16);
+    work.ensure(16);
+    CU(cudaMemset(err.p, 0, 16));
+    CU(cudaMemset(work.p, 0, 16));
+    InflateArgs a{};
+    a.comp = comp.as<uint8_t>();
+    a.blk_coff = coff.as<uint64_t>();
+    a.blk_uoff = uoff.as<uint64_t>();
+    a.out = infl.as<uint8_t>();
+    a.status = st.as<int32_t>();
+    a.error_flag = err.as<int32_t>();
+    a.work_counter = work.as<uint32_t>();
+    a.crc = ctx.d_crc;
+    a.n_blocks = (uint32_t)nblk;
+    a.verify_crc = 1;
+    CU(launch_inflate(a, ctx.sm_count, ctx.sets[0].stream));
+    CU(cudaStreamSynchronize(ctx.sets[0].stream));
+    if (!out.empty()) CU(cudaMemcpy(out.data(), infl.p, out.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(status.data(), st.p, nblk * 4, cudaMemcpyDeviceToHost));
+  } catch (...) {
+    for (DevBuf *b : {&comp, &coff, &uoff, &infl, &st, &err, &work}) b->release();
+    throw;
+  }
+  for (DevBuf *b : {&comp, &coff, &uoff, &infl, &st, &err, &work}) b->release();
+}
+
+// ---- construction ---------------------------------------------------------------------------------------------------
+Pileup::Pileup(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter) : im_(new Impl()) {
+  if (!cfg || !cfg->bam_path) fail("missing BAM path", ERR_INVALID);
+  cfg_ = *cfg;
+  bam_path_ = cfg->bam_path;
+  cfg_.bam_path = nullptr;
+  if (cfg_.bin_size == 0) fail("bin size must be greater than 0", ERR_INVALID);
+  im_->ctx = &ctx_for(cfg_.device);
+  open();
+  bnd_filter_cfg dflt;
+  memset(&dflt, 0, sizeof dflt);
+  dflt.max_length = 0xffffffffu;
+  dflt.barcode_csv_column = -1;
+  filt_ = make_filter_host(filter ? filter : &dflt, hdr_);
+  geo_ = make_geometry(hdr_, bai_, cfg_.bin_size);
+
+  // device copies of geometry and filter tables
+  Impl &im = *im_;
+  const size_t n_ref = hdr_.names.size();
+  upload(im.d_ref_len, hdr_.lens.data(), n_ref);
+  upload(im.d_first_bin, geo_.ref_first_bin.data(), n_ref + 1);
+  upload(im.d_first_chunk, geo_.ref_first_chunk.data(), n_ref + 1);
+  GeomDev &g = im.gdev;
+  g.n_ref = (int32_t)n_ref;
+  g.ref_len = im.d_ref_len.as<uint64_t>();
+  g.ref_first_bin = im.d_first_bin.as<uint64_t>();
+  g.ref_first_chunk = im.d_first_chunk.as<uint64_t>();
+  g.L = geo_.L;
+  g.bin = geo_.bin;
+  g.nbf = geo_.nbf;
+
+  FilterDev &f = im.fdev;
+  const bnd_filter_cfg &c = filt_.cfg;
+  f.strand = c.strand;
+  f.proper_pair = c.proper_pair != 0;
+  f.min_mapq = c.min_mapq;
+  f.min_length = c.min_length;
+  f.max_length = c.max_length;
+  f.has_min_frag = c.has_min_fragment_length != 0;
+  f.min_frag = c.min_fragment_length;
+  f.has_max_frag = c.has_max_fragment_length != 0;
+  f.max_frag = c.max_fragment_length;
+  f.ex_dup = c.exclude_duplicates != 0;
+  f.ex_sec = c.exclude_secondary != 0;
+  f.ex_sup = c.exclude_supplementary != 0;
+  if (filt_.has_rg) {
+    upload(im.d_rg, filt_.rg.data(), filt_.rg.size());
+    f.has_rg = 1;
+    f.rg_len = (int32_t)filt_.rg.size();
+    f.rg = im.d_rg.as<char>();
+  }
+  if (filt_.has_tag && filt_.has_tag_value) {  // `--tag` alone is ignored (read_filter.rs:769-771)
+    upload(im.d_tagv, filt_.tag_value.data(), filt_.tag_value.size());
+    f.has_tag = 1;
+    f.tag_name_ok = filt_.tag.size() == 2;
+    f.tag0 = f.tag_name_ok ? filt_.tag[0] : 0;
+    f.tag1 = f.tag_name_ok ? filt_.tag[1] : 0;
+    f.tagv_len = (int32_t)filt_.tag_value.size();
+    f.tagv = im.d_tagv.as<char>();
+  }
+  if (filt_.has_blacklist) {
+    upload(im.d_bl_off, filt_.bl_off.data(), filt_.bl_off.size());
+    upload(im.d_bl_starts, filt_.bl_starts.data(), filt_.bl_starts.size());
+    upload(im.d_bl_stops, filt_.bl_stops.data(), filt_.bl_stops.size());
+    f.has_blacklist = 1;
+    f.bl_off = im.d_bl_off.as<uint64_t>();
+    f.bl_starts = im.d_bl_starts.as<uint64_t>();
+    f.bl_stops = im.d_bl_stops.as<uint64_t>();
+  }
+  if (filt_.has_barcodes) {
+    upload(im.d_bc_table, filt_.bc_table.data(), filt_.bc_table.size());
+    upload(im.d_bc_off, filt_.bc_off.data(), filt_.bc_off.size());
+    upload(im.d_bc_pool, filt_.bc_pool.data(), filt_.bc_pool.size());
+    f.has_barcodes = 1;
+    f.bc_mask = (uint32_t)filt_.bc_table.size() - 1;
+    f.bc_table = im.d_bc_table.as<uint32_t>();
+    f.bc_off = im.d_bc_off.as<uint32_t>();
+    f.bc_pool = im.d_bc_pool.as<char>();
+  }
+  PileDev &p = im.pdev;
+  p.use_fragment = cfg_.use_fragment != 0;
+  if (cfg_.has_shift) {
+    for (int i = 0; i < 4; i++) p.shift[i] = cfg_.shift[i];
+    p.shift_on = p.shift[0] || p.shift[1] || p.shift[2] || p.shift[3];
+  }
+  if (cfg_.has_truncate) {
+    p.has_trunc = 1;
+    p.t_has5 = cfg_.trunc_has5 != 0;
+    p.t5 = cfg_.trunc5;
+    p.t_has3 = cfg_.trunc_has3 != 0;
+    p.t3 = cfg_.trunc3;
+  }
+  // this process's shard of the genomic chunks: contiguous chunk ranges balanced by compressed bytes
+  const uint64_t nchunks = geo_.total_chunks();
+  uint64_t lo = 0, hi = nchunks;
+  const int world = cfg_.shard_world > 1 ? cfg_.shard_world : 1;
+  const int rank = world > 1 ? cfg_.shard_rank : 0;
+  if (rank < 0 || rank >= world) fail("shard_rank out of range", ERR_INVALID);
+  if (world > 1 && nchunks > 0) {
+    auto boundary = [&](int k) -> uint64_t {  // first chunk of rank k
+      if (k <= 0) return 0;
+      if (k >= world) return nchunks;
+      if (nchunks > (1u << 22)) return nchunks * (uint64_t)k / (uint64_t)world;  // degenerate geometry: split by count
+      const uint64_t first = hdr_.first_record_voff >> 16;
+      const uint64_t target = first + (file_size_ - first) * (uint64_t)k / (uint64_t)world;
+      uint64_t a = 0, b = nchunks;  // smallest chunk whose lower-bound offset reaches the target
+      while (a < b) {
+        uint64_t mid = (a + b) / 2;
+        int r = geo_.ref_of_chunk(mid);
+        uint64_t cs = (mid - geo_.ref_first_chunk[r]) * geo_.L + 1;
+        uint64_t v = voff_lower_bound(bai_, r, cs);
+        uint64_t co = v == ~0ull ? file_size_ : (v >> 16);
+        if (co < target) a = mid + 1;
+        else b = mid;
+      }
+      return a;
+    };
+    lo = boundary(rank);
+    hi = boundary(rank + 1);
+    if (hi < lo) hi = lo;
+  }
+  shard_ = range_for_chunks(lo, hi);
+  shape_.chunk_len = geo_.L;
+  shape_.n_chunks = nchunks;
+}
+
+Pileup::~Pileup() = default;
+
+void Pileup::open() {
+  Impl &im = *im_;
+  im.fd = ::open(bam_path_.c_str(), O_RDONLY);
+  if (im.fd < 0) fail("File not found: " + bam_path_);
+  struct stat st;
+  if (fstat(im.fd, &st) != 0) fail("cannot stat " + bam_path_);
+  file_size_ = (uint64_t)st.st_size;
+  bai_ = read_bai(bam_path_ + ".bai");
+  // header: inflate leading BGZF blocks on the device until the header parses
+  uint64_t want = 1u << 18;
+  std::vector<uint8_t> raw, inflated;
+  std::vector<int32_t> status;
+  for (;;) {
+    want = std::min<uint64_t>(want, file_size_);
+    raw.resize(want);
+    uint64_t got = 0;
+    while (got < want) {
+      ssize_t r = pread(im.fd, raw.data() + got, want - got, (off_t)got);
+      if (r <= 0) fail("read error on " + bam_path_);
+      got += (uint64_t)r;
+    }
+    BlockTable tab;
+    scan_bgzf_blocks(raw.data(), want, tab);
+    if (tab.coff.size() < 2) {
+      if (want == file_size_) fail("not a BGZF file: " + bam_path_);
+      want *= 4;
+      continue;
+    }
+    device_inflate(raw.data(), tab.coff.back(), inflated, status, im.ctx->device);
+    for (size_t i = 0; i < status.size(); i++)
+      if (status[i] != 0) fail("BGZF inflate failed in the BAM header (block " + std::to_string(i) + ", status " + std::to_string(status[i]) + ")");
+    uint64_t consumed = 0;
+    if (parse_bam_header(inflated.data(), inflated.size(), hdr_, consumed)) {
+      // virtual offset of the first record: block holding inflated byte `consumed`
+      size_t b = (size_t)(std::upper_bound(tab.uoff.begin(), tab.uoff.end(), consumed) - tab.uoff.begin()) - 1;
+      if (b >= tab.coff.size() - 1) {  // header ends exactly at the end of the inflated data
+        b = tab.coff.size() - 1;
+        hdr_.first_record_voff = tab.coff[b] << 16;
+      } else {
+        hdr_.first_record_voff = (tab.coff[b] << 16) | (consumed - tab.uoff[b]);
+      }
+      break;
+    }
+    if (want == file_size_) fail("truncated BAM header: " + bam_path_);
+    want *= 4;
+  }
+  // block starts known from the index: segment cut points
+  std::vector<uint64_t> &cp = im.cut_points;
+  for (const BaiRef &R : bai_.refs) {
+    for (const BaiChunk &c : R.chunks) {
+      cp.push_back(c.beg >> 16);
+      cp.push_back(c.end >> 16);
+    }
+    for (uint64_t v : R.linear)
+      if (v) cp.push_back(v >> 16);
+  }
+  std::sort(cp.begin(), cp.end());
+  cp.erase(std::unique(cp.begin(), cp.end()), cp.end());
+  while (!cp.empty() && cp.back() >= file_size_) cp.pop_back();
+}
+
+Pileup::Range Pileup::range_for_chunks(uint64_t lo, uint64_t hi) const {
+  Range r;
+  r.chunk_lo = lo;
+  r.chunk_hi = hi;
+  const uint64_t nchunks = geo_.total_chunks();
+  if (lo >= hi) {
+    r.byte_begin = r.byte_end = file_size_;
+    return r;
+  }
+  const uint64_t first = hdr_.first_record_voff;
+  uint64_t v0;
+  if (lo == 0) {
+    v0 = first;
+  } else {
+    int ref = geo_.ref_of_chunk(lo);
+    uint64_t cs = (lo - geo_.ref_first_chunk[ref]) * geo_.L + 1;
+    v0 = voff_lower_bound(bai_, ref, cs);
+    if (v0 != ~0ull && v0 < first) v0 = first;
+  }
+  if (v0 == ~0ull) {
+    r.byte_begin = r.byte_end = file_size_;
+    return r;
+  }
+  r.byte_begin = v0 >> 16;
+  r.entry_uoff = v0 & 0xffff;
+  if (hi >= nchunks) {
+    r.byte_end = file_size_;
+    return r;
+  }
+  int ref_e = geo_.ref_of_chunk(hi - 1);
+  uint64_t ce = std::min((hi - geo_.ref_first_chunk[ref_e]) * geo_.L, hdr_.lens[ref_e]);
+  r.bounded = true;
+  r.end_ref = ref_e;
+  r.end_pos = ce;
+  uint64_t v1 = voff_lower_bound(bai_, ref_e, ce + 1 + 2 * 16384);
+  if (v1 == ~0ull) {
+    r.byte_end = file_size_;
+  } else {
+    const std::vector<uint64_t> &cp = im_->cut_points;
+    auto it = std::upper_bound(cp.begin(), cp.end(), v1 >> 16);
+    r.byte_end = it == cp.end() ? file_size_ : *it;
+  }
+  if (r.byte_end < r.byte_begin) r.byte_end = r.byte_begin;
+  return r;
+}
+
+void Pileup::reset_accumulators(const Range &r) {
+  Impl &im = *im_;
+  GeomDev &g = im.gdev;
+  g.chunk_lo = r.chunk_lo;
+  g.chunk_hi = r.chunk_hi;
+  g.bin_lo = geo_.first_bin_of_chunk(r.chunk_lo);
+  g.bin_hi = geo_.first_bin_of_chunk(r.chunk_hi);
+  const uint64_t nb = g.bin_hi - g.bin_lo;
+  im.d_diff.ensure((nb + 1) * sizeof(int32_t) + 64);
+  CU(cudaMemset(im.d_diff.p, 0, (nb + 1) * sizeof(int32_t)));
+  im.d_stats.ensure(ST_N_COUNTERS * 8);
+  CU(cudaMemset(im.d_stats.p, 0, ST_N_COUNTERS * 8));
+  im.d_probe.ensure(16);
+  CU(cudaMemset(im.d_probe.p, 0, 16));
+  im.d_err.ensure(16);
+  CU(cudaMemset(im.d_err.p, 0, 16));
+  CU(cudaDeviceSynchronize());  // the pass runs on non-blocking streams: order it after the clears
+  memset(stats_, 0, sizeof stats_);
+  total_stats_set_ = false;
+  finalized_ = false;
+  im.n_runs = 0;
+  im.max_val = 0;
+}
+
+// ---- the hot path: segments of compressed bytes -> inflate -> record index -> filter/scatter ----------------------------
+void Pileup::run_pass(const Range &range, bool resident) {
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  const double t_wall0 = now_ms();
+  const unsigned long long launches0 = launch_count();
+  reset_accumulators(range);
+  tm_ = Timings();
+  shape_.records = shape_.comp_bytes = shape_.inflated_bytes = shape_.blocks = 0;
+  shape_.bins = im.gdev.bin_hi - im.gdev.bin_lo;
+
+  // ---- plan segments: cut at block starts known from the index ----
+  std::vector<Segment> segs;
+  const std::vector<uint64_t> &cp = im.cut_points;
+  auto next_cut = [&](uint64_t cur, uint64_t limit) -> uint64_t {  // a block start in (cur, limit], as far as seg_bytes allows
+    uint64_t target = cur + ctx.seg_bytes;
+    if (target >= limit) return limit;
+    auto it = std::upper_bound(cp.begin(), cp.end(), target);  // first > target
+    if (it != cp.begin()) {
+      uint64_t c = *(it - 1);
+      if (c > cur) return std::min(c, limit);
+    }
+    if (it != cp.end()) return std::min(*it, limit);
+    return limit;
+  };
+  if (resident) {
+    segs = im.res_segs;
+  } else {
+    for (uint64_t cur = range.byte_begin; cur < range.byte_end;) {
+      uint64_t nx = next_cut(cur, range.byte_end);
+      segs.push_back(Segment{cur, nx});
+      cur = nx;
+    }
+  }
+
+  const int n_slots = (int)ctx.slots.size();
+  std::unique_ptr<ReaderPool> pool;
+  auto submit = [&](size_t i) {
+    StageSlot &slot = ctx.slots[i % n_slots];
+    if (slot.h2d_pending) {
+      CU(cudaEventSynchronize(slot.ev_h2d));
+      slot.h2d_pending = false;
+    }
+    slot.ensure(segs[i].end - segs[i].begin + 64);
+    pool->submit(i, (int)(i % n_slots));
+  };
+  if (!resident) {
+    pool.reset(new ReaderPool(im.fd, ctx, segs, std::max(1, std::min(ctx.n_readers, n_slots))));
+    for (size_t i = 0; i < segs.size() && i < (size_t)n_slots; i++) submit(i);
+  }
+
+  struct SegEvents {
+    cudaEvent_t e[5];  // h2d begin, inflate begin, index begin, pileup begin, end
+  };
+  std::vector<SegEvents> evs;
+  const bool verify_crc = env_u64("BND_VERIFY_CRC", 1) != 0;
+  const int use_window = (int)env_u64("BND_USE_WINDOW", 1);
+  for (auto &s : ctx.sets) s.carry_pending = false;
+
+  size_t i = 0;
+  unsigned long long probe_host[2] = {0, 0};
+  for (;;) {
+    for (; i < segs.size(); i++) {
+      const Segment &sg = segs[i];
+      SegSet &S = ctx.sets[i % NSET];
+      const BlockTable *tab;
+      const uint8_t *host_src = nullptr;
+      if (resident) {
+        tab = &im.res_tabs[i];
+      } else {
+        pool->wait(i);
+        StageSlot &slot = ctx.slots[i % n_slots];
+        tab = &slot.tab;
+        host_src = slot.pin;
+      }
+      const uint64_t clen = sg.end - sg.begin;
+      const uint64_t nblk = tab->coff.size() - 1;
+      const uint64_t ulen = tab->uoff.back();
+      const uint64_t data_end = ctx.carry_cap + ulen;
+      const uint32_t n_tiles = (uint32_t)((data_end + REC_TILE - 1) / REC_TILE);
+      // the segment that followed this set's previous use must have taken its carry before the buffers are reused
+      if (S.carry_pending) {
+        CU(cudaStreamWaitEvent(S.stream, S.ev_carry, 0));
+        S.carry_pending = false;
+      }
+      const bool grow = (!resident && clen + 64 > S.comp.cap) || (nblk + 1) * 8 > S.coff.cap || data_end + 64 > S.infl.cap ||
+                        (size_t)n_tiles * 8 > S.t_entry.cap || (ulen / 36 + 2) * 8 > S.rec_off.cap;
+      if (grow) {
+        for (auto &q : ctx.sets) CU(cudaStreamSynchronize(q.stream));  // rare: nothing may still use the old buffers
+        if (!resident) S.comp.ensure(clen + 64);
+        S.coff.ensure((nblk + 1) * 8);
+        S.uoff.ensure((nblk + 1) * 8);
+        S.infl.ensure(data_end + 64);
+        S.t_entry.ensure((size_t)n_tiles * 8);
+        S.t_exit.ensure((size_t)n_tiles * 8);
+        S.t_count.ensure((size_t)n_tiles * 4);
+        S.t_base.ensure((size_t)n_tiles * 8);
+        S.t_slots.ensure((size_t)n_tiles * REC_SLOTS * 2);
+        S.rec_off.ensure((ulen / 36 + 2) * 8);
+      }
+      evs.emplace_back();
+      SegEvents &E = evs.back();
+      for (auto &e : E.e) CU(cudaEventCreate(&e));
+      cudaStream_t st = S.stream;
+      CU(cudaEventRecord(E.e[0], st));
+      const uint8_t *d_comp;
+      if (resident) {
+        d_comp = im.d_resident.as<uint8_t>() + (sg.begin - im.res_segs.front().begin);
+      } else {
+        CU(cudaMemcpyAsync(S.comp.p, host_src, clen, cudaMemcpyHostToDevice, st));
+        d_comp = S.comp.as<uint8_t>();
+      }
+      CU(cudaMemcpyAsync(S.coff.p, tab->coff.data(), (nblk + 1) * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(S.uoff.p, tab->uoff.data(), (nblk + 1) * 8, cudaMemcpyHostToDevice, st));
+      if (!resident) {
+        StageSlot &slot = ctx.slots[i % n_slots];
+        CU(cudaEventRecord(slot.ev_h2d, st));
+        slot.h2d_pending = true;
+      }
+      CU(cudaMemsetAsync(S.work, 0, 4, st));
+      CU(cudaEventRecord(E.e[1], st));
+      InflateArgs ia{};
+      ia.comp = d_comp;
+      ia.blk_coff = S.coff.as<uint64_t>();
+      ia.blk_uoff = S.uoff.as<uint64_t>();
+      ia.out = S.infl.as<uint8_t>() + ctx.carry_cap;
+      ia.status = nullptr;
+      ia.error_flag = im.d_err.as<int32_t>();
+      ia.work_counter = S.work;
+      ia.crc = ctx.d_crc;
+      ia.n_blocks = (uint32_t)nblk;
+      ia.verify_crc = verify_crc;
+      CU(launch_inflate(ia, ctx.sm_count, st));
+      CU(cudaEventRecord(E.e[2], st));
+      if (i == 0) {
+        SegState s0;
+        memset(&s0, 0, sizeof s0);
+        s0.entry_off = ctx.carry_cap + range.entry_uoff;
+        CU(cudaMemcpyAsync(S.st, &s0, sizeof s0, cudaMemcpyHostToDevice, st));
+      } else {
+        SegSet &P = ctx.sets[(i - 1) % NSET];
+        CU(cudaStreamWaitEvent(st, P.ev_idx, 0));
+        CU(launch_carry_copy(P.infl.as<uint8_t>(), S.infl.as<uint8_t>(), P.st, S.st, ctx.carry_cap, st));
+        CU(cudaEventRecord(P.ev_carry, st));
+        P.carry_pending = true;
+      }
+      RecArgs ra{};
+      ra.buf = S.infl.as<uint8_t>();
+      ra.tile0 = 0;
+      ra.data_end = data_end;
+      ra.n_tiles = n_tiles;
+      ra.n_ref = (int32_t)hdr_.names.size();
+      ra.tile_entry = S.t_entry.as<uint64_t>();
+      ra.tile_exit = S.t_exit.as<uint64_t>();
+      ra.tile_count = S.t_count.as<uint32_t>();
+      ra.tile_base = S.t_base.as<uint64_t>();
+      ra.tile_slots = S.t_slots.as<uint16_t>();
+      ra.rec_off = S.rec_off.as<uint64_t>();
+      ra.st = S.st;
+      ra.carry_cap = ctx.carry_cap;
+      CU(launch_record_index(ra, st));
+      CU(cudaEventRecord(S.ev_idx, st));
+      CU(cudaEventRecord(E.e[3], st));
+      PileArgs pa{};
+      pa.buf = S.infl.as<uint8_t>();
+      pa.rec_off = S.rec_off.as<uint64_t>();
+      pa.st = S.st;
+      pa.diff = im.d_diff.as<int32_t>();
+      pa.stats = im.d_stats.as<unsigned long long>();
+      pa.range_probe = im.d_probe.as<unsigned long long>();
+      pa.f = im.fdev;
+      pa.p = im.pdev;
+      pa.g = im.gdev;
+      pa.use_window = use_window;
+      CU(launch_pileup(pa, ctx.sm_count, st));
+      CU(cudaEventRecord(E.e[4], st));
+      shape_.comp_bytes += clen;
+      shape_.inflated_bytes += ulen;
+      shape_.blocks += nblk;
+      // refill the staging ring
+      if (!resident && i + n_slots < segs.size()) submit(i + n_slots);
+    }
+    for (auto &s : ctx.sets) CU(cudaStreamSynchronize(s.stream));
+    // a bounded range ends where the index says it should; keep going while the last record seen is still inside it
+    if (!range.bounded || segs.empty() || segs.back().end >= file_size_) break;
+    CU(cudaMemcpy(probe_host, im.d_probe.p, 16, cudaMemcpyDeviceToHost));
+    const unsigned long long end_key = ((unsigned long long)(uint32_t)(range.end_ref + 1) << 32) | (uint32_t)range.end_pos;
+    if (probe_host[0] > end_key) break;
+    if (resident) fail("the staged byte range ends before the shard's last record; use accumulate()");
+    uint64_t cur = segs.back().end;
+    segs.push_back(Segment{cur, next_cut(cur, file_size_)});
+    submit(segs.size() - 1);
+  }
+  pool.reset();
+
+  // ---- collect: errors, counters, timings ----
+  int32_t err[4] = {0, 0, 0, 0};
+  CU(cudaMemcpy(err, im.d_err.p, 16, cudaMemcpyDeviceToHost));
+  if (err[0] != 0)
+    fail("BGZF inflate failed on the device (status " + std::to_string(err[0] & 0xff) + ", block " + std::to_string((unsigned)err[0] >> 8) + " of its segment)");
+  if (!segs.empty()) {
+    SegState last;
+    CU(cudaMemcpy(&last, ctx.sets[(segs.size() - 1) % NSET].st, sizeof last, cudaMemcpyDeviceToHost));
+    if (last.error == SEG_ERR_BAD_RECORD) fail("invalid BAM record (block_size < 32)");
+    if (last.error == SEG_ERR_CARRY_TOO_LARGE) fail("a BAM record larger than BND_CARRY_BYTES straddles two segments");
+    shape_.records = last.total_records;
+    if (!range.bounded && last.carry_len != 0) fail("truncated BAM record at end of file");
+  }
+  unsigned long long st[ST_N_COUNTERS];
+  CU(cudaMemcpy(st, im.d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < ST_N_COUNTERS; k++) stats_[k] = st[k];
+  for (auto &E : evs) {
+    float ms;
+    CU(cudaEventElapsedTime(&ms, E.e[0], E.e[1]));
+    tm_.h2d_ms += ms;
+    CU(cudaEventElapsedTime(&ms, E.e[1], E.e[2]));
+    tm_.inflate_ms += ms;
+    CU(cudaEventElapsedTime(&ms, E.e[2], E.e[3]));
+    tm_.index_ms += ms;
+    CU(cudaEventElapsedTime(&ms, E.e[3], E.e[4]));
+    tm_.pileup_ms += ms;
+    for (int k = 0; k < 5; k++) cudaEventDestroy(E.e[k]);
+  }
+  tm_.wall_ms = now_ms() - t_wall0;
+  shape_.launches = launch_count() - launches0;
+  accumulated_ = true;
+}
+
+void Pileup::accumulate() { run_pass(shard_, false); }
+
+void Pileup::stage() {
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  im.res_segs.clear();
+  im.res_tabs.clear();
+  Range r = shard_;
+  if (r.bounded && r.byte_end < file_size_) {  // margin for records of the last chunk that sit past the planned end
+    const std::vector<uint64_t> &cps = im.cut_points;
+    auto it = std::upper_bound(cps.begin(), cps.end(), r.byte_end + ctx.seg_bytes);
+    r.byte_end = it == cps.end() ? file_size_ : *it;
+  }
+  const uint64_t total = r.byte_end - r.byte_begin;
+  im.d_resident.ensure(total + 64);
+  if (total == 0) return;
+  // one pass over the file through a pinned bounce buffer; segment tables are kept on the host
+  const std::vector<uint64_t> &cp = im.cut_points;
+  std::vector<uint8_t> tmp;
+  for (uint64_t cur = r.byte_begin; cur < r.byte_end;) {
+    uint64_t target = cur + ctx.seg_bytes, nx = r.byte_end;
+    if (target < r.byte_end) {
+      auto it = std::upper_bound(cp.begin(), cp.end(), target);
+      if (it != cp.begin() && *(it - 1) > cur) nx = std::min(*(it - 1), r.byte_end);
+      else if (it != cp.end()) nx = std::min(*it, r.byte_end);
+    }
+    const uint64_t len = nx - cur;
+    tmp.resize(len);
+    uint64_t got = 0;
+    while (got < len) {
+      ssize_t k = pread(im.fd, tmp.data() + got, len - got, (off_t)(cur + got));
+      if (k <= 0) fail("read error on " + bam_path_);
+      got += (uint64_t)k;
+    }
+    BlockTable tab;
+    scan_bgzf_blocks(tmp.data(), len, tab);
+    if (tab.coff.back() != len) fail("BAM segment does not end on a BGZF block boundary (corrupt file or index)");
+    CU(cudaMemcpy(im.d_resident.as<uint8_t>() + (cur - r.byte_begin), tmp.data(), len, cudaMemcpyHostToDevice));
+    im.res_segs.push_back(Segment{cur, nx});
+    im.res_tabs.push_back(std::move(tab));
+    cur = nx;
+  }
+}
+
+void Pileup::accumulate_resident() {
+  if (im_->res_segs.empty() && shard_.byte_end > shard_.byte_begin) fail("accumulate_resident called before stage", ERR_INVALID);
+  run_pass(shard_, true);
+}
+
+void Pileup::set_total_stats(const uint64_t s[ST_N_COUNTERS]) {
+  for (int k = 0; k < ST_N_COUNTERS; k++) stats_[k] = s[k];
+  total_stats_set_ = true;
+}
+
+void Pileup::stats(uint64_t out[ST_N_COUNTERS]) const {
+  for (int k = 0; k < ST_N_COUNTERS; k++) out[k] = stats_[k];
+}
+
+double Pileup::norm_factor() const {
+  // NormalizationMethod::scale_factor (signal_normalization.rs:50-74) over n_reads_after_filtering (read_filter.rs:229-243)
+  uint64_t failed = 0;
+  for (int k = 1; k < ST_N_COUNTERS; k++) failed += stats_[k];
+  return bnd_scale_factor(cfg_.norm_method, cfg_.scale_factor, cfg_.bin_size, stats_[0] - failed);
+}
+
+// ---- K5: scan + collapse ------------------------------------------------------------------------------------------------
+uint64_t Pileup::finalize_range(bool dense_counts) {
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  cudaStream_t st = ctx.sets[0].stream;
+  const GeomDev &g = im.gdev;
+  const uint64_t nb = g.bin_hi - g.bin_lo;
+  const uint64_t n_tiles64 = (nb + FIN_TILE - 1) / FIN_TILE;
+  if (n_tiles64 > 0xffffffffull) fail("too many bins for one shard");
+  const uint32_t n_tiles = (uint32_t)n_tiles64;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  im.d_tile_sum.ensure((size_t)n_tiles * 4 + 16);
+  im.d_tile_heads.ensure((size_t)n_tiles * 8 + 16);
+  im.d_fs.ensure(sizeof(FinState));
+  CU(cudaMemsetAsync(im.d_fs.p, 0, sizeof(FinState), st));
+  FinArgs a{};
+  a.diff = im.d_diff.as<int32_t>();
+  a.n_bins = nb;
+  a.g = g;
+  a.collapse = cfg_.collapse != 0;
+  a.tile_sum = im.d_tile_sum.as<int32_t>();
+  a.tile_heads = im.d_tile_heads.as<uint64_t>();
+  a.n_tiles = n_tiles;
+  a.fs = im.d_fs.as<FinState>();
+  CU(cudaEventRecord(e0, st));
+  CU(launch_bins_reduce(a, ctx.sm_count, st));
+  CU(launch_tile_scan(a, st));
+  FinState fs;
+  CU(cudaMemcpyAsync(&fs, im.d_fs.p, sizeof fs, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  im.n_runs = fs.n_runs;
+  im.d_run_bin.ensure((size_t)im.n_runs * 8 + 16);
+  im.d_run_val.ensure((size_t)im.n_runs * 4 + 16);
+  a.run_bin = im.d_run_bin.as<uint64_t>();
+  a.run_val = im.d_run_val.as<uint32_t>();
+  if (dense_counts) {
+    im.d_counts.ensure((size_t)nb * 4 + 16);
+    a.counts = im.d_counts.as<uint32_t>();
+  }
+  CU(launch_bins_emit(a, ctx.sm_count, st));
+  CU(cudaMemcpyAsync(&fs, im.d_fs.p, sizeof fs, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(e1, st));
+  CU(cudaStreamSynchronize(st));
+  im.max_val = fs.max_val;
+  im.fin_bins = nb;
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  tm_.finalize_ms = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  finalized_ = true;
+  return im.n_runs;
+}
+
+uint64_t Pileup::finalize() {
+  if (!accumulated_) fail("finalize called before accumulate", ERR_INVALID);
+  return finalize_range(false);
+}
+
+void Pileup::ensure_finalized() {
+  if (!accumulated_) accumulate();
+  if (!finalized_) finalize_range(false);
+}
+
+void Pileup::fetch_rows(std::vector<RunRow> &out) {
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  out.resize(im.n_runs);
+  if (im.n_runs == 0) return;
+  DevBuf rows;
+  rows.ensure(im.n_runs * sizeof(RunRow));
+  RunArgs a{};
+  a.run_bin = im.d_run_bin.as<uint64_t>();
+  a.run_val = im.d_run_val.as<uint32_t>();
+  a.n_runs = im.n_runs;
+  a.g = im.gdev;
+  a.rows = rows.as<RunRow>();
+  cudaStream_t st = ctx.sets[0].stream;
+  try {
+    CU(launch_expand_runs(a, ctx.sm_count, st));
+    CU(cudaMemcpyAsync(out.data(), rows.p, im.n_runs * sizeof(RunRow), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  } catch (...) {
+    rows.release();
+    throw;
+  }
+  rows.release();
+}
+
+void Pileup::runs(std::vector<RunRow> &out) {
+  ensure_finalized();
+  fetch_rows(out);
+}
+
+void Pileup::chromosome(const std::string &chrom, std::vector<RunRow> &out) {
+  auto it = hdr_.name_to_id.find(chrom);
+  if (it == hdr_.name_to_id.end() || !geo_.in_stats[it->second]) fail("Chromosome " + chrom + " not found", ERR_NOT_FOUND);
+  const int r = it->second;
+  Range range = range_for_chunks(geo_.ref_first_chunk[r], geo_.ref_first_chunk[r + 1]);
+  run_pass(range, false);
+  finalize_range(false);
+  fetch_rows(out);
+}
+
+void Pileup::signal(const std::string &chrom, std::vector<float> &out) {
+  auto it = hdr_.name_to_id.find(chrom);
+  if (it == hdr_.name_to_id.end()) fail("Chromosome " + chrom + " not found in BAM file.", ERR_NOT_FOUND);
+  const int r = it->second;
+  if (!geo_.in_stats[r]) fail("Chromosome " + chrom + " not found");
+  Impl &im = *im_;
+  // the Python entry point passes no shift / truncate and always piles up raw counts (lib.rs:275-287)
+  PileDev saved = im.pdev;
+  im.pdev.shift_on = 0;
+  im.pdev.has_trunc = 0;
+  Range range = range_for_chunks(geo_.ref_first_chunk[r], geo_.ref_first_chunk[r + 1]);
+  try {
+    run_pass(range, false);
+  } catch (...) {
+    im.pdev = saved;
+    throw;
+  }
+  im.pdev = saved;
+  finalize_range(true);
+  DeviceCtx &ctx = *im.ctx;
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  const uint64_t n = hdr_.lens[r];
+  out.assign(n, 0.f);
+  if (n == 0) return;
+  DevBuf d_out;
+  d_out.ensure(n * 4);
+  SignalArgs a{};
+  a.counts = im.d_counts.as<uint32_t>();
+  a.g = im.gdev;
+  a.ref = r;
+  a.chrom_size = n;
+  a.scale = cfg_.scale_factor;
+  a.out = d_out.as<float>();
+  cudaStream_t st = ctx.sets[0].stream;
+  try {
+    CU(launch_dense_signal(a, ctx.sm_count, st));
+    CU(cudaMemcpyAsync(out.data(), d_out.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  } catch (...) {
+    d_out.release();
+    throw;
+  }
+  d_out.release();
+}
+
+// ---- bedGraph text ------------------------------------------------------------------------------------------------------
+void Pileup::bedgraph_text(std::string &out) {
+  ensure_finalized();
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  out.clear();
+  const size_t n_ref = hdr_.names.size();
+  if (im.n_runs == 0) return;
+  const double t0 = now_ms();
+  // score text per distinct raw count: (count as f64) * factor, printed like a polars Float64 column
+  const double factor = norm_factor();
+  const uint64_t n_scores = (uint64_t)im.max_val + 1;
+  if (n_scores > (1ull << 26)) fail("bin counts too large for the score table");
+  std::vector<char> score_text(n_scores * SCORE_W, 0);
+  {
+    const int nt = (int)std::max<uint64_t>(1, std::min<uint64_t>(std::thread::hardware_concurrency(), n_scores / 4096 + 1));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+      th.emplace_back([&, t] {
+        for (uint64_t v = (uint64_t)t; v < n_scores; v += (uint64_t)nt) {
+          std::string s = format_f64((double)(uint32_t)v * factor);
+          if (s.size() > SCORE_W - 1) s.resize(SCORE_W - 1);
+          score_text[v * SCORE_W] = (char)s.size();
+          memcpy(&score_text[v * SCORE_W + 1], s.data(), s.size());
+        }
+      });
+    for (auto &t : th) t.join();
+  }
+  std::string names;
+  std::vector<uint32_t> name_off(n_ref + 1, 0);
+  std::vector<uint8_t> skip(n_ref, 0);
+  size_t max_name = 0;
+  for (size_t r = 0; r < n_ref; r++) {
+    names += hdr_.names[r];
+    name_off[r + 1] = (uint32_t)names.size();
+    max_name = std::max(max_name, hdr_.names[r].size());
+    skip[r] = cfg_.ignore_scaffold && is_scaffold(hdr_.names[r]);
+  }
+  if (max_name > 60000) fail("reference name too long");
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  cudaStream_t st = ctx.sets[0].stream;
+  DevBuf d_names, d_name_off, d_skip, d_scores, d_row_len, d_tile_off, d_text, d_ref_off;
+  auto release_all = [&] {
+    for (DevBuf *b : {&d_names, &d_name_off, &d_skip, &d_scores, &d_row_len, &d_tile_off, &d_text, &d_ref_off}) b->release();
+  };
+  try {
+    upload(d_names, names.data(), names.size());
+    upload(d_name_off, name_off.data(), name_off.size());
+    upload(d_skip, skip.data(), skip.size());
+    upload(d_scores, score_text.data(), score_text.size());
+    const uint64_t n_tiles64 = (im.n_runs + TEXT_THREADS - 1) / TEXT_THREADS;
+    if (n_tiles64 > 0xffffffffull) fail("too many rows for one shard");
+    d_row_len.ensure(im.n_runs * 2 + 16);
+    d_tile_off.ensure(n_tiles64 * 8 + 16);
+    d_ref_off.ensure((n_ref + 1) * 8);
+    CU(cudaMemsetAsync(d_ref_off.p, 0xff, (n_ref + 1) * 8, st));
+    TextArgs a{};
+    a.run_bin = im.d_run_bin.as<uint64_t>();
+    a.run_val = im.d_run_val.as<uint32_t>();
+    a.n_runs = im.n_runs;
+    a.g = im.gdev;
+    a.names = d_names.as<char>();
+    a.name_off = d_name_off.as<uint32_t>();
+    a.ref_skip = d_skip.as<uint8_t>();
+    a.score_text = d_scores.as<char>();
+    a.n_scores = (uint32_t)n_scores;
+    a.row_len = d_row_len.as<uint16_t>();
+    a.tile_off = d_tile_off.as<uint64_t>();
+    a.n_tiles = (uint32_t)n_tiles64;
+    a.fs = im.d_fs.as<FinState>();
+    a.ref_text_off = d_ref_off.as<uint64_t>();
+    CU(launch_text_len(a, ctx.sm_count, st));
+    CU(launch_text_scan(a, st));
+    FinState fs;
+    CU(cudaMemcpyAsync(&fs, im.d_fs.p, sizeof fs, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t nbytes = fs.text_bytes;
+    d_text.ensure(nbytes + 16);
+    a.text = d_text.as<char>();
+    CU(launch_text_write(a, ctx.sm_count, st));
+    std::string raw(nbytes, '\0');
+    std::vector<uint64_t> ref_off(n_ref + 1);
+    if (nbytes) CU(cudaMemcpyAsync(&raw[0], d_text.p, nbytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ref_off.data(), d_ref_off.p, (n_ref + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // device text is in header order; write_bedgraph sorts by (chrom as a byte string, start)
+    std::vector<std::pair<uint64_t, uint64_t>> piece(n_ref, {0, 0});  // [begin, end) per reference
+    uint64_t next = nbytes;
+    for (size_t r = n_ref; r-- > 0;) {
+      if (ref_off[r] != ~0ull) {
+        piece[r] = {ref_off[r], next};
+        next = ref_off[r];
+      }
+    }
+    std::vector<int> order(n_ref);
+    for (size_t r = 0; r < n_ref; r++) order[r] = (int)r;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return hdr_.names[x] < hdr_.names[y]; });
+    bool identity = true;
+    uint64_t pos = 0;
+    for (int r : order) {
+      if (piece[r].second > piece[r].first) {
+        if (piece[r].first != pos) identity = false;
+        pos = piece[r].second;
+      }
+    }
+    if (identity) {
+      out.swap(raw);
+    } else {
+      out.reserve(nbytes);
+      for (int r : order) out.append(raw, piece[r].first, piece[r].second - piece[r].first);
+    }
+  } catch (...) {
+    release_all();
+    throw;
+  }
+  release_all();
+  tm_.text_ms = now_ms() - t0;
+}
+
+void Pileup::to_bedgraph(const std::string &path) {
+  if (!accumulated_) accumulate();
+  if (!finalized_) finalize_range(false);
+  std::string text;
+  bedgraph_text(text);
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) fail("cannot create " + path);
+  size_t w = text.empty() ? 0 : fwrite(text.data(), 1, text.size(), f);
+  int rc = fclose(f);
+  if (w != text.size() || rc != 0) fail("write error on " + path);
+}
+
+}  // namespace bnd

@@ -1,0 +1,95 @@
+// engine.h — host engine of the B200 coverage path: streams compressed BAM bytes through pinned buffers into the
+// kernels of kernels.cu and keeps the per-bin difference array, counters and compacted runs resident in HBM.
+//
+// It stands where BamPileup stands in the reference (bamnado/src/coverage_analysis.rs:136-760); the C ABI in
+// capi.cpp is a thin shell over this class.
+#pragma once
+#include <stdint.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/bamnado_b200.h"
+#include "bamio.h"
+#include "filter_host.h"
+#include "kernel_args.h"
+
+namespace bnd {
+
+struct DeviceCtx;  // per-process, per-device pools (streams, pinned staging ring, segment buffers)
+
+struct Timings {
+  double inflate_ms = 0, index_ms = 0, pileup_ms = 0, finalize_ms = 0, h2d_ms = 0, text_ms = 0, wall_ms = 0, read_ms = 0;
+};
+struct Shape {
+  uint64_t records = 0, comp_bytes = 0, inflated_bytes = 0, blocks = 0, bins = 0, launches = 0, chunk_len = 0, n_chunks = 0;
+};
+
+class Pileup {
+ public:
+  Pileup(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter);
+  ~Pileup();
+  Pileup(const Pileup &) = delete;
+
+  // --- whole-object operations (mirror BamPileup) ---
+  void to_bedgraph(const std::string &path);
+  void runs(std::vector<RunRow> &out);                      // all rows of this shard, (ref_id, start) order
+  void chromosome(const std::string &chrom, std::vector<RunRow> &out);
+  void signal(const std::string &chrom, std::vector<float> &out);
+  double norm_factor() const;
+  void stats(uint64_t out[ST_N_COUNTERS]) const;
+
+  // --- staged operations ---
+  void accumulate();            // host file -> pinned -> device, hot path
+  void stage();                 // copy the shard's compressed bytes into HBM
+  void accumulate_resident();   // hot path over the staged bytes
+  void set_total_stats(const uint64_t s[ST_N_COUNTERS]);
+  uint64_t finalize();          // scan + collapse; returns the number of rows
+  void bedgraph_text(std::string &out);
+  const Timings &timings() const { return tm_; }
+  const Shape &shape() const { return shape_; }
+
+  const BamHeader &header() const { return hdr_; }
+  const Geometry &geometry() const { return geo_; }
+
+ private:
+  struct Range {  // what part of the file / genome a pass covers
+    uint64_t chunk_lo = 0, chunk_hi = 0;
+    uint64_t byte_begin = 0, byte_end = 0;  // file offsets of BGZF block starts
+    uint64_t entry_uoff = 0;                // offset of the first record inside the first block
+    bool bounded = false;                   // stop once records pass (end_ref, end_pos)
+    int end_ref = 0;
+    uint64_t end_pos = 0;
+  };
+  struct Impl;
+  std::unique_ptr<Impl> im_;
+
+  void open();
+  Range range_for_chunks(uint64_t chunk_lo, uint64_t chunk_hi) const;
+  void run_pass(const Range &r, bool resident);
+  void reset_accumulators(const Range &r);
+  uint64_t finalize_range(bool dense_counts);
+  void fetch_rows(std::vector<RunRow> &out);
+  void ensure_finalized();
+
+  bnd_pileup_cfg cfg_;
+  std::string bam_path_;
+  FilterHost filt_;
+  BamHeader hdr_;
+  Bai bai_;
+  Geometry geo_;
+  uint64_t file_size_ = 0;
+  Range shard_;
+  bool accumulated_ = false, finalized_ = false, total_stats_set_ = false;
+  uint64_t stats_[ST_N_COUNTERS] = {0};
+  Timings tm_;
+  Shape shape_;
+};
+
+// K1 exposed on its own (bnd_bgzf_inflate): inflate BGZF blocks held in host memory on the device.
+void device_inflate(const uint8_t *bgzf, uint64_t n_bytes, std::vector<uint8_t> &out, std::vector<int32_t> &status, int device);
+
+int device_count();
+
+}  // namespace bnd

@@ -1,0 +1,222 @@
+// kernel_args.h — plain-data argument blocks shared by the CUDA kernels (kernels.cu) and the C++ host engine.
+// No device code here, so host translation units can include it without nvcc.
+#pragma once
+#include <stdint.h>
+
+namespace bnd {
+
+// status codes written per block
+enum InflateStatus : int32_t {
+  INF_OK = 0,
+  INF_BAD_BTYPE = 1,
+  INF_BAD_STORED = 2,
+  INF_BAD_CODELEN = 3,
+  INF_BAD_SYMBOL = 4,
+  INF_BAD_DISTANCE = 5,
+  INF_OUTPUT_OVERRUN = 6,
+  INF_INPUT_OVERRUN = 7,
+  INF_SIZE_MISMATCH = 8,
+  INF_CRC_MISMATCH = 9,
+  INF_BAD_HEADER = 10,
+};
+
+struct CrcTables {
+  uint32_t t[256];        // byte table of the reflected CRC-32 (poly 0xEDB88320)
+  uint32_t z[4][256];     // "advance by 32*G zero bits" operator, sliced by byte
+};
+
+struct InflateArgs {
+  const uint8_t *comp;        // compressed bytes of the segment (padded by >= 16 readable bytes)
+  const uint64_t *blk_coff;   // [n+1] offset of each BGZF block (gzip header) within comp
+  const uint64_t *blk_uoff;   // [n+1] offset of each block's output within out
+  uint8_t *out;               // inflated bytes
+  int32_t *status;            // [n] per-block status, or nullptr
+  int32_t *error_flag;        // sticky: first non-zero status (atomicCAS)
+  uint32_t *work_counter;     // dynamic block scheduler (zeroed before launch)
+  const CrcTables *crc;       // device-resident tables for this G
+  uint32_t n_blocks;
+  int verify_crc;
+};
+
+constexpr uint32_t REC_TILE = 8192;    // bytes of inflated stream per tile
+constexpr uint32_t REC_SLOTS = 232;    // >= ceil(REC_TILE / 36): a record is at least 4 + 32 bytes
+constexpr uint64_t REC_NONE = ~0ull;   // "no / invalid offset"
+constexpr uint32_t REC_MAX_SIZE = 1u << 28;
+
+enum SegError : int32_t {
+  SEG_OK = 0,
+  SEG_ERR_BAD_RECORD = 1,      // block_size < 32 on the true chain
+  SEG_ERR_CARRY_TOO_LARGE = 2, // a record larger than the carry area straddles two segments
+};
+
+// Device-resident state chained from segment to segment of one pipeline.
+struct SegState {
+  uint64_t entry_off;      // buffer offset of the first record of this segment
+  uint64_t next_entry_off; // where the next segment's first record starts in *its* buffer (carry_cap - carry_len)
+  uint64_t n_records;      // records fully contained in the segment just indexed
+  uint64_t carry_len;      // bytes of the trailing incomplete record of the segment just indexed
+  uint64_t carry_src;      // buffer offset of those bytes
+  uint64_t total_records;  // running total over all segments
+  uint64_t last_ref_pos;   // (ref_id + 1) << 32 | (pos + 1) of the last complete record seen (range termination)
+  int32_t error;           // sticky SegError
+  uint32_t fix_rounds;     // diagnostics: fixed-point rounds and re-walked tiles
+  uint32_t rewalked;
+  uint32_t pad;
+};
+
+struct RecArgs {
+  const uint8_t *buf;      // segment buffer: [carry area][inflated bytes]
+  uint64_t tile0;          // buffer offset of tile 0 (tiles cover [tile0, data_end))
+  uint64_t data_end;       // buffer offset one past the last inflated byte
+  uint32_t n_tiles;
+  int32_t n_ref;
+  uint64_t *tile_entry;    // [n_tiles]
+  uint64_t *tile_exit;     // [n_tiles]
+  uint32_t *tile_count;    // [n_tiles]
+  uint64_t *tile_base;     // [n_tiles] first record index of the tile (after the scan)
+  uint16_t *tile_slots;    // [n_tiles][REC_SLOTS]
+  uint64_t *rec_off;       // [capacity] buffer offsets of the records, in stream order
+  SegState *st;
+  uint64_t carry_cap;      // size of the carry area of the *next* buffer
+};
+
+enum {
+  ST_N_TOTAL = 0, ST_FAIL_PROPER_PAIR, ST_FAIL_MAPQ, ST_FAIL_LENGTH, ST_FAIL_BLACKLIST, ST_FAIL_BARCODE,
+  ST_FAIL_READ_GROUP, ST_FAIL_STRAND, ST_FAIL_TAG, ST_FAIL_FRAGMENT_LENGTH, ST_FAIL_DUPLICATE, ST_FAIL_SECONDARY,
+  ST_FAIL_SUPPLEMENTARY, ST_N_COUNTERS
+};
+
+struct FilterDev {
+  int32_t strand;  // 0 both, 1 forward, 2 reverse
+  int32_t proper_pair;
+  uint32_t min_mapq, min_length, max_length;
+  int32_t has_min_frag, has_max_frag;
+  uint32_t min_frag, max_frag;
+  int32_t ex_dup, ex_sec, ex_sup;
+  int32_t has_rg, rg_len;
+  const char *rg;
+  int32_t has_tag;      // both --tag and --tag-value were given
+  int32_t tag_name_ok;  // tag name has exactly two characters
+  char tag0, tag1;
+  int32_t tagv_len;
+  const char *tagv;
+  int32_t has_blacklist;
+  const uint64_t *bl_off;     // [n_ref + 1] slice of bl_starts / bl_stops per reference
+  const uint64_t *bl_starts;  // per reference: interval starts, sorted
+  const uint64_t *bl_stops;   // per reference: interval stops, sorted independently
+  int32_t has_barcodes;
+  uint32_t bc_mask;           // table size - 1 (power of two)
+  const uint32_t *bc_table;   // open addressing: 0 = empty, else barcode index + 1
+  const uint32_t *bc_off;     // [n + 1] offsets into bc_pool
+  const char *bc_pool;
+};
+
+struct PileDev {
+  int32_t use_fragment;
+  int32_t shift_on;
+  int32_t shift[4];
+  int32_t has_trunc, t_has5, t_has3;
+  uint64_t t5, t3;
+};
+
+// Chunk / bin geometry (bamnado/src/bam_utils.rs:384-436 + bin_intervals).  Bins of all chunks of all references
+// are laid out back to back in header order; chunk c of reference r starts at ref_first_bin[r] + c * nbf.
+struct GeomDev {
+  int32_t n_ref;
+  const uint64_t *ref_len;          // [n_ref]
+  const uint64_t *ref_first_bin;    // [n_ref + 1]
+  const uint64_t *ref_first_chunk;  // [n_ref + 1] ordinal of the reference's first chunk (refs without chunks repeat)
+  uint64_t L;                       // chunk length
+  uint64_t bin;                     // bin size
+  uint64_t nbf;                     // bins of a full chunk = ceil((L - 1) / bin)
+  uint64_t chunk_lo, chunk_hi;      // chunk ordinals owned by this shard: [lo, hi)
+  uint64_t bin_lo, bin_hi;          // global bin range of those chunks; the diff array has bin_hi - bin_lo + 1 slots
+};
+
+constexpr int PILE_THREADS = 256;
+constexpr int PILE_RPT = 4;                      // records per thread per tile
+constexpr uint32_t PILE_WIN = 2048;              // bins in the CTA-private window
+constexpr uint32_t PILE_WIN_MARGIN = PILE_WIN / 8;
+
+struct PileArgs {
+  const uint8_t *buf;
+  const uint64_t *rec_off;
+  const SegState *st;            // n_records of this segment
+  int32_t *diff;                 // [bin_hi - bin_lo + 1]
+  unsigned long long *stats;     // [ST_N_COUNTERS]
+  unsigned long long *range_probe;  // [2]: max (ref+1)<<32|(pos+1) seen, records visited
+  FilterDev f;
+  PileDev p;
+  GeomDev g;
+  int use_window;
+};
+
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_IPT = 16;  // bins per thread
+constexpr uint32_t FIN_TILE = FIN_THREADS * FIN_IPT;
+
+struct FinState {
+  unsigned long long n_runs;
+  unsigned int max_val;
+  unsigned int pad;
+  unsigned long long text_bytes;
+};
+
+struct FinArgs {
+  const int32_t *diff;   // [n_bins (+1)]
+  uint64_t n_bins;       // bins of this shard (bin_hi - bin_lo)
+  GeomDev g;
+  int collapse;
+  int32_t *tile_sum;     // [n_tiles] -> exclusive carry after the tile scan
+  uint64_t *tile_heads;  // [n_tiles] -> exclusive run base after the tile scan
+  uint32_t n_tiles;
+  uint64_t *run_bin;     // [n_runs] global bin index of each run head
+  uint32_t *run_val;     // [n_runs] count
+  uint32_t *counts;      // optional dense per-bin counts [n_bins]
+  FinState *fs;
+};
+
+struct RunRow {  // == bnd_run of the C ABI
+  int32_t ref_id;
+  uint32_t val;
+  uint64_t start, stop;
+};
+
+struct RunArgs {
+  const uint64_t *run_bin;
+  const uint32_t *run_val;
+  uint64_t n_runs;
+  GeomDev g;
+  RunRow *rows;
+};
+
+struct SignalArgs {
+  const uint32_t *counts;  // dense per-bin counts of the shard
+  GeomDev g;
+  int32_t ref;
+  uint64_t chrom_size;
+  float scale;
+  float *out;
+};
+
+struct TextArgs {
+  const uint64_t *run_bin;
+  const uint32_t *run_val;
+  uint64_t n_runs;
+  GeomDev g;
+  const char *names;         // concatenated reference names
+  const uint32_t *name_off;  // [n_ref + 1]
+  const uint8_t *ref_skip;   // [n_ref] 1 = drop rows of this reference (--ignore-scaffold)
+  const char *score_text;    // [n_scores][SCORE_W]: byte 0 = length, then the text
+  uint32_t n_scores;
+  uint16_t *row_len;         // [n_runs]
+  uint64_t *tile_off;        // [n_text_tiles] -> exclusive offsets after the scan
+  uint32_t n_tiles;
+  char *text;
+  FinState *fs;
+  uint64_t *ref_text_off;    // [n_ref + 1] byte offset of each reference's first row
+};
+constexpr int SCORE_W = 32;
+constexpr int TEXT_THREADS = 256;
+
+}  // namespace bnd

@@ -1,0 +1,134 @@
+// kernels.cu — the single device translation unit: all sm_100a kernels of the coverage path and their launchers.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see bamnado_b200/build.py).
+#include "kernels.h"
+
+#include <atomic>
+
+#include "finalize.cuh"
+#include "inflate.cuh"
+#include "pileup.cuh"
+#include "records.cuh"
+
+namespace bnd {
+
+namespace {
+std::atomic<unsigned long long> g_launches{0};
+constexpr int INFLATE_G = 32;        // lanes cooperating on one BGZF block
+constexpr int INFLATE_THREADS = 128; // 4 blocks in flight per CTA
+constexpr int INFLATE_CTAS_PER_SM = 6;
+inline cudaError_t launched() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+inline unsigned grid_for(uint64_t items, uint64_t per_cta, uint64_t cap) {
+  uint64_t n = (items + per_cta - 1) / per_cta;
+  if (n < 1) n = 1;
+  if (n > cap) n = cap;
+  return (unsigned)n;
+}
+}  // namespace
+
+unsigned long long launch_count() { return g_launches.load(); }
+int inflate_ctas_per_sm() { return INFLATE_CTAS_PER_SM; }
+
+void make_crc_tables(CrcTables *T) {
+  for (uint32_t i = 0; i < 256; i++) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+    T->t[i] = c;
+  }
+  // z[b][x]: the CRC register value (x << 8b) advanced over 32*G zero bits (= 4*G zero bytes)
+  for (int b = 0; b < 4; b++)
+    for (uint32_t x = 0; x < 256; x++) {
+      uint32_t c = x << (8 * b);
+      for (int k = 0; k < 4 * INFLATE_G; k++) c = T->t[c & 0xff] ^ (c >> 8);
+      T->z[b][x] = c;
+    }
+}
+
+cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_blocks == 0) return cudaSuccess;
+  auto kern = bgzf_inflate_kernel<INFLATE_G, INFLATE_THREADS>;
+  constexpr int groups = INFLATE_THREADS / INFLATE_G;
+  const size_t smem = inflate_smem_bytes(groups);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  unsigned grid = grid_for(a.n_blocks, groups, (uint64_t)sm_count * INFLATE_CTAS_PER_SM);
+  BND_LAUNCH(kern, dim3(grid), dim3(INFLATE_THREADS), smem, s, a);
+  return launched();
+}
+
+cudaError_t launch_record_index(const RecArgs &a, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  constexpr int T = 256;
+  auto k1 = rec_guess_walk_kernel<T>;
+  auto k2 = rec_fix_scan_kernel<1024>;
+  auto k3 = rec_compact_kernel<T>;
+  unsigned grid = (unsigned)(((uint64_t)a.n_tiles * 32 + T - 1) / T);
+  BND_LAUNCH(k1, dim3(grid), dim3(T), 0, s, a);
+  cudaError_t e = launched();
+  if (e != cudaSuccess) return e;
+  BND_LAUNCH(k2, dim3(1), dim3(1024), 0, s, a);
+  e = launched();
+  if (e != cudaSuccess) return e;
+  BND_LAUNCH(k3, dim3(grid), dim3(T), 0, s, a);
+  return launched();
+}
+
+cudaError_t launch_carry_copy(const uint8_t *src_buf, uint8_t *dst_buf, const SegState *prev, SegState *cur,
+                              uint64_t carry_cap, cudaStream_t s) {
+  BND_LAUNCH(carry_copy_kernel, dim3(8), dim3(256), 0, s, src_buf, dst_buf, prev, cur, carry_cap);
+  return launched();
+}
+
+cudaError_t launch_pileup(const PileArgs &a, int sm_count, cudaStream_t s) {
+  BND_LAUNCH(pileup_kernel, dim3((unsigned)(sm_count * 8)), dim3(PILE_THREADS), 0, s, a);
+  return launched();
+}
+
+cudaError_t launch_bins_reduce(const FinArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bins_reduce_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(FIN_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_tile_scan(const FinArgs &a, cudaStream_t s) {
+  auto k = tile_scan_kernel<1024>;
+  BND_LAUNCH(k, dim3(1), dim3(1024), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bins_emit(const FinArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bins_emit_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(FIN_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_expand_runs(const RunArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_runs == 0) return cudaSuccess;
+  BND_LAUNCH(expand_runs_kernel, dim3(grid_for(a.n_runs, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+cudaError_t launch_dense_signal(const SignalArgs &a, int sm_count, cudaStream_t s) {
+  if (a.chrom_size == 0) return cudaSuccess;
+  BND_LAUNCH(dense_signal_kernel, dim3(grid_for(a.chrom_size, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+cudaError_t launch_text_len(const TextArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(text_len_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(TEXT_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_text_scan(const TextArgs &a, cudaStream_t s) {
+  auto k = text_scan_kernel<1024>;
+  BND_LAUNCH(k, dim3(1), dim3(1024), 0, s, a);
+  return launched();
+}
+cudaError_t launch_text_write(const TextArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(text_write_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(TEXT_THREADS), 0, s, a);
+  return launched();
+}
+
+}  // namespace bnd

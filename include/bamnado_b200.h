@@ -1,0 +1,157 @@
+/*
+ * bamnado_b200.h — C ABI of the B200-native BamNado coverage path.
+ *
+ * This is the drop-in boundary: the thin `extern "C"` surface a Rust `-sys` crate / pyo3
+ * module / CLI binds instead of calling the reference's Rust engine directly.  Plain pointers and sizes only;
+ * no torch, no C++ types.  Every entry point cites the reference interface it replaces (paths are relative to
+ * the reference repository, alsmith151/BamNado v0.9.0).
+ *
+ * All functions returning `int` return 0 on success, non-zero on failure; `bnd_last_error()` then holds a
+ * thread-local message and `bnd_last_error_class()` the class, so a binding can raise the reference's
+ * exception types (RuntimeError / KeyError / ValueError; bamnado-python/src/lib.rs:22-24,109-116,265-270).
+ *
+ * There is no CPU fallback: the library needs a CUDA device (sm_100a build) for every compute call.
+ */
+#ifndef BAMNADO_B200_H
+#define BAMNADO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BND_ABI_VERSION 1
+
+/* error classes */
+enum { BND_OK = 0, BND_ERR_RUNTIME = 1, BND_ERR_NOT_FOUND = 2, BND_ERR_INVALID = 3 };
+
+/* Filter counters, in the order of BamReadFilterStats (bamnado/src/read_filter.rs:31-58). */
+enum {
+  BND_N_TOTAL = 0, BND_FAIL_PROPER_PAIR, BND_FAIL_MAPQ, BND_FAIL_LENGTH, BND_FAIL_BLACKLIST, BND_FAIL_BARCODE,
+  BND_FAIL_READ_GROUP, BND_FAIL_STRAND, BND_FAIL_TAG, BND_FAIL_FRAGMENT_LENGTH, BND_FAIL_DUPLICATE,
+  BND_FAIL_SECONDARY, BND_FAIL_SUPPLEMENTARY, BND_N_COUNTERS
+};
+
+/* BamReadFilter::new + with_exclude_* (bamnado/src/read_filter.rs:438-492) as plain data.  File-based fields
+ * mirror what the CLI / Python layer loads before constructing the filter (src/cli.rs:648-720,
+ * bamnado-python/src/lib.rs:167-219). */
+typedef struct bnd_filter_cfg {
+  int32_t strand;            /* 0 both, 1 forward, 2 reverse (bam_utils.rs:95-133) */
+  int32_t proper_pair;
+  uint32_t min_mapq;
+  uint32_t min_length;
+  uint32_t max_length;
+  int32_t has_min_fragment_length;
+  uint32_t min_fragment_length;
+  int32_t has_max_fragment_length;
+  uint32_t max_fragment_length;
+  int32_t exclude_duplicates, exclude_secondary, exclude_supplementary;
+  const char *read_group;        /* NULL = none */
+  const char *filter_tag;        /* NULL = none */
+  const char *filter_tag_value;  /* NULL = none */
+  const char *blacklist_bed;     /* NULL = none; BED path, >= 4 columns (bam_utils.rs:650-684) */
+  int32_t blacklist_merge_overlaps; /* 1 on the single-BAM CLI path (src/cli.rs:672-678) */
+  const char *barcode_csv;       /* NULL = none; CSV with a header (bam_utils.rs:186-269) */
+  int32_t barcode_csv_column;    /* -1: column named `barcode`; >= 0: that column index (CellBarcodesMulti) */
+  int32_t has_barcode_list;      /* explicit list (Python ReadFilter.whitelisted_barcodes) */
+  uint64_t n_barcodes;
+  const char *const *barcodes;
+} bnd_filter_cfg;
+
+/* BamPileup::new (bamnado/src/coverage_analysis.rs:298-324) as plain data, plus device/shard placement. */
+typedef struct bnd_pileup_cfg {
+  const char *bam_path;
+  uint64_t bin_size;
+  int32_t norm_method;       /* 0 raw, 1 rpkm, 2 cpm (signal_normalization.rs:13-21) */
+  float scale_factor;
+  int32_t use_fragment;
+  int32_t collapse;
+  int32_t ignore_scaffold;
+  int32_t has_shift;  int32_t shift[4];   /* genomic_intervals.rs:50-59 */
+  int32_t has_truncate; int32_t trunc_has5; uint64_t trunc5; int32_t trunc_has3; uint64_t trunc3;
+  int32_t n_threads;         /* BigWig writer threads (coverage_analysis.rs:752-754); <= 0: 6 */
+  int32_t device;            /* CUDA device ordinal; < 0: current device */
+  int32_t shard_rank;        /* this process's shard of the genomic chunks (0 .. shard_world-1) */
+  int32_t shard_world;       /* <= 1: unsharded */
+} bnd_pileup_cfg;
+
+typedef struct bnd_run {     /* one output row: rust_lapper::Interval<usize,u32> + contig (bam_utils.rs:32) */
+  int32_t ref_id;
+  uint32_t val;
+  uint64_t start, stop;      /* 1-based half-open, as the reference keeps them */
+} bnd_run;
+
+typedef struct bnd_pileup bnd_pileup;  /* opaque; single owner, not thread-safe */
+
+const char *bnd_last_error(void);
+int bnd_last_error_class(void);
+void bnd_free(void *p);                /* frees buffers returned through out-pointers */
+int bnd_abi_version(void);
+int bnd_device_count(void);
+
+/* ---- BamPileup (coverage_analysis.rs:136-760) ------------------------------------------------------------ */
+/* BamPileup::new + BamReadFilter::new; opens BAM header + BAI (BamStats::new, bam_utils.rs:311-378). */
+bnd_pileup *bnd_pileup_create(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter);
+void bnd_pileup_destroy(bnd_pileup *p);
+/* to_bedgraph (coverage_analysis.rs:618-632) */
+int bnd_pileup_to_bedgraph(bnd_pileup *p, const char *out_path);
+/* to_bigwig (coverage_analysis.rs:642-759); BigWig encoding runs on the host */
+int bnd_pileup_to_bigwig(bnd_pileup *p, const char *out_path);
+/* pileup_chromosome (coverage_analysis.rs:337-430): runs of one contig; unknown contig -> BND_ERR_NOT_FOUND */
+int bnd_pileup_chromosome(bnd_pileup *p, const char *chrom, bnd_run **runs, uint64_t *n_runs);
+/* pileup_genome / pileup_to_polars rows (coverage_analysis.rs:436-598), sorted by (ref_id, start) */
+int bnd_pileup_runs(bnd_pileup *p, bnd_run **runs, uint64_t *n_runs);
+/* normalization_factor (coverage_analysis.rs:326-333); valid after a pileup ran on this handle */
+int bnd_pileup_norm_factor(bnd_pileup *p, double *factor);
+/* filter.stats() snapshot (read_filter.rs:805-808) */
+int bnd_pileup_stats(bnd_pileup *p, uint64_t stats[BND_N_COUNTERS]);
+
+/* ---- staged interface used for sharded (multi-GPU) runs and device-resident timing ------------------------ */
+/* Stream this shard's BAM bytes host->device and accumulate the per-bin difference array + filter counters. */
+int bnd_pileup_accumulate(bnd_pileup *p);
+/* Copy this shard's compressed BAM bytes into HBM once (not part of any timed hot path). */
+int bnd_pileup_stage(bnd_pileup *p);
+/* Run the hot path (inflate, record index, filter, scatter, scan, collapse) over the staged bytes. */
+int bnd_pileup_accumulate_resident(bnd_pileup *p);
+/* Replace the counters by job-wide totals (after an all-reduce over ranks) before normalising. */
+int bnd_pileup_set_total_stats(bnd_pileup *p, const uint64_t stats[BND_N_COUNTERS]);
+/* Scan + normalise + collapse on device; returns the number of output rows this shard owns. */
+int bnd_pileup_finalize(bnd_pileup *p, uint64_t *n_runs);
+/* bedGraph text of this shard's rows, in final (chrom byte order, start) order (device formats the text). */
+int bnd_pileup_bedgraph_text(bnd_pileup *p, char **text, uint64_t *n_bytes);
+/* per-stage device time of the last accumulate call, ms: [inflate, record index, filter+scatter, finalize, h2d] */
+int bnd_pileup_timings(bnd_pileup *p, double ms[8]);
+/* shape of the last run: [records visited, compressed bytes, inflated bytes, BGZF blocks, bins, kernel launches,
+   chunk length, n chunks] */
+int bnd_pileup_shape(bnd_pileup *p, uint64_t shape[8]);
+
+/* ---- Python front door (bamnado-python/src/lib.rs:248-304) ------------------------------------------------ */
+/* get_signal_for_chromosome: dense float32[chrom_size]; unknown contig -> BND_ERR_NOT_FOUND */
+int bnd_signal_for_chromosome(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter, const char *chrom,
+                              float **signal, uint64_t *n);
+
+/* ---- MultiBamPileup::to_tsv (coverage_analysis.rs:766-865) ------------------------------------------------ */
+int bnd_multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int32_t n_bams, const char *out_path);
+
+/* ---- collapse-bedgraph (src/cli.rs:1149-1205 + bedgraph_utils.rs:5-45) ------------------------------------ */
+int bnd_collapse_bedgraph(const char *in_path, const char *out_path);
+
+/* ---- NormalizationMethod::scale_factor (signal_normalization.rs:50-74) ------------------------------------ */
+double bnd_scale_factor(int32_t method, float base_scale, uint64_t bin_size, uint64_t n_reads);
+
+/* ---- BamStats (bam_utils.rs:311-436): [n_mapped, n_unmapped, genome_len, chunk_len, n_chunks, n_refs] ----- */
+int bnd_bam_stats(const char *bam_path, uint64_t bin_size, uint64_t out[6]);
+
+/* ---- run_cli (src/cli.rs:737-757): same subcommands/flags/exit codes for the coverage path ---------------- */
+int bnd_cli_main(int argc, const char *const *argv);
+
+/* ---- kernel-level entry points (parity tests and micro-benchmarks) ---------------------------------------- */
+/* Inflate `n_blocks` BGZF blocks held in host memory on the device; writes the concatenated output into `out`
+ * (capacity out_cap) and per-block status (0 ok) into `status`.  CRC32 and ISIZE are verified on the device. */
+int bnd_bgzf_inflate(const uint8_t *bgzf, uint64_t n_bytes, uint8_t *out, uint64_t out_cap, uint64_t *out_len,
+                     int32_t *status, uint64_t status_cap, uint64_t *n_blocks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
