@@ -25,7 +25,7 @@ STRAND = {"both": 0, "forward": 1, "reverse": 2}
 ERR_RUNTIME, ERR_NOT_FOUND, ERR_INVALID = 1, 2, 3
 
 EXPORTS = [
-    "bnd_last_error", "bnd_last_error_class", "bnd_free", "bnd_abi_version", "bnd_device_count", "bnd_pileup_create",
+    "bnd_last_error", "bnd_last_error_class", "bnd_free", "bnd_abi_version", "bnd_device_count", "bnd_launch_count", "bnd_pileup_create",
     "bnd_pileup_destroy", "bnd_pileup_to_bedgraph", "bnd_pileup_to_bigwig", "bnd_pileup_chromosome", "bnd_pileup_runs",
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
@@ -131,6 +131,7 @@ class Native:
             raise RuntimeError(f"libbamnado_b200 is missing symbols: {missing}")
         L.bnd_last_error.restype = C.c_char_p
         L.bnd_free.argtypes = [C.c_void_p]
+        L.bnd_launch_count.restype = C.c_uint64
         L.bnd_pileup_create.restype = C.c_void_p
         L.bnd_pileup_create.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg)]
         L.bnd_pileup_destroy.argtypes = [C.c_void_p]
@@ -173,6 +174,9 @@ class Native:
     # ---- plain functions ----------------------------------------------------------------------------------------
     def device_count(self) -> int:
         return self.L.bnd_device_count()
+
+    def launch_count(self) -> int:
+        return int(self.L.bnd_launch_count())
 
     def scale_factor(self, method: str, base_scale: float, bin_size: int, n_reads: int) -> float:
         return self.L.bnd_scale_factor(NORM[method], base_scale, bin_size, n_reads)
@@ -254,7 +258,11 @@ class PileupHandle:
             pass
 
     def _rows(self, ptr, n):
-        arr = np.frombuffer(C.string_at(ptr, n * C.sizeof(Run)), dtype=RUN_DTYPE).copy() if n else np.zeros(0, dtype=RUN_DTYPE)
+        if n:
+            raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * C.sizeof(Run),))
+            arr = raw.view(RUN_DTYPE).copy()
+        else:
+            arr = np.zeros(0, dtype=RUN_DTYPE)
         self.n.L.bnd_free(ptr)
         return arr
 

@@ -6,6 +6,7 @@
 
 #include "../../include/bamnado_b200.h"
 #include "engine.h"
+#include "kernels.h"
 #include "outputs.h"
 
 namespace {
@@ -56,6 +57,7 @@ int bnd_last_error_class(void) { return g_err_class; }
 void bnd_free(void *p) { free(p); }
 int bnd_abi_version(void) { return BND_ABI_VERSION; }
 int bnd_device_count(void) { return bnd::device_count(); }
+uint64_t bnd_launch_count(void) { return bnd::launch_count(); }
 
 bnd_pileup *bnd_pileup_create(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter) {
   bnd::Pileup *p = nullptr;

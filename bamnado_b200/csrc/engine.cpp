@@ -594,6 +594,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
   CU(cudaSetDevice(ctx.device));
   const double t_wall0 = now_ms();
   const unsigned long long launches0 = launch_count();
+  ctx.seg_bytes = std::max<uint64_t>(env_u64("BND_SEGMENT_BYTES", 96ull << 20), 1u << 16);  // re-read per pass (tests shrink it)
   reset_accumulators(range);
   tm_ = Timings();
   shape_.records = shape_.comp_bytes = shape_.inflated_bytes = shape_.blocks = 0;
@@ -645,6 +646,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
   std::vector<SegEvents> evs;
   const bool verify_crc = env_u64("BND_VERIFY_CRC", 1) != 0;
   const int use_window = (int)env_u64("BND_USE_WINDOW", 1);
+  const bool serialize = env_u64("BND_SERIALIZE", 0) != 0;  // one segment at a time: clean per-kernel event timings
   for (auto &s : ctx.sets) s.carry_pending = false;
 
   size_t i = 0;
@@ -767,6 +769,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
       shape_.comp_bytes += clen;
       shape_.inflated_bytes += ulen;
       shape_.blocks += nblk;
+      if (serialize) CU(cudaStreamSynchronize(st));
       // refill the staging ring
       if (!resident && i + n_slots < segs.size()) submit(i + n_slots);
     }
@@ -1039,14 +1042,66 @@ void Pileup::signal(const std::string &chrom, std::vector<float> &out) {
 }
 
 // ---- bedGraph text ------------------------------------------------------------------------------------------------------
-void Pileup::bedgraph_text(std::string &out) {
-  ensure_finalized();
+// The rows are formatted on the device in header order; write_bedgraph's (chrom byte string, start) order is a
+// permutation of whole per-reference pieces, applied while the bytes leave the pinned bounce buffers.
+namespace {
+struct TextPiece {
+  uint64_t dev_begin, dev_end;  // byte range inside the device text
+  uint64_t out_off;             // where it goes in the output
+};
+
+struct PinnedBounce {  // process-wide pinned bounce buffers for device -> host text
+  static constexpr int N = 2;
+  uint8_t *buf[N] = {nullptr, nullptr};
+  size_t cap = 0;
+  cudaEvent_t ev[N] = {nullptr, nullptr};
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    for (int i = 0; i < N; i++) {
+      if (buf[i]) CU(cudaFreeHost(buf[i]));
+      buf[i] = nullptr;
+      CU(cudaHostAlloc((void **)&buf[i], n, cudaHostAllocDefault));
+      if (!ev[i]) CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    cap = n;
+  }
+};
+PinnedBounce g_bounce;
+
+// copies [a, b) of the device text, as seen through `pieces`, to its destinations via `sink(src, len, out_off)`
+template <class Sink>
+void scatter_chunk(const std::vector<TextPiece> &pieces, const uint8_t *src, uint64_t a, uint64_t b, Sink sink) {
+  // pieces are sorted by dev_begin
+  size_t lo = 0, hi = pieces.size();
+  while (lo < hi) {
+    size_t mid = (lo + hi) / 2;
+    if (pieces[mid].dev_end <= a) lo = mid + 1;
+    else hi = mid;
+  }
+  for (size_t k = lo; k < pieces.size() && pieces[k].dev_begin < b; k++) {
+    uint64_t x = std::max(a, pieces[k].dev_begin), y = std::min(b, pieces[k].dev_end);
+    if (y > x) sink(src + (x - a), y - x, pieces[k].out_off + (x - pieces[k].dev_begin));
+  }
+}
+}  // namespace
+
+struct Pileup::TextJob {
+  DevBuf d_names, d_name_off, d_skip, d_scores, d_row_len, d_tile_off, d_text, d_ref_off;
+  uint64_t nbytes = 0;
+  std::vector<TextPiece> pieces;  // sorted by dev_begin
+  ~TextJob() {
+    for (DevBuf *b : {&d_names, &d_name_off, &d_skip, &d_scores, &d_row_len, &d_tile_off, &d_text, &d_ref_off}) b->release();
+  }
+};
+
+// Formats every row on the device; returns the device text and how its per-reference pieces map to the output order.
+void Pileup::format_text(TextJob &job) {
   Impl &im = *im_;
   DeviceCtx &ctx = *im.ctx;
-  out.clear();
   const size_t n_ref = hdr_.names.size();
+  job.nbytes = 0;
+  job.pieces.clear();
   if (im.n_runs == 0) return;
-  const double t0 = now_ms();
   // score text per distinct raw count: (count as f64) * factor, printed like a polars Float64 column
   const double factor = norm_factor();
   const uint64_t n_scores = (uint64_t)im.max_val + 1;
@@ -1077,97 +1132,195 @@ void Pileup::bedgraph_text(std::string &out) {
     skip[r] = cfg_.ignore_scaffold && is_scaffold(hdr_.names[r]);
   }
   if (max_name > 60000) fail("reference name too long");
-  std::lock_guard<std::mutex> lock(ctx.mu);
   CU(cudaSetDevice(ctx.device));
   cudaStream_t st = ctx.sets[0].stream;
-  DevBuf d_names, d_name_off, d_skip, d_scores, d_row_len, d_tile_off, d_text, d_ref_off;
-  auto release_all = [&] {
-    for (DevBuf *b : {&d_names, &d_name_off, &d_skip, &d_scores, &d_row_len, &d_tile_off, &d_text, &d_ref_off}) b->release();
+  upload(job.d_names, names.data(), names.size());
+  upload(job.d_name_off, name_off.data(), name_off.size());
+  upload(job.d_skip, skip.data(), skip.size());
+  upload(job.d_scores, score_text.data(), score_text.size());
+  const uint64_t n_tiles64 = (im.n_runs + TEXT_THREADS - 1) / TEXT_THREADS;
+  if (n_tiles64 > 0xffffffffull) fail("too many rows for one shard");
+  job.d_row_len.ensure(im.n_runs * 2 + 16);
+  job.d_tile_off.ensure(n_tiles64 * 8 + 16);
+  job.d_ref_off.ensure((n_ref + 1) * 8);
+  CU(cudaMemsetAsync(job.d_ref_off.p, 0xff, (n_ref + 1) * 8, st));
+  TextArgs a{};
+  a.run_bin = im.d_run_bin.as<uint64_t>();
+  a.run_val = im.d_run_val.as<uint32_t>();
+  a.n_runs = im.n_runs;
+  a.g = im.gdev;
+  a.names = job.d_names.as<char>();
+  a.name_off = job.d_name_off.as<uint32_t>();
+  a.ref_skip = job.d_skip.as<uint8_t>();
+  a.score_text = job.d_scores.as<char>();
+  a.n_scores = (uint32_t)n_scores;
+  a.row_len = job.d_row_len.as<uint16_t>();
+  a.tile_off = job.d_tile_off.as<uint64_t>();
+  a.n_tiles = (uint32_t)n_tiles64;
+  a.fs = im.d_fs.as<FinState>();
+  a.ref_text_off = job.d_ref_off.as<uint64_t>();
+  CU(launch_text_len(a, ctx.sm_count, st));
+  CU(launch_text_scan(a, st));
+  FinState fs;
+  CU(cudaMemcpyAsync(&fs, im.d_fs.p, sizeof fs, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  job.nbytes = fs.text_bytes;
+  job.d_text.ensure(job.nbytes + 16);
+  a.text = job.d_text.as<char>();
+  CU(launch_text_write(a, ctx.sm_count, st));
+  std::vector<uint64_t> ref_off(n_ref + 1);
+  CU(cudaMemcpyAsync(ref_off.data(), job.d_ref_off.p, (n_ref + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  // device text is in header order; write_bedgraph sorts by (chrom as a byte string, start)
+  std::vector<std::pair<uint64_t, uint64_t>> span(n_ref, {0, 0});
+  uint64_t next = job.nbytes;
+  for (size_t r = n_ref; r-- > 0;)
+    if (ref_off[r] != ~0ull) {
+      span[r] = {ref_off[r], next};
+      next = ref_off[r];
+    }
+  std::vector<int> order(n_ref);
+  for (size_t r = 0; r < n_ref; r++) order[r] = (int)r;
+  std::sort(order.begin(), order.end(), [&](int x, int y) { return hdr_.names[x] < hdr_.names[y]; });
+  uint64_t out_off = 0;
+  for (int r : order)
+    if (span[r].second > span[r].first) {
+      job.pieces.push_back(TextPiece{span[r].first, span[r].second, out_off});
+      out_off += span[r].second - span[r].first;
+    }
+  std::sort(job.pieces.begin(), job.pieces.end(), [](const TextPiece &x, const TextPiece &y) { return x.dev_begin < y.dev_begin; });
+}
+
+// Streams the device text through the pinned bounce buffers; `sink(src, len, out_off)` may be called concurrently.
+template <class Sink>
+static void drain_text(DeviceCtx &ctx, const uint8_t *d_text, uint64_t nbytes, const std::vector<TextPiece> &pieces, int n_threads, Sink sink) {
+  if (nbytes == 0) return;
+  const uint64_t CH = std::min<uint64_t>(env_u64("BND_TEXT_CHUNK_BYTES", 64ull << 20), nbytes);
+  g_bounce.ensure(CH);
+  cudaStream_t st = ctx.sets[0].stream;
+  const uint64_t n_chunks = (nbytes + CH - 1) / CH;
+  // worker pool consuming (chunk, sub-range) tasks
+  struct Task {
+    const uint8_t *src;
+    uint64_t a, b;
+  };
+  std::mutex mu;
+  std::condition_variable cv, cv_done;
+  std::deque<Task> q;
+  int outstanding[PinnedBounce::N] = {0, 0};
+  bool stop = false;
+  std::string err;
+  auto worker = [&] {
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return stop || !q.empty(); });
+        if (q.empty()) return;
+        t = q.front();
+        q.pop_front();
+      }
+      try {
+        scatter_chunk(pieces, t.src, t.a, t.b, sink);
+      } catch (const std::exception &e) {
+        std::lock_guard<std::mutex> g(mu);
+        if (err.empty()) err = e.what();
+      }
+      {
+        std::lock_guard<std::mutex> g(mu);
+        for (int i = 0; i < PinnedBounce::N; i++)
+          if (t.src >= g_bounce.buf[i] && t.src < g_bounce.buf[i] + g_bounce.cap) outstanding[i]--;
+      }
+      cv_done.notify_all();
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 0; i < std::max(1, n_threads); i++) th.emplace_back(worker);
+  auto finish = [&] {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    for (auto &t : th) t.join();
   };
   try {
-    upload(d_names, names.data(), names.size());
-    upload(d_name_off, name_off.data(), name_off.size());
-    upload(d_skip, skip.data(), skip.size());
-    upload(d_scores, score_text.data(), score_text.size());
-    const uint64_t n_tiles64 = (im.n_runs + TEXT_THREADS - 1) / TEXT_THREADS;
-    if (n_tiles64 > 0xffffffffull) fail("too many rows for one shard");
-    d_row_len.ensure(im.n_runs * 2 + 16);
-    d_tile_off.ensure(n_tiles64 * 8 + 16);
-    d_ref_off.ensure((n_ref + 1) * 8);
-    CU(cudaMemsetAsync(d_ref_off.p, 0xff, (n_ref + 1) * 8, st));
-    TextArgs a{};
-    a.run_bin = im.d_run_bin.as<uint64_t>();
-    a.run_val = im.d_run_val.as<uint32_t>();
-    a.n_runs = im.n_runs;
-    a.g = im.gdev;
-    a.names = d_names.as<char>();
-    a.name_off = d_name_off.as<uint32_t>();
-    a.ref_skip = d_skip.as<uint8_t>();
-    a.score_text = d_scores.as<char>();
-    a.n_scores = (uint32_t)n_scores;
-    a.row_len = d_row_len.as<uint16_t>();
-    a.tile_off = d_tile_off.as<uint64_t>();
-    a.n_tiles = (uint32_t)n_tiles64;
-    a.fs = im.d_fs.as<FinState>();
-    a.ref_text_off = d_ref_off.as<uint64_t>();
-    CU(launch_text_len(a, ctx.sm_count, st));
-    CU(launch_text_scan(a, st));
-    FinState fs;
-    CU(cudaMemcpyAsync(&fs, im.d_fs.p, sizeof fs, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const uint64_t nbytes = fs.text_bytes;
-    d_text.ensure(nbytes + 16);
-    a.text = d_text.as<char>();
-    CU(launch_text_write(a, ctx.sm_count, st));
-    std::string raw(nbytes, '\0');
-    std::vector<uint64_t> ref_off(n_ref + 1);
-    if (nbytes) CU(cudaMemcpyAsync(&raw[0], d_text.p, nbytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ref_off.data(), d_ref_off.p, (n_ref + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    // device text is in header order; write_bedgraph sorts by (chrom as a byte string, start)
-    std::vector<std::pair<uint64_t, uint64_t>> piece(n_ref, {0, 0});  // [begin, end) per reference
-    uint64_t next = nbytes;
-    for (size_t r = n_ref; r-- > 0;) {
-      if (ref_off[r] != ~0ull) {
-        piece[r] = {ref_off[r], next};
-        next = ref_off[r];
+    for (uint64_t k = 0; k < n_chunks + 1; k++) {
+      if (k < n_chunks) {
+        const int b = (int)(k % PinnedBounce::N);
+        {  // the buffer must have been fully consumed
+          std::unique_lock<std::mutex> g(mu);
+          cv_done.wait(g, [&] { return outstanding[b] == 0; });
+        }
+        const uint64_t a0 = k * CH, a1 = std::min(nbytes, a0 + CH);
+        CU(cudaMemcpyAsync(g_bounce.buf[b], d_text + a0, a1 - a0, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(g_bounce.ev[b], st));
+      }
+      if (k > 0) {  // hand the previous chunk to the workers while this one is in flight
+        const uint64_t j = k - 1;
+        const int b = (int)(j % PinnedBounce::N);
+        CU(cudaEventSynchronize(g_bounce.ev[b]));
+        const uint64_t a0 = j * CH, a1 = std::min(nbytes, a0 + CH);
+        const uint64_t SUB = 4ull << 20;
+        std::lock_guard<std::mutex> g(mu);
+        for (uint64_t x = a0; x < a1; x += SUB) {
+          q.push_back(Task{g_bounce.buf[b] + (x - a0), x, std::min(a1, x + SUB)});
+          outstanding[b]++;
+        }
+        cv.notify_all();
       }
     }
-    std::vector<int> order(n_ref);
-    for (size_t r = 0; r < n_ref; r++) order[r] = (int)r;
-    std::sort(order.begin(), order.end(), [&](int x, int y) { return hdr_.names[x] < hdr_.names[y]; });
-    bool identity = true;
-    uint64_t pos = 0;
-    for (int r : order) {
-      if (piece[r].second > piece[r].first) {
-        if (piece[r].first != pos) identity = false;
-        pos = piece[r].second;
-      }
-    }
-    if (identity) {
-      out.swap(raw);
-    } else {
-      out.reserve(nbytes);
-      for (int r : order) out.append(raw, piece[r].first, piece[r].second - piece[r].first);
+    {
+      std::unique_lock<std::mutex> g(mu);
+      cv_done.wait(g, [&] { return outstanding[0] == 0 && outstanding[1] == 0; });
     }
   } catch (...) {
-    release_all();
+    finish();
     throw;
   }
-  release_all();
+  finish();
+  if (!err.empty()) fail(err);
+}
+
+void Pileup::bedgraph_text(std::string &out) {
+  ensure_finalized();
+  DeviceCtx &ctx = *im_->ctx;
+  const double t0 = now_ms();
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  TextJob job;
+  format_text(job);
+  out.assign(job.nbytes, '\0');
+  char *dst = out.empty() ? nullptr : &out[0];
+  drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, 4,
+             [dst](const uint8_t *src, uint64_t len, uint64_t off) { memcpy(dst + off, src, len); });
   tm_.text_ms = now_ms() - t0;
 }
 
 void Pileup::to_bedgraph(const std::string &path) {
-  if (!accumulated_) accumulate();
-  if (!finalized_) finalize_range(false);
-  std::string text;
-  bedgraph_text(text);
-  FILE *f = fopen(path.c_str(), "wb");
-  if (!f) fail("cannot create " + path);
-  size_t w = text.empty() ? 0 : fwrite(text.data(), 1, text.size(), f);
-  int rc = fclose(f);
-  if (w != text.size() || rc != 0) fail("write error on " + path);
+  ensure_finalized();
+  DeviceCtx &ctx = *im_->ctx;
+  const double t0 = now_ms();
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  TextJob job;
+  format_text(job);
+  int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) fail("cannot create " + path);
+  try {
+    drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, (int)env_u64("BND_WRITERS", 6),
+               [fd](const uint8_t *src, uint64_t len, uint64_t off) {
+                 uint64_t done = 0;
+                 while (done < len) {
+                   ssize_t w = pwrite(fd, src + done, len - done, (off_t)(off + done));
+                   if (w <= 0) fail("write error on the bedGraph output");
+                   done += (uint64_t)w;
+                 }
+               });
+  } catch (...) {
+    close(fd);
+    throw;
+  }
+  if (close(fd) != 0) fail("write error on " + path);
+  tm_.text_ms = now_ms() - t0;
 }
 
 }  // namespace bnd

@@ -63,7 +63,9 @@ class Pileup {
     uint64_t end_pos = 0;
   };
   struct Impl;
+  struct TextJob;
   std::unique_ptr<Impl> im_;
+  void format_text(TextJob &job);
 
   void open();
   Range range_for_chunks(uint64_t chunk_lo, uint64_t chunk_hi) const;

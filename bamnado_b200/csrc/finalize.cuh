@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(TEXT_THREADS) text_write_kernel(TextArgs a) {
       uint64_t start, stop;
       run_coords(a.g, gb, nx, ref, start, stop);
       // first row of a reference records where that reference's text begins
-      if (gb == __ldg(a.g.ref_first_bin + ref)) a.ref_text_off[ref] = off;
+      if (gb == tmax<uint64_t>(__ldg(a.g.ref_first_bin + ref), a.g.bin_lo)) a.ref_text_off[ref] = off;  // first row of the reference in this shard
       if (len) {
         char *p = a.text + off;
         const uint32_t n0 = a.name_off[ref], n1 = a.name_off[ref + 1];

@@ -88,6 +88,8 @@ int bnd_last_error_class(void);
 void bnd_free(void *p);                /* frees buffers returned through out-pointers */
 int bnd_abi_version(void);
 int bnd_device_count(void);
+/* CUDA kernel launches issued by this library since the process started (bench.py's gpu_launches) */
+uint64_t bnd_launch_count(void);
 
 /* ---- BamPileup (coverage_analysis.rs:136-760) ------------------------------------------------------------ */
 /* BamPileup::new + BamReadFilter::new; opens BAM header + BAI (BamStats::new, bam_utils.rs:311-378). */

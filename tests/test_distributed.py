@@ -1,0 +1,59 @@
+"""N > 1 path on CPU: two `gloo` ranks, each piles up its shard of the genomic chunks (emulator backend), the 13 filter
+counters are summed with one all-reduce, and the concatenated rows equal the oracle's whole-genome rows."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+from conftest import ROOT
+
+WORKER = textwrap.dedent("""
+    import ctypes, os, sys
+    import numpy as np
+    import torch, torch.distributed as dist
+    sys.path.insert(0, {root!r})
+    from bamnado_b200 import _native
+    from bamnado_b200.build import build_emul
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    N = _native.Native(ctypes.CDLL(str(build_emul())))
+    pile = dict(bam_path={bam!r}, bin_size=50, norm="rpkm", shard_rank=rank, shard_world=world)
+    filt = dict(min_mapq=30, proper_pair=True)
+    with N.pileup(pile, filt) as h:
+        h.accumulate()
+        t = torch.tensor(list(h.stats().values()), dtype=torch.int64)
+        dist.all_reduce(t)
+        h.set_total_stats(t.tolist())
+        h.finalize()
+        np.save({out!r} + f".runs{{rank}}.npy", h.runs())
+        if rank == 0:
+            np.save({out!r} + ".stats.npy", t.numpy())
+            open({out!r} + ".factor", "w").write(repr(h.norm_factor()))
+        text = h.bedgraph_text()
+        open({out!r} + f".text{{rank}}", "wb").write(text)
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_gloo_sharded_coverage(oracle, make_bam, tmp_path, native_emul):
+    bam = make_bam("pe", "--pairs", 20000, "--odd")
+    out = str(tmp_path / "dist")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=str(ROOT), bam=bam, out=out))
+    env = dict(os.environ, BND_SEGMENT_BYTES="262144", BND_EMUL_WORKERS="2", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    pile, filt = dict(bam_path=bam, bin_size=50, norm="rpkm"), dict(min_mapq=30, proper_pair=True)
+    oruns, ostats, ofactor = oracle.pileup_runs(pile, filt)
+    runs = np.concatenate([np.load(out + f".runs{k}.npy") for k in range(2)])
+    assert len(runs) == len(oruns) and (runs == oruns).all()
+    assert list(np.load(out + ".stats.npy")) == list(ostats.values())
+    assert float(open(out + ".factor").read()) == ofactor
+    # every rank's text rows use the job-wide factor; together they are the oracle's bedGraph (as a set of lines)
+    ref = tmp_path / "oracle.bdg"
+    oracle.pileup_to_bedgraph(pile, filt, ref)
+    got = sorted(open(out + ".text0", "rb").read().splitlines() + open(out + ".text1", "rb").read().splitlines())
+    assert got == sorted(ref.read_bytes().splitlines())
