@@ -3,6 +3,7 @@
 #include "kernels.h"
 
 #include <atomic>
+#include <cstdlib>
 
 #include "finalize.cuh"
 #include "inflate.cuh"
@@ -13,9 +14,6 @@ namespace bnd {
 
 namespace {
 std::atomic<unsigned long long> g_launches{0};
-constexpr int INFLATE_G = 32;        // lanes cooperating on one BGZF block
-constexpr int INFLATE_THREADS = 128; // 4 blocks in flight per CTA
-constexpr int INFLATE_CTAS_PER_SM = 6;
 inline cudaError_t launched() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
@@ -29,9 +27,43 @@ inline unsigned grid_for(uint64_t items, uint64_t per_cta, uint64_t cap) {
 }  // namespace
 
 unsigned long long launch_count() { return g_launches.load(); }
-int inflate_ctas_per_sm() { return INFLATE_CTAS_PER_SM; }
+
+namespace {
+struct InflateVariant {
+  int g, threads, ctas_per_sm;
+};
+// lane-group width / CTA size / resident CTAs per SM; selected with BND_INFLATE_VARIANT (default 0)
+const InflateVariant kVariants[] = {{32, 128, 9}, {32, 256, 5}, {32, 512, 2}, {16, 256, 2}, {16, 128, 5}, {8, 384, 1}, {32, 192, 6}};
+int variant_index() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("BND_INFLATE_VARIANT");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v >= (int)(sizeof(kVariants) / sizeof(kVariants[0]))) v = 0;
+  }
+  return v;
+}
+template <int G, int T, int MINB>
+cudaError_t launch_inflate_t(const InflateArgs &a, int sm_count, int ctas_per_sm, cudaStream_t s) {
+  auto kern = bgzf_inflate_kernel<G, T, MINB>;
+  constexpr int groups = T / G;
+  const size_t smem = inflate_smem_bytes(groups);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  unsigned grid = grid_for(a.n_blocks, groups, (uint64_t)sm_count * ctas_per_sm);
+  BND_LAUNCH(kern, dim3(grid), dim3(T), smem, s, a);
+  return launched();
+}
+}  // namespace
+
+int inflate_ctas_per_sm() { return kVariants[variant_index()].ctas_per_sm; }
 
 void make_crc_tables(CrcTables *T) {
+  const int G = kVariants[variant_index()].g;
   for (uint32_t i = 0; i < 256; i++) {
     uint32_t c = i;
     for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
@@ -41,25 +73,23 @@ void make_crc_tables(CrcTables *T) {
   for (int b = 0; b < 4; b++)
     for (uint32_t x = 0; x < 256; x++) {
       uint32_t c = x << (8 * b);
-      for (int k = 0; k < 4 * INFLATE_G; k++) c = T->t[c & 0xff] ^ (c >> 8);
+      for (int k = 0; k < 4 * G; k++) c = T->t[c & 0xff] ^ (c >> 8);
       T->z[b][x] = c;
     }
 }
 
 cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_blocks == 0) return cudaSuccess;
-  auto kern = bgzf_inflate_kernel<INFLATE_G, INFLATE_THREADS>;
-  constexpr int groups = INFLATE_THREADS / INFLATE_G;
-  const size_t smem = inflate_smem_bytes(groups);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
+  const InflateVariant &v = kVariants[variant_index()];
+  switch (variant_index()) {
+    case 1: return launch_inflate_t<32, 256, 5>(a, sm_count, v.ctas_per_sm, s);
+    case 2: return launch_inflate_t<32, 512, 2>(a, sm_count, v.ctas_per_sm, s);
+    case 3: return launch_inflate_t<16, 256, 2>(a, sm_count, v.ctas_per_sm, s);
+    case 4: return launch_inflate_t<16, 128, 5>(a, sm_count, v.ctas_per_sm, s);
+    case 5: return launch_inflate_t<8, 384, 1>(a, sm_count, v.ctas_per_sm, s);
+    case 6: return launch_inflate_t<32, 192, 6>(a, sm_count, v.ctas_per_sm, s);
+    default: return launch_inflate_t<32, 128, 9>(a, sm_count, v.ctas_per_sm, s);
   }
-  unsigned grid = grid_for(a.n_blocks, groups, (uint64_t)sm_count * INFLATE_CTAS_PER_SM);
-  BND_LAUNCH(kern, dim3(grid), dim3(INFLATE_THREADS), smem, s, a);
-  return launched();
 }
 
 cudaError_t launch_record_index(const RecArgs &a, cudaStream_t s) {
