@@ -887,7 +887,7 @@ double Pileup::norm_factor() const {
 }
 
 // ---- K5: scan + collapse ------------------------------------------------------------------------------------------------
-uint64_t Pileup::finalize_range(bool dense_counts) {
+uint64_t Pileup::finalize_range(bool dense_counts, bool emit_runs) {
   Impl &im = *im_;
   DeviceCtx &ctx = *im.ctx;
   std::lock_guard<std::mutex> lock(ctx.mu);
@@ -920,11 +920,13 @@ uint64_t Pileup::finalize_range(bool dense_counts) {
   FinState fs;
   CU(cudaMemcpyAsync(&fs, im.d_fs.p, sizeof fs, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  im.n_runs = fs.n_runs;
-  im.d_run_bin.ensure((size_t)im.n_runs * 8 + 16);
-  im.d_run_val.ensure((size_t)im.n_runs * 4 + 16);
-  a.run_bin = im.d_run_bin.as<uint64_t>();
-  a.run_val = im.d_run_val.as<uint32_t>();
+  im.n_runs = emit_runs ? fs.n_runs : 0;
+  if (emit_runs) {
+    im.d_run_bin.ensure((size_t)im.n_runs * 8 + 16);
+    im.d_run_val.ensure((size_t)im.n_runs * 4 + 16);
+    a.run_bin = im.d_run_bin.as<uint64_t>();
+    a.run_val = im.d_run_val.as<uint32_t>();
+  }
   if (dense_counts) {
     im.d_counts.ensure((size_t)nb * 4 + 16);
     a.counts = im.d_counts.as<uint32_t>();
@@ -1039,6 +1041,195 @@ void Pileup::signal(const std::string &chrom, std::vector<float> &out) {
     throw;
   }
   d_out.release();
+}
+
+// ---- BamStats::is_paired_end ----------------------------------------------------------------------------------------------
+bool Pileup::is_paired_end() {
+  Impl &im = *im_;
+  const uint64_t begin = hdr_.first_record_voff >> 16;
+  uint64_t want = std::min<uint64_t>(file_size_ - begin, 4u << 20);
+  std::vector<uint8_t> raw(want), inflated;
+  std::vector<int32_t> status;
+  uint64_t got = 0;
+  while (got < want) {
+    ssize_t r = pread(im.fd, raw.data() + got, want - got, (off_t)(begin + got));
+    if (r <= 0) fail("Failed to open BAM file to check paired-end status");
+    got += (uint64_t)r;
+  }
+  BlockTable tab;
+  scan_bgzf_blocks(raw.data(), want, tab, 64);
+  device_inflate(raw.data(), tab.coff.back(), inflated, status, im.ctx->device);
+  uint64_t p = hdr_.first_record_voff & 0xffff;
+  for (int i = 0; i <= 1000; i++) {
+    if (p + 36 > inflated.size()) break;
+    uint32_t bs = (uint32_t)inflated[p] | ((uint32_t)inflated[p + 1] << 8) | ((uint32_t)inflated[p + 2] << 16) | ((uint32_t)inflated[p + 3] << 24);
+    if (bs < 32) break;
+    uint32_t flag = (uint32_t)inflated[p + 18] | ((uint32_t)inflated[p + 19] << 8);
+    if (flag & 0x1) return true;
+    p += 4ull + bs;
+  }
+  return false;
+}
+
+// ---- MultiBamPileup ---------------------------------------------------------------------------------------------------------
+void Pileup::multi_collapse(std::vector<Pileup *> &bams, std::vector<RunRow> &rows, std::vector<uint32_t> &vals) {
+  rows.clear();
+  vals.clear();
+  if (bams.empty()) fail("At least one BAM pileup is required", ERR_INVALID);
+  if ((int)bams.size() > MULTI_MAX_BAMS) fail("too many BAM files for one multi-bam-coverage call", ERR_INVALID);
+  Pileup &first = *bams[0];
+  for (Pileup *b : bams) {
+    if (b->cfg_.bin_size != first.cfg_.bin_size) fail("All BAM pileups must have the same bin size", ERR_INVALID);
+    if (b->cfg_.collapse) fail("All BAM pileups must have collapse set to false", ERR_INVALID);
+    if (b->hdr_.names != first.hdr_.names || b->hdr_.lens != first.hdr_.lens || b->geo_.L != first.geo_.L || b->geo_.in_stats != first.geo_.in_stats)
+      fail("multi-bam-coverage on the B200 path needs BAMs with the same reference dictionary and chunk length");
+    if (b->im_->ctx != first.im_->ctx) fail("all BAMs of one multi-bam-coverage call must use the same device", ERR_INVALID);
+  }
+  // per-BAM raw counts; the scan runs in place so every BAM keeps one u32 per bin in HBM
+  MultiArgs a{};
+  a.n_bams = (int)bams.size();
+  for (size_t i = 0; i < bams.size(); i++) {
+    Pileup &b = *bams[i];
+    b.run_pass(b.shard_, false);
+    b.finalize_range(true, false);
+    a.counts[i] = b.im_->d_counts.as<uint32_t>();
+  }
+  DeviceCtx &ctx = *first.im_->ctx;
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  cudaStream_t st = ctx.sets[0].stream;
+  a.g = first.im_->gdev;
+  a.n_bins = a.g.bin_hi - a.g.bin_lo;
+  const uint64_t n_tiles64 = (a.n_bins + 255) / 256;
+  if (n_tiles64 > 0xffffffffull) fail("too many bins for one shard");
+  a.n_tiles = (uint32_t)n_tiles64;
+  if (a.n_bins == 0) return;
+  DevBuf d_tiles, d_total, d_run_bin, d_vals, d_rows;
+  auto release = [&] {
+    for (DevBuf *b : {&d_tiles, &d_total, &d_run_bin, &d_vals, &d_rows}) b->release();
+  };
+  try {
+    d_tiles.ensure((size_t)a.n_tiles * 8 + 16);
+    d_total.ensure(16);
+    a.tile_heads = d_tiles.as<uint64_t>();
+    CU(launch_multi_count(a, ctx.sm_count, st));
+    CU(launch_u64_scan(a.tile_heads, a.n_tiles, d_total.as<unsigned long long>(), st));
+    unsigned long long n_runs = 0;
+    CU(cudaMemcpyAsync(&n_runs, d_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    d_run_bin.ensure(n_runs * 8 + 16);
+    d_vals.ensure(n_runs * 4 * bams.size() + 16);
+    d_rows.ensure(n_runs * sizeof(RunRow) + 16);
+    a.run_bin = d_run_bin.as<uint64_t>();
+    a.out_vals = d_vals.as<uint32_t>();
+    a.n_runs_cap = n_runs;
+    CU(launch_multi_emit(a, ctx.sm_count, st));
+    RunArgs ra{};
+    ra.run_bin = a.run_bin;
+    ra.run_val = nullptr;
+    ra.n_runs = n_runs;
+    ra.g = a.g;
+    ra.rows = d_rows.as<RunRow>();
+    CU(launch_multi_rows(ra, ctx.sm_count, st));
+    rows.resize(n_runs);
+    vals.resize(n_runs * bams.size());
+    if (n_runs) {
+      CU(cudaMemcpyAsync(rows.data(), d_rows.p, n_runs * sizeof(RunRow), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(vals.data(), d_vals.p, n_runs * 4 * bams.size(), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+  } catch (...) {
+    release();
+    throw;
+  }
+  release();
+}
+
+// ---- collapse-bedgraph ------------------------------------------------------------------------------------------------------
+void collapse_rows_device(const BdgRows &in, BdgRows &out, int device) {
+  out = BdgRows();
+  const uint64_t n = in.chrom.size();
+  if (n == 0) return;
+  DeviceCtx &ctx = ctx_for(device);
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  cudaStream_t st = ctx.sets[0].stream;
+  DevBuf d_chrom, d_start, d_end, d_score, d_perm, d_flag, d_tiles, d_total, o_chrom, o_start, o_end, o_score;
+  auto release = [&] {
+    for (DevBuf *b : {&d_chrom, &d_start, &d_end, &d_score, &d_perm, &d_flag, &d_tiles, &d_total, &o_chrom, &o_start, &o_end, &o_score}) b->release();
+  };
+  try {
+    upload(d_chrom, in.chrom.data(), n);
+    upload(d_start, in.start.data(), n);
+    upload(d_end, in.end.data(), n);
+    upload(d_score, in.score.data(), n);
+    d_flag.ensure(16);
+    CU(cudaMemset(d_flag.p, 0, 16));
+    BdgArgs a{};
+    a.chrom = d_chrom.as<uint32_t>();
+    a.start = d_start.as<long long>();
+    a.end = d_end.as<long long>();
+    a.score = d_score.as<double>();
+    a.n = n;
+    a.n_tiles = (uint32_t)((n + 255) / 256);
+    a.unsorted = d_flag.as<unsigned int>();
+    CU(launch_bdg_sorted_check(a, ctx.sm_count, st));
+    unsigned int unsorted = 0;
+    CU(cudaMemcpyAsync(&unsorted, d_flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (unsorted) {
+      // sort (chrom, start): permutation from the device radix sort, columns gathered on the host side of the copy
+      d_perm.ensure(n * 4);
+      CU(sort_rows_by_chrom_start(a.chrom, a.start, n, d_perm.as<uint32_t>(), st));
+      std::vector<uint32_t> perm(n);
+      CU(cudaMemcpy(perm.data(), d_perm.p, n * 4, cudaMemcpyDeviceToHost));
+      BdgRows s;
+      s.chrom.resize(n), s.start.resize(n), s.end.resize(n), s.score.resize(n);
+      for (uint64_t i = 0; i < n; i++) {
+        s.chrom[i] = in.chrom[perm[i]];
+        s.start[i] = in.start[perm[i]];
+        s.end[i] = in.end[perm[i]];
+        s.score[i] = in.score[perm[i]];
+      }
+      upload(d_chrom, s.chrom.data(), n);
+      upload(d_start, s.start.data(), n);
+      upload(d_end, s.end.data(), n);
+      upload(d_score, s.score.data(), n);
+      a.chrom = d_chrom.as<uint32_t>();
+      a.start = d_start.as<long long>();
+      a.end = d_end.as<long long>();
+      a.score = d_score.as<double>();
+    }
+    d_tiles.ensure((size_t)a.n_tiles * 8 + 16);
+    d_total.ensure(16);
+    a.tile_heads = d_tiles.as<uint64_t>();
+    CU(launch_bdg_count(a, ctx.sm_count, st));
+    CU(launch_u64_scan(a.tile_heads, a.n_tiles, d_total.as<unsigned long long>(), st));
+    unsigned long long m = 0;
+    CU(cudaMemcpyAsync(&m, d_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<long long> init_min(m, INT64_MAX), init_max(m, INT64_MIN);
+    o_chrom.ensure(m * 4 + 16);
+    o_score.ensure(m * 8 + 16);
+    upload(o_start, init_min.data(), m);
+    upload(o_end, init_max.data(), m);
+    a.out_chrom = o_chrom.as<uint32_t>();
+    a.out_start = o_start.as<long long>();
+    a.out_end = o_end.as<long long>();
+    a.out_score = o_score.as<double>();
+    CU(launch_bdg_emit(a, ctx.sm_count, st));
+    out.chrom.resize(m), out.start.resize(m), out.end.resize(m), out.score.resize(m);
+    if (m) {
+      CU(cudaMemcpyAsync(out.chrom.data(), o_chrom.p, m * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(out.start.data(), o_start.p, m * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(out.end.data(), o_end.p, m * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(out.score.data(), o_score.p, m * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+  } catch (...) {
+    release();
+    throw;
+  }
+  release();
 }
 
 // ---- bedGraph text ------------------------------------------------------------------------------------------------------

@@ -52,6 +52,12 @@ class Pileup {
 
   const BamHeader &header() const { return hdr_; }
   const Geometry &geometry() const { return geo_; }
+  const bnd_pileup_cfg &config() const { return cfg_; }
+  const std::string &bam_path() const { return bam_path_; }
+  // BamStats::is_paired_end (bam_utils.rs:564-582): any of the first ~1000 records carries the 0x1 flag
+  bool is_paired_end();
+  // MultiBamPileup (coverage_analysis.rs:783-848): raw per-bin counts of every BAM, collapsed where all samples agree
+  static void multi_collapse(std::vector<Pileup *> &bams, std::vector<RunRow> &rows, std::vector<uint32_t> &vals);
 
  private:
   struct Range {  // what part of the file / genome a pass covers
@@ -71,7 +77,7 @@ class Pileup {
   Range range_for_chunks(uint64_t chunk_lo, uint64_t chunk_hi) const;
   void run_pass(const Range &r, bool resident);
   void reset_accumulators(const Range &r);
-  uint64_t finalize_range(bool dense_counts);
+  uint64_t finalize_range(bool dense_counts, bool emit_runs = true);
   void fetch_rows(std::vector<RunRow> &out);
   void ensure_finalized();
 
@@ -93,5 +99,14 @@ class Pileup {
 void device_inflate(const uint8_t *bgzf, uint64_t n_bytes, std::vector<uint8_t> &out, std::vector<int32_t> &status, int device);
 
 int device_count();
+
+// collapse_adjacent_bins (bedgraph_utils.rs:5-45) on the device.  Inputs are rows in file order with the chromosome
+// as its rank in byte-string order; outputs are the collapsed groups in (chrom, start) order.
+struct BdgRows {
+  std::vector<uint32_t> chrom;
+  std::vector<long long> start, end;
+  std::vector<double> score;
+};
+void collapse_rows_device(const BdgRows &in, BdgRows &out, int device);
 
 }  // namespace bnd

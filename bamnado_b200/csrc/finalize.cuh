@@ -165,8 +165,10 @@ __global__ void __launch_bounds__(FIN_THREADS) bins_emit_kernel(FinArgs a) {
         run += (uint32_t)d[i];
         if (a.counts) a.counts[first + i] = run;
         if ((hm >> i) & 1u) {
-          a.run_bin[pos] = first + (uint64_t)i + a.g.bin_lo;
-          a.run_val[pos] = run;
+          if (a.run_bin) {
+            a.run_bin[pos] = first + (uint64_t)i + a.g.bin_lo;
+            a.run_val[pos] = run;
+          }
           pos++;
           my_max = tmax(my_max, run);
         }

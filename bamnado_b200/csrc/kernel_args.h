@@ -219,4 +219,31 @@ struct TextArgs {
 constexpr int SCORE_W = 32;
 constexpr int TEXT_THREADS = 256;
 
+// collapse-bedgraph rows (sorted by chrom rank, start) and their collapsed groups
+struct BdgArgs {
+  const uint32_t *chrom;  // rank of the chromosome name in byte-string order
+  const long long *start, *end;
+  const double *score;
+  uint64_t n;
+  uint32_t n_tiles;
+  uint64_t *tile_heads;
+  unsigned int *unsorted;
+  uint32_t *out_chrom;
+  long long *out_start, *out_end;  // pre-filled with +inf / -inf
+  double *out_score;
+};
+
+constexpr int MULTI_MAX_BAMS = 64;
+struct MultiArgs {
+  const uint32_t *counts[MULTI_MAX_BAMS];  // dense per-bin counts of each BAM (identical geometry)
+  int n_bams;
+  uint64_t n_bins;
+  GeomDev g;
+  uint32_t n_tiles;
+  uint64_t *tile_heads;
+  uint64_t *run_bin;
+  uint32_t *out_vals;  // [n_bams][n_runs_cap]
+  uint64_t n_runs_cap;
+};
+
 }  // namespace bnd

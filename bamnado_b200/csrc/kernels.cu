@@ -2,9 +2,16 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see bamnado_b200/build.py).
 #include "kernels.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <numeric>
+#include <vector>
+#if !defined(BND_EMUL)
+#include <cub/device/device_radix_sort.cuh>
+#endif
 
+#include "collapse.cuh"
 #include "finalize.cuh"
 #include "inflate.cuh"
 #include "pileup.cuh"
@@ -159,6 +166,93 @@ cudaError_t launch_text_write(const TextArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_tiles == 0) return cudaSuccess;
   BND_LAUNCH(text_write_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(TEXT_THREADS), 0, s, a);
   return launched();
+}
+
+cudaError_t launch_bdg_sorted_check(const BdgArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n < 2) return cudaSuccess;
+  BND_LAUNCH(bdg_sorted_check_kernel, dim3(grid_for(a.n, COL_THREADS, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_count(const BdgArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_count_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_emit(const BdgArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_emit_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_u64_scan(uint64_t *v, uint32_t n, unsigned long long *total_out, cudaStream_t s) {
+  auto k = u64_scan_kernel<1024>;
+  BND_LAUNCH(k, dim3(1), dim3(1024), 0, s, v, n, total_out);
+  return launched();
+}
+cudaError_t launch_multi_count(const MultiArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(multi_count_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_multi_emit(const MultiArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(multi_emit_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_multi_rows(const RunArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_runs == 0) return cudaSuccess;
+  BND_LAUNCH(multi_rows_kernel, dim3(grid_for(a.n_runs, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+
+cudaError_t sort_rows_by_chrom_start(const uint32_t *d_chrom, const long long *d_start, uint64_t n, uint32_t *d_perm, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+#if defined(BND_EMUL)
+  (void)s;  // tests/emul: device memory is host memory
+  std::iota(d_perm, d_perm + n, 0u);
+  std::stable_sort(d_perm, d_perm + n, [&](uint32_t x, uint32_t y) {
+    return d_chrom[x] != d_chrom[y] ? d_chrom[x] < d_chrom[y] : d_start[x] < d_start[y];
+  });
+  return cudaSuccess;
+#else
+  // LSD: stable sort by start (sign bit flipped so that i64 order == u64 order), then stable sort by chrom rank
+  if (n > 0x7fffffffull) return cudaErrorInvalidValue;
+  const int N = (int)n;
+  uint64_t *k0 = nullptr, *k1 = nullptr;
+  uint32_t *v0 = nullptr, *c0 = nullptr, *c1 = nullptr;
+  void *tmp = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto done = [&](cudaError_t err) {
+    cudaFree(k0), cudaFree(k1), cudaFree(v0), cudaFree(c0), cudaFree(c1), cudaFree(tmp);
+    return err;
+  };
+  if ((e = cudaMalloc((void **)&k0, n * 8)) || (e = cudaMalloc((void **)&k1, n * 8)) || (e = cudaMalloc((void **)&v0, n * 4)) ||
+      (e = cudaMalloc((void **)&c0, n * 4)) || (e = cudaMalloc((void **)&c1, n * 4)))
+    return done(e);
+  std::vector<long long> h_start(n);
+  std::vector<uint32_t> iota(n), h_chrom(n);
+  std::iota(iota.begin(), iota.end(), 0u);
+  if ((e = cudaMemcpyAsync(h_start.data(), d_start, n * 8, cudaMemcpyDeviceToHost, s)) ||
+      (e = cudaMemcpyAsync(h_chrom.data(), d_chrom, n * 4, cudaMemcpyDeviceToHost, s)) || (e = cudaStreamSynchronize(s)))
+    return done(e);
+  std::vector<uint64_t> keys(n);
+  for (uint64_t i = 0; i < n; i++) keys[i] = (uint64_t)h_start[i] ^ 0x8000000000000000ull;
+  if ((e = cudaMemcpyAsync(k0, keys.data(), n * 8, cudaMemcpyHostToDevice, s)) || (e = cudaMemcpyAsync(v0, iota.data(), n * 4, cudaMemcpyHostToDevice, s)))
+    return done(e);
+  size_t tb = 0, tb2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, d_perm, N, 0, 64, s);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb2, c0, c1, d_perm, v0, N, 0, 32, s);
+  tb = std::max(tb, tb2);
+  if ((e = cudaMalloc(&tmp, tb))) return done(e);
+  if ((e = cub::DeviceRadixSort::SortPairs(tmp, tb, k0, k1, v0, d_perm, N, 0, 64, s))) return done(e);
+  std::vector<uint32_t> perm(n), gathered(n);
+  if ((e = cudaMemcpyAsync(perm.data(), d_perm, n * 4, cudaMemcpyDeviceToHost, s)) || (e = cudaStreamSynchronize(s))) return done(e);
+  for (uint64_t i = 0; i < n; i++) gathered[i] = h_chrom[perm[i]];
+  if ((e = cudaMemcpyAsync(c0, gathered.data(), n * 4, cudaMemcpyHostToDevice, s))) return done(e);
+  if ((e = cub::DeviceRadixSort::SortPairs(tmp, tb, c0, c1, d_perm, v0, N, 0, 32, s))) return done(e);
+  if ((e = cudaMemcpyAsync(d_perm, v0, n * 4, cudaMemcpyDeviceToDevice, s)) || (e = cudaStreamSynchronize(s))) return done(e);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return done(cudaSuccess);
+#endif
 }
 
 }  // namespace bnd

@@ -28,6 +28,17 @@ cudaError_t launch_text_len(const TextArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_text_scan(const TextArgs &a, cudaStream_t s);
 cudaError_t launch_text_write(const TextArgs &a, int sm_count, cudaStream_t s);
 
+// K6 — collapse-bedgraph and multi-BAM collapse (collapse.cuh)
+cudaError_t launch_bdg_sorted_check(const BdgArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_count(const BdgArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_emit(const BdgArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_u64_scan(uint64_t *v, uint32_t n, unsigned long long *total_out, cudaStream_t s);
+cudaError_t launch_multi_count(const MultiArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_multi_emit(const MultiArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_multi_rows(const RunArgs &a, int sm_count, cudaStream_t s);
+// stable sort permutation of rows by (chrom rank, start): CUB radix sort (library) — only used when the input is unsorted
+cudaError_t sort_rows_by_chrom_start(const uint32_t *d_chrom, const long long *d_start, uint64_t n, uint32_t *d_perm, cudaStream_t s);
+
 // number of kernel launches issued through this file since process start (bench's gpu_launches)
 unsigned long long launch_count();
 

@@ -1,9 +1,856 @@
-// outputs.cpp — see outputs.h.
+// outputs.cpp — see outputs.h: BigWig encoding (host, north_star keeps it there), the multi-BAM TSV, the
+// collapse-bedgraph file front end and the CLI mirror of src/cli.rs for the three coverage subcommands.
 #include "outputs.h"
 
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+
 namespace bnd {
-void pileup_to_bigwig(Pileup &, const std::string &) { fail("BigWig output is not built yet"); }
-void multi_to_tsv(const bnd_pileup_cfg *, const bnd_filter_cfg *, int, const char *) { fail("multi-bam-coverage is not built yet"); }
-void collapse_bedgraph_file(const char *, const char *) { fail("collapse-bedgraph is not built yet"); }
-int cli_main(int, const char *const *) { return 1; }
+
+namespace {
+
+// ---- little-endian writer ---------------------------------------------------------------------------------------------
+struct Buf {
+  std::vector<uint8_t> d;
+  void u8(uint8_t v) { d.push_back(v); }
+  void u16(uint16_t v) {
+    for (int i = 0; i < 2; i++) d.push_back((uint8_t)(v >> (8 * i)));
+  }
+  void u32(uint32_t v) {
+    for (int i = 0; i < 4; i++) d.push_back((uint8_t)(v >> (8 * i)));
+  }
+  void u64(uint64_t v) {
+    for (int i = 0; i < 8; i++) d.push_back((uint8_t)(v >> (8 * i)));
+  }
+  void f32(float v) {
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    u32(b);
+  }
+  void f64(double v) {
+    uint64_t b;
+    memcpy(&b, &v, 8);
+    u64(b);
+  }
+  void bytes(const void *p, size_t n) { d.insert(d.end(), (const uint8_t *)p, (const uint8_t *)p + n); }
+  void pad_to(size_t n) { d.resize(std::max(d.size(), n), 0); }
+  void put_u64_at(size_t off, uint64_t v) {
+    for (int i = 0; i < 8; i++) d[off + i] = (uint8_t)(v >> (8 * i));
+  }
+};
+
+struct Section {  // one BigWig data section (<= ITEMS_PER_SLOT bedGraph items of one chromosome)
+  uint32_t chrom, start, end;
+  uint64_t offset, size;
+};
+constexpr uint32_t ITEMS_PER_SLOT = 1024, BLOCK = 256;
+
+// B+ tree over (name -> id, size), keys sorted bytewise
+void write_chrom_tree(Buf &b, std::vector<std::tuple<std::string, uint32_t, uint32_t>> items) {
+  std::sort(items.begin(), items.end());
+  uint32_t key_size = 1;
+  for (auto &it : items) key_size = std::max<uint32_t>(key_size, (uint32_t)std::get<0>(it).size());
+  const uint64_t n = items.size();
+  b.u32(0x78CA8C91);
+  b.u32(BLOCK);
+  b.u32(key_size);
+  b.u32(8);
+  b.u64(n);
+  b.u64(0);
+  // levels: leaves hold up to BLOCK items; each upper node up to BLOCK children
+  std::vector<uint64_t> level_nodes;  // nodes per level, leaf level first
+  uint64_t cnt = std::max<uint64_t>(n, 1);
+  level_nodes.push_back((cnt + BLOCK - 1) / BLOCK);
+  while (level_nodes.back() > 1) level_nodes.push_back((level_nodes.back() + BLOCK - 1) / BLOCK);
+  const int levels = (int)level_nodes.size();
+  const uint64_t leaf_item = key_size + 8, inner_item = key_size + 8;
+  // items covered by one node at level l (0 = leaf)
+  auto span = [&](int l) {
+    uint64_t s = BLOCK;
+    for (int i = 0; i < l; i++) s *= BLOCK;
+    return s;
+  };
+  // offsets of each level (root first in the file)
+  std::vector<uint64_t> level_off(levels);
+  uint64_t off = b.d.size();
+  for (int l = levels - 1; l >= 0; l--) {
+    level_off[l] = off;
+    uint64_t nodes = level_nodes[l];
+    // every node is written at full size so child offsets are arithmetic
+    off += nodes * (4 + (uint64_t)BLOCK * (l == 0 ? leaf_item : inner_item));
+  }
+  auto key = [&](const std::string &s) {
+    std::string k = s;
+    k.resize(key_size, '\0');
+    return k;
+  };
+  for (int l = levels - 1; l >= 0; l--) {
+    const uint64_t nodes = level_nodes[l], per = span(l), item_sz = l == 0 ? leaf_item : inner_item;
+    for (uint64_t nd = 0; nd < nodes; nd++) {
+      const uint64_t first = nd * per;
+      uint64_t children;
+      if (l == 0) children = n > first ? std::min<uint64_t>(BLOCK, n - first) : 0;
+      else {
+        const uint64_t child_span = span(l - 1);
+        children = n > first ? std::min<uint64_t>(BLOCK, (n - first + child_span - 1) / child_span) : 0;
+      }
+      b.u8(l == 0 ? 1 : 0);
+      b.u8(0);
+      b.u16((uint16_t)children);
+      for (uint64_t c = 0; c < BLOCK; c++) {
+        if (c < children) {
+          if (l == 0) {
+            auto &it = items[first + c];
+            b.bytes(key(std::get<0>(it)).data(), key_size);
+            b.u32(std::get<1>(it));
+            b.u32(std::get<2>(it));
+          } else {
+            const uint64_t child_span = span(l - 1), child = nd * BLOCK + c;
+            b.bytes(key(std::get<0>(items[first + c * child_span])).data(), key_size);
+            b.u64(level_off[l - 1] + child * (4 + (uint64_t)BLOCK * (l - 1 == 0 ? leaf_item : inner_item)));
+          }
+        } else {
+          for (uint64_t z = 0; z < item_sz; z++) b.u8(0);
+        }
+      }
+    }
+  }
+}
+
+// cirTree (R-tree) over the sections, built bottom-up with full-size nodes
+void write_rtree(Buf &b, const std::vector<Section> &secs, uint64_t end_file_offset) {
+  const uint64_t n = secs.size();
+  b.u32(0x2468ACE0);
+  b.u32(BLOCK);
+  b.u64(n);
+  b.u32(n ? secs.front().chrom : 0);
+  b.u32(n ? secs.front().start : 0);
+  b.u32(n ? secs.back().chrom : 0);
+  b.u32(n ? secs.back().end : 0);
+  b.u64(end_file_offset);
+  b.u32(ITEMS_PER_SLOT);
+  b.u32(0);
+  struct Node {
+    uint32_t sc, sb, ec, eb;
+  };
+  // level 0 = leaf nodes over sections
+  std::vector<std::vector<Node>> bounds;  // per level: bounding box of each node
+  std::vector<uint64_t> level_nodes;
+  uint64_t cnt = std::max<uint64_t>(n, 1);
+  level_nodes.push_back((cnt + BLOCK - 1) / BLOCK);
+  while (level_nodes.back() > 1) level_nodes.push_back((level_nodes.back() + BLOCK - 1) / BLOCK);
+  const int levels = (int)level_nodes.size();
+  bounds.resize(levels);
+  auto merge = [](Node &a, const Node &x, bool first) {
+    if (first) {
+      a = x;
+      return;
+    }
+    if (x.sc < a.sc || (x.sc == a.sc && x.sb < a.sb)) a.sc = x.sc, a.sb = x.sb;
+    if (x.ec > a.ec || (x.ec == a.ec && x.eb > a.eb)) a.ec = x.ec, a.eb = x.eb;
+  };
+  for (int l = 0; l < levels; l++) {
+    bounds[l].resize(level_nodes[l]);
+    for (uint64_t nd = 0; nd < level_nodes[l]; nd++) {
+      Node box{0, 0, 0, 0};
+      bool first = true;
+      const uint64_t lo = nd * BLOCK, hi = l == 0 ? std::min<uint64_t>(n, lo + BLOCK) : std::min<uint64_t>(level_nodes[l - 1], lo + BLOCK);
+      for (uint64_t c = lo; c < hi; c++) {
+        Node x = l == 0 ? Node{secs[c].chrom, secs[c].start, secs[c].chrom, secs[c].end} : bounds[l - 1][c];
+        merge(box, x, first);
+        first = false;
+      }
+      bounds[l][nd] = box;
+    }
+  }
+  std::vector<uint64_t> level_off(levels);
+  uint64_t off = b.d.size();
+  for (int l = levels - 1; l >= 0; l--) {
+    level_off[l] = off;
+    off += level_nodes[l] * (4 + (uint64_t)BLOCK * (l == 0 ? 32 : 24));
+  }
+  for (int l = levels - 1; l >= 0; l--) {
+    for (uint64_t nd = 0; nd < level_nodes[l]; nd++) {
+      const uint64_t lo = nd * BLOCK, hi = l == 0 ? std::min<uint64_t>(n, lo + BLOCK) : std::min<uint64_t>(level_nodes[l - 1], lo + BLOCK);
+      const uint64_t children = hi > lo ? hi - lo : 0;
+      b.u8(l == 0 ? 1 : 0);
+      b.u8(0);
+      b.u16((uint16_t)children);
+      for (uint64_t c = 0; c < BLOCK; c++) {
+        if (c < children) {
+          if (l == 0) {
+            const Section &s = secs[lo + c];
+            b.u32(s.chrom), b.u32(s.start), b.u32(s.chrom), b.u32(s.end);
+            b.u64(s.offset), b.u64(s.size);
+          } else {
+            const Node &x = bounds[l - 1][lo + c];
+            b.u32(x.sc), b.u32(x.sb), b.u32(x.ec), b.u32(x.eb);
+            b.u64(level_off[l - 1] + (lo + c) * (4 + (uint64_t)BLOCK * (l - 1 == 0 ? 32 : 24)));
+          }
+        } else {
+          for (int z = 0; z < (l == 0 ? 32 : 24); z++) b.u8(0);
+        }
+      }
+    }
+  }
+}
+
+std::string lower(std::string s) {
+  for (auto &c : s) c = (char)tolower((unsigned char)c);
+  return s;
+}
+
+}  // namespace
+
+// ---- to_bigwig (coverage_analysis.rs:642-759) -------------------------------------------------------------------------------
+// Rows: optional scaffold drop, BAM header order, start-1 / end-1, score = (count as f64 * factor) as f32.
+// The file is a version-4 bigWig with bedGraph sections, no zoom levels and uncompressed sections (uncompressBufSize 0).
+void pileup_to_bigwig(Pileup &p, const std::string &path) {
+  std::vector<RunRow> rows;
+  p.runs(rows);
+  const double factor = p.norm_factor();
+  const BamHeader &h = p.header();
+  const bool skip_scaffold = p.config().ignore_scaffold != 0;
+  const size_t n_ref = h.names.size();
+  std::vector<uint8_t> keep(n_ref, 1);
+  std::vector<std::tuple<std::string, uint32_t, uint32_t>> chroms;
+  for (size_t r = 0; r < n_ref; r++) {
+    if (skip_scaffold && is_scaffold(h.names[r])) keep[r] = 0;
+    if (h.lens[r] > 0xffffffffull) fail("chromosome too long for BigWig");
+    if (keep[r]) chroms.emplace_back(h.names[r], (uint32_t)r, (uint32_t)h.lens[r]);
+  }
+  Buf b;
+  b.pad_to(64 + 40);  // header + total summary, filled at the end
+  const uint64_t chrom_tree_off = b.d.size();
+  write_chrom_tree(b, chroms);
+  const uint64_t data_off = b.d.size();
+  b.u64(0);  // section count, patched below
+  std::vector<Section> secs;
+  uint64_t covered = 0;
+  double mn = 0, mx = 0, sum = 0, sumsq = 0;
+  bool any = false;
+  size_t i = 0;
+  while (i < rows.size()) {
+    const int32_t ref = rows[i].ref_id;
+    size_t j = i;
+    while (j < rows.size() && rows[j].ref_id == ref) j++;
+    if (keep[ref]) {
+      for (size_t s0 = i; s0 < j; s0 += ITEMS_PER_SLOT) {
+        const size_t s1 = std::min(j, s0 + ITEMS_PER_SLOT);
+        Section sec;
+        sec.chrom = (uint32_t)ref;
+        sec.offset = b.d.size();
+        if (rows[s0].start == 0 || rows[s1 - 1].stop - 1 > 0xffffffffull) fail("interval out of range for BigWig");
+        sec.start = (uint32_t)(rows[s0].start - 1);
+        sec.end = (uint32_t)(rows[s1 - 1].stop - 1);
+        b.u32(sec.chrom), b.u32(sec.start), b.u32(sec.end);
+        b.u32(0), b.u32(0);
+        b.u8(1), b.u8(0);
+        b.u16((uint16_t)(s1 - s0));
+        for (size_t k = s0; k < s1; k++) {
+          const uint32_t st = (uint32_t)(rows[k].start - 1), en = (uint32_t)(rows[k].stop - 1);
+          const float v = (float)((double)rows[k].val * factor);
+          b.u32(st), b.u32(en), b.f32(v);
+          const double w = (double)(en - st), dv = (double)v;
+          covered += en - st;
+          sum += dv * w;
+          sumsq += dv * dv * w;
+          if (!any || dv < mn) mn = dv;
+          if (!any || dv > mx) mx = dv;
+          any = true;
+        }
+        sec.size = b.d.size() - sec.offset;
+        secs.push_back(sec);
+      }
+    }
+    i = j;
+  }
+  b.put_u64_at(data_off, secs.size());
+  const uint64_t index_off = b.d.size();
+  write_rtree(b, secs, index_off);
+  // header
+  Buf hd;
+  hd.u32(0x888FFC26);
+  hd.u16(4);
+  hd.u16(0);  // zoom levels
+  hd.u64(chrom_tree_off);
+  hd.u64(data_off);
+  hd.u64(index_off);
+  hd.u16(0), hd.u16(0);
+  hd.u64(0);
+  hd.u64(64);  // total summary offset
+  hd.u32(0);   // uncompressBufSize: sections are stored raw
+  hd.u64(0);
+  hd.u64(covered), hd.f64(mn), hd.f64(mx), hd.f64(sum), hd.f64(sumsq);
+  memcpy(b.d.data(), hd.d.data(), hd.d.size());
+  b.u32(0x888FFC26);  // trailing magic, as UCSC writers append
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) fail("cannot create " + path);
+  size_t w = fwrite(b.d.data(), 1, b.d.size(), f);
+  if (fclose(f) != 0 || w != b.d.size()) fail("write error on " + path);
+}
+
+// ---- MultiBamPileup::to_tsv (coverage_analysis.rs:783-864), intended semantics ------------------------------------
+void multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int n, const char *out) {
+  if (n < 1) fail("At least one BAM pileup is required", ERR_INVALID);
+  std::vector<std::unique_ptr<Pileup>> owned;
+  std::vector<Pileup *> bams;
+  for (int i = 0; i < n; i++) {
+    owned.emplace_back(new Pileup(&cfgs[i], filters ? &filters[i] : nullptr));
+    bams.push_back(owned.back().get());
+  }
+  std::vector<RunRow> rows;
+  std::vector<uint32_t> vals;
+  Pileup::multi_collapse(bams, rows, vals);
+  const BamHeader &h = bams[0]->header();
+  // rows come in header order; report them sorted by (chrom byte string, start) like collapse_equal_bins sorts
+  std::vector<int> order(h.names.size());
+  for (size_t r = 0; r < order.size(); r++) order[r] = (int)r;
+  std::sort(order.begin(), order.end(), [&](int x, int y) { return h.names[x] < h.names[y]; });
+  std::vector<size_t> first(h.names.size() + 1, 0);
+  for (auto &r : rows) first[r.ref_id + 1]++;
+  for (size_t r = 0; r < h.names.size(); r++) first[r + 1] += first[r];
+  std::string text = "chrom\tstart\tend";
+  for (int i = 0; i < n; i++) {
+    text.push_back('\t');
+    text += bams[i]->bam_path();
+  }
+  text.push_back('\n');
+  const size_t n_rows = rows.size();
+  for (int ref : order) {
+    for (size_t k = first[ref]; k < first[ref + 1]; k++) {
+      text += h.names[ref];
+      text.push_back('\t');
+      text += std::to_string(rows[k].start);
+      text.push_back('\t');
+      text += std::to_string(rows[k].stop);
+      for (int i = 0; i < n; i++) {
+        text.push_back('\t');
+        text += std::to_string(vals[(size_t)i * n_rows + k]);
+      }
+      text.push_back('\n');
+    }
+  }
+  FILE *f = fopen(out, "wb");
+  if (!f) fail(std::string("cannot create ") + out);
+  size_t w = fwrite(text.data(), 1, text.size(), f);
+  if (fclose(f) != 0 || w != text.size()) fail(std::string("write error on ") + out);
+}
+
+// ---- collapse-bedgraph (src/cli.rs:1149-1205) -----------------------------------------------------------------------------------
+namespace {
+void collapse_stream(std::istream &in, std::ostream &out) {
+  std::vector<std::string> names;
+  std::map<std::string, uint32_t> id_of;
+  BdgRows rows;
+  std::vector<uint32_t> name_id;
+  std::string line;
+  while (std::getline(in, line)) {
+    size_t a = 0, b = line.size();
+    while (a < b && isspace((unsigned char)line[a])) a++;
+    while (b > a && isspace((unsigned char)line[b - 1])) b--;
+    if (a == b || line[a] == '#') continue;
+    std::vector<std::string> parts;
+    for (size_t i = a; i < b;) {
+      while (i < b && isspace((unsigned char)line[i])) i++;
+      size_t j = i;
+      while (j < b && !isspace((unsigned char)line[j])) j++;
+      if (j > i) parts.push_back(line.substr(i, j - i));
+      i = j;
+    }
+    if (parts.size() < 4) continue;
+    char *e1 = nullptr, *e2 = nullptr, *e3 = nullptr;
+    errno = 0;
+    long long s = strtoll(parts[1].c_str(), &e1, 10), e = strtoll(parts[2].c_str(), &e2, 10);
+    double sc = strtod(parts[3].c_str(), &e3);
+    if (*e1 || *e2 || *e3 || e1 == parts[1].c_str() || e2 == parts[2].c_str() || e3 == parts[3].c_str())
+      fail("invalid bedGraph line: " + line);
+    auto it = id_of.find(parts[0]);
+    if (it == id_of.end()) {
+      it = id_of.emplace(parts[0], (uint32_t)names.size()).first;
+      names.push_back(parts[0]);
+    }
+    name_id.push_back(it->second);
+    rows.start.push_back(s);
+    rows.end.push_back(e);
+    rows.score.push_back(sc);
+  }
+  // chromosome rank = position in byte-string order (polars sorts the string column bytewise)
+  std::vector<uint32_t> rank(names.size());
+  {
+    uint32_t r = 0;
+    for (auto &kv : id_of) rank[kv.second] = r++;
+  }
+  std::vector<std::string> by_rank(names.size());
+  for (auto &kv : id_of) by_rank[rank[kv.second]] = kv.first;
+  rows.chrom.resize(name_id.size());
+  for (size_t i = 0; i < name_id.size(); i++) rows.chrom[i] = rank[name_id[i]];
+  BdgRows res;
+  collapse_rows_device(rows, res, -1);
+  std::string text;
+  for (size_t i = 0; i < res.chrom.size(); i++) {
+    text += by_rank[res.chrom[i]];
+    text.push_back('\t');
+    text += std::to_string(res.start[i]);
+    text.push_back('\t');
+    text += std::to_string(res.end[i]);
+    text.push_back('\t');
+    text += format_f64(res.score[i]);
+    text.push_back('\n');
+    if (text.size() > (1u << 22)) {
+      out.write(text.data(), (std::streamsize)text.size());
+      text.clear();
+    }
+  }
+  out.write(text.data(), (std::streamsize)text.size());
+  out.flush();
+  if (!out) fail("write error on the collapsed bedGraph");
+}
+}  // namespace
+
+void collapse_bedgraph_file(const char *in_path, const char *out_path) {
+  std::ifstream fin;
+  std::ofstream fout;
+  if (in_path) {
+    fin.open(in_path, std::ios::binary);
+    if (!fin) fail(std::string("cannot open ") + in_path);
+  }
+  if (out_path) {
+    fout.open(out_path, std::ios::binary | std::ios::trunc);
+    if (!fout) fail(std::string("cannot create ") + out_path);
+  }
+  collapse_stream(in_path ? (std::istream &)fin : std::cin, out_path ? (std::ostream &)fout : std::cout);
+}
+
+// ---- run_cli (src/cli.rs:737-757) for bam-coverage / multi-bam-coverage / collapse-bedgraph -------------------------------------
+namespace {
+
+const char *VERSION = "bamnado 0.9.0";
+
+struct CliError {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void usage_error(const std::string &m) { throw CliError{2, "error: " + m + "\n\nFor more information, try '--help'.\n"}; }
+
+const char *TOP_HELP =
+    "Fast BAM and BigWig utilities for genomics workflows.\n\n"
+    "Usage: bamnado [OPTIONS] <COMMAND>\n\n"
+    "Commands (B200 coverage path):\n"
+    "  bam-coverage        Generate a coverage track from one BAM file [aliases: coverage]\n"
+    "  multi-bam-coverage  Merge coverage from multiple BAM files into one track [aliases: multi-coverage]\n"
+    "  collapse-bedgraph   Collapse adjacent bins with equal scores in a bedGraph file [aliases: collapse]\n\n"
+    "Options:\n"
+    "  -v, --verbose <LEVEL>  Log verbosity from 0 (quiet) to 4 (debug) [default: 2]\n"
+    "  -h, --help             Print help\n"
+    "  -V, --version          Print version\n";
+
+const char *COVERAGE_HELP =
+    "Options:\n"
+    "  -b, --bam <BAM> / --bams <BAM>...   Input BAM file(s)\n"
+    "  -o, --output <FILE>                 Output bedGraph, BigWig or TSV path\n\n"
+    "Coverage Options:\n"
+    "  -s, --bin-size <BP>                 Bin size for the output track\n"
+    "  -n, --normalize <METHOD>            raw | rpkm | cpm [default: raw] [aliases: --norm-method]\n"
+    "  -f, --scale-factor <FLOAT>          Multiply the final signal by this factor\n"
+    "      --fragment-counts               Count fragments instead of reads [aliases: --use-fragment]\n"
+    "      --shift <L,R,FL,FR>             Shift read or fragment ends before pileup [default: 0,0,0,0]\n"
+    "      --truncate <L,R,FL,FR>          Trim read or fragment ends before pileup\n"
+    "      --ignore-scaffolds              Skip scaffold or unplaced chromosomes [aliases: --ignore-scaffold]\n"
+    "      --threads <N>                   Threads to use while writing BigWig output [default: 6]\n\n"
+    "Read Filters:\n"
+    "      --strand <STRAND>               both | forward | reverse [default: both]\n"
+    "      --proper-pairs                  Keep only properly paired reads [aliases: --proper-pair]\n"
+    "      --min-mapq <INT>                [default: 20]\n"
+    "      --min-length <BP>               [default: 20]\n"
+    "      --max-length <BP>               [default: 1000]\n"
+    "      --blacklist <BED>               [aliases: --blacklisted-locations]\n"
+    "      --barcode-allowlist <FILE>      [aliases: --whitelisted-barcodes]\n"
+    "      --read-group <RG>\n"
+    "      --tag <TAG>                     [aliases: --filter-tag]\n"
+    "      --tag-value <VALUE>             [aliases: --filter-tag-value]\n"
+    "      --min-fragment-len <BP>         [aliases: --min-fragment-length]\n"
+    "      --max-fragment-len <BP>         [aliases: --max-fragment-length]\n"
+    "      --ignore-duplicates             [aliases: --no-duplicates]\n"
+    "      --ignore-secondary\n"
+    "      --ignore-supplementary\n"
+    "  -h, --help                          Print help\n";
+
+struct Opts {
+  std::vector<std::string> bams;
+  bool has_output = false;
+  std::string output;
+  bool has_input = false;
+  std::string input;
+  bool has_bin = false;
+  uint64_t bin = 50;
+  int norm = 0;
+  float scale = 1.0f;
+  bool use_fragment = false, ignore_scaffold = false;
+  bool has_shift = true;
+  int32_t shift[4] = {0, 0, 0, 0};
+  bool has_truncate = false, t_has5 = false, t_has3 = false;
+  uint64_t t5 = 0, t3 = 0;
+  int threads = 6;
+  int strand = 0;
+  bool proper_pair = false;
+  uint32_t min_mapq = 20, min_length = 20, max_length = 1000;
+  bool has_blacklist = false, has_barcodes = false, has_rg = false, has_tag = false, has_tag_value = false;
+  std::string blacklist, barcodes, rg, tag, tag_value;
+  bool has_min_frag = false, has_max_frag = false;
+  uint32_t min_frag = 0, max_frag = 0;
+  bool ex_dup = false, ex_sec = false, ex_sup = false;
+};
+
+uint64_t parse_uint(const std::string &opt, const std::string &v, uint64_t max) {
+  if (v.empty()) usage_error("invalid value '" + v + "' for '" + opt + "'");
+  uint64_t x = 0;
+  for (char c : v) {
+    if (c < '0' || c > '9') usage_error("invalid value '" + v + "' for '" + opt + "': invalid digit found in string");
+    x = x * 10 + (uint64_t)(c - '0');
+    if (x > max) usage_error("invalid value '" + v + "' for '" + opt + "': number too large to fit in target type");
+  }
+  return x;
+}
+
+std::vector<std::string> split_commas(const std::string &s) {
+  std::vector<std::string> out;
+  std::string cur;
+  for (char c : s) {
+    if (c == ',') out.push_back(cur), cur.clear();
+    else cur.push_back(c);
+  }
+  out.push_back(cur);
+  return out;
+}
+
+bool parse_i32(const std::string &s, int32_t &v) {
+  if (s.empty()) return false;
+  char *e = nullptr;
+  errno = 0;
+  long long x = strtoll(s.c_str(), &e, 10);
+  if (*e || errno || x < INT32_MIN || x > INT32_MAX) return false;
+  v = (int32_t)x;
+  return true;
+}
+
+// Parses the flags shared by the coverage subcommands.  `multi`: -b/--bams collects a list.
+void parse_coverage_args(const std::vector<std::string> &args, bool multi, Opts &o, bool &help) {
+  for (size_t i = 0; i < args.size(); i++) {
+    std::string a = args[i], inline_val;
+    bool has_inline = false;
+    if (a.rfind("--", 0) == 0) {
+      size_t eq = a.find('=');
+      if (eq != std::string::npos) {
+        inline_val = a.substr(eq + 1);
+        a = a.substr(0, eq);
+        has_inline = true;
+      }
+    } else if (a.size() > 2 && a[0] == '-' && a[1] != '-') {  // -s50
+      inline_val = a.substr(2);
+      if (!inline_val.empty() && inline_val[0] == '=') inline_val = inline_val.substr(1);
+      a = a.substr(0, 2);
+      has_inline = true;
+    }
+    auto value = [&]() -> std::string {
+      if (has_inline) return inline_val;
+      if (i + 1 >= args.size()) usage_error("a value is required for '" + a + "' but none was supplied");
+      return args[++i];
+    };
+    auto flag = [&]() {
+      if (has_inline) usage_error("unexpected value '" + inline_val + "' for '" + a + "' found; no more were expected");
+    };
+    if (a == "-h" || a == "--help") {
+      help = true;
+      return;
+    } else if (a == "-v" || a == "--verbose") {
+      parse_uint(a, value(), 255);
+    } else if ((!multi && (a == "-b" || a == "--bam")) || (multi && (a == "-b" || a == "--bams"))) {
+      o.bams.push_back(value());
+      if (multi)
+        while (!has_inline && i + 1 < args.size() && !args[i + 1].empty() && args[i + 1][0] != '-') o.bams.push_back(args[++i]);
+    } else if (a == "-o" || a == "--output") {
+      o.output = value();
+      o.has_output = true;
+    } else if (a == "-s" || a == "--bin-size") {
+      o.bin = parse_uint(a, value(), UINT64_MAX / 16);
+      o.has_bin = true;
+    } else if (a == "-n" || a == "--normalize" || a == "--norm-method") {
+      std::string v = lower(value());
+      if (v == "raw") o.norm = 0;
+      else if (v == "rpkm") o.norm = 1;
+      else if (v == "cpm") o.norm = 2;
+      else usage_error("invalid value '" + v + "' for '--normalize <METHOD>'\n  [possible values: raw, rpkm, cpm]");
+    } else if (a == "-f" || a == "--scale-factor") {
+      std::string v = value();
+      char *e = nullptr;
+      o.scale = strtof(v.c_str(), &e);
+      if (v.empty() || *e) usage_error("invalid value '" + v + "' for '--scale-factor <FLOAT>': invalid float literal");
+    } else if (a == "--fragment-counts" || a == "--use-fragment") {
+      flag();
+      o.use_fragment = true;
+    } else if (a == "--shift") {
+      auto parts = split_commas(value());
+      if (parts.size() != 4) usage_error("invalid value for '--shift <L,R,FL,FR>': Shift must be in the format '5,3,5r,3r'");
+      for (int k = 0; k < 4; k++)
+        if (!parse_i32(parts[k], o.shift[k])) o.shift[k] = 0;  // unparseable parts silently become 0
+      o.has_shift = true;
+    } else if (a == "--truncate") {
+      auto parts = split_commas(value());
+      if (parts.size() != 2) usage_error("invalid value for '--truncate <L,R,FL,FR>': Truncate must be in the format '5,3'");
+      o.has_truncate = true;
+      auto parse_usize = [](const std::string &s, uint64_t &v) {
+        if (s.empty()) return false;
+        v = 0;
+        for (char c : s) {
+          if (c < '0' || c > '9') return false;
+          v = v * 10 + (uint64_t)(c - '0');
+        }
+        return true;
+      };
+      o.t_has5 = parse_usize(parts[0], o.t5);
+      o.t_has3 = parse_usize(parts[1], o.t3);
+    } else if (a == "--ignore-scaffolds" || a == "--ignore-scaffold") {
+      flag();
+      o.ignore_scaffold = true;
+    } else if (a == "--threads") {
+      o.threads = (int)parse_uint(a, value(), 1u << 20);
+    } else if (a == "--strand") {
+      std::string v = lower(value());
+      if (v == "both") o.strand = 0;
+      else if (v == "forward") o.strand = 1;
+      else if (v == "reverse") o.strand = 2;
+      else usage_error("invalid value '" + v + "' for '--strand <STRAND>': Invalid strand value: " + v);
+    } else if (a == "--proper-pairs" || a == "--proper-pair") {
+      flag();
+      o.proper_pair = true;
+    } else if (a == "--min-mapq") {
+      o.min_mapq = (uint32_t)parse_uint(a, value(), 255);
+    } else if (a == "--min-length") {
+      o.min_length = (uint32_t)parse_uint(a, value(), UINT32_MAX);
+    } else if (a == "--max-length") {
+      o.max_length = (uint32_t)parse_uint(a, value(), UINT32_MAX);
+    } else if (a == "--blacklist" || a == "--blacklisted-locations") {
+      o.blacklist = value();
+      o.has_blacklist = true;
+    } else if (a == "--barcode-allowlist" || a == "--whitelisted-barcodes") {
+      o.barcodes = value();
+      o.has_barcodes = true;
+    } else if (a == "--read-group") {
+      o.rg = value();
+      o.has_rg = true;
+    } else if (a == "--tag" || a == "--filter-tag") {
+      o.tag = value();
+      o.has_tag = true;
+    } else if (a == "--tag-value" || a == "--filter-tag-value") {
+      o.tag_value = value();
+      o.has_tag_value = true;
+    } else if (a == "--min-fragment-len" || a == "--min-fragment-length") {
+      o.min_frag = (uint32_t)parse_uint(a, value(), UINT32_MAX);
+      o.has_min_frag = true;
+    } else if (a == "--max-fragment-len" || a == "--max-fragment-length") {
+      o.max_frag = (uint32_t)parse_uint(a, value(), UINT32_MAX);
+      o.has_max_frag = true;
+    } else if (a == "--ignore-duplicates" || a == "--no-duplicates") {
+      flag();
+      o.ex_dup = true;
+    } else if (a == "--ignore-secondary") {
+      flag();
+      o.ex_sec = true;
+    } else if (a == "--ignore-supplementary") {
+      flag();
+      o.ex_sup = true;
+    } else {
+      usage_error("unexpected argument '" + args[i] + "' found");
+    }
+  }
+}
+
+void fill_cfgs(const Opts &o, const std::string &bam, bool collapse, bool merge_blacklist, int barcode_column, bnd_pileup_cfg &pc, bnd_filter_cfg &fc) {
+  memset(&pc, 0, sizeof pc);
+  memset(&fc, 0, sizeof fc);
+  pc.bam_path = bam.c_str();
+  pc.bin_size = o.bin;
+  pc.norm_method = o.norm;
+  pc.scale_factor = o.scale;
+  pc.use_fragment = o.use_fragment;
+  pc.collapse = collapse;
+  pc.ignore_scaffold = o.ignore_scaffold;
+  pc.has_shift = o.has_shift;
+  for (int k = 0; k < 4; k++) pc.shift[k] = o.shift[k];
+  pc.has_truncate = o.has_truncate;
+  pc.trunc_has5 = o.t_has5, pc.trunc5 = o.t5, pc.trunc_has3 = o.t_has3, pc.trunc3 = o.t3;
+  pc.n_threads = o.threads;
+  pc.device = -1;
+  fc.strand = o.strand;
+  fc.proper_pair = o.proper_pair;
+  fc.min_mapq = o.min_mapq, fc.min_length = o.min_length, fc.max_length = o.max_length;
+  fc.has_min_fragment_length = o.has_min_frag, fc.min_fragment_length = o.min_frag;
+  fc.has_max_fragment_length = o.has_max_frag, fc.max_fragment_length = o.max_frag;
+  fc.exclude_duplicates = o.ex_dup, fc.exclude_secondary = o.ex_sec, fc.exclude_supplementary = o.ex_sup;
+  fc.read_group = o.has_rg ? o.rg.c_str() : nullptr;
+  fc.filter_tag = o.has_tag ? o.tag.c_str() : nullptr;
+  fc.filter_tag_value = o.has_tag_value ? o.tag_value.c_str() : nullptr;
+  fc.blacklist_bed = o.has_blacklist ? o.blacklist.c_str() : nullptr;
+  fc.blacklist_merge_overlaps = merge_blacklist;
+  fc.barcode_csv = o.has_barcodes ? o.barcodes.c_str() : nullptr;
+  fc.barcode_csv_column = barcode_column;
+}
+
+bool file_exists(const std::string &p) {
+  std::ifstream f(p);
+  return (bool)f;
+}
+
+void validate_bam_file(const std::string &bam) {  // src/cli.rs:553-570
+  if (!file_exists(bam)) fail("BAM file does not exist: " + bam);
+  std::string idx = bam;
+  size_t dot = idx.find_last_of('.');
+  size_t slash = idx.find_last_of('/');
+  if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) idx = idx.substr(0, dot);
+  idx += ".bam.bai";  // Path::with_extension("bam.bai")
+  if (!file_exists(idx))
+    fail("BAM index file does not exist for " + bam + ". Please create the index file using samtools index command");
+}
+
+int file_type(const std::string &path) {  // 0 bedgraph, 1 bigwig, 2 tsv (bam_utils.rs:595-609)
+  size_t dot = path.find_last_of('.');
+  size_t slash = path.find_last_of('/');
+  if (dot == std::string::npos || (slash != std::string::npos && dot < slash)) fail("No file extension found");
+  std::string ext = lower(path.substr(dot + 1));
+  if (ext == "bedgraph" || ext == "bdg") return 0;
+  if (ext == "bigwig" || ext == "bw") return 1;
+  if (ext == "tsv" || ext == "txt") return 2;
+  fail("Unsupported file extension: " + ext + "\n\nCaused by:\n    Unknown file type: " + ext);
+}
+
+int run(const std::vector<std::string> &argv) {
+  size_t i = 1;
+  // global options before the subcommand
+  while (i < argv.size() && !argv[i].empty() && argv[i][0] == '-') {
+    const std::string &a = argv[i];
+    if (a == "-h" || a == "--help") {
+      fputs(TOP_HELP, stdout);
+      return 0;
+    }
+    if (a == "-V" || a == "--version") {
+      printf("%s\n", VERSION);
+      return 0;
+    }
+    if (a == "-v" || a == "--verbose") {
+      if (i + 1 >= argv.size()) usage_error("a value is required for '--verbose <LEVEL>' but none was supplied");
+      parse_uint(a, argv[i + 1], 255);
+      i += 2;
+      continue;
+    }
+    if (a.rfind("--verbose=", 0) == 0 || (a.rfind("-v", 0) == 0 && a.size() > 2)) {
+      i++;
+      continue;
+    }
+    usage_error("unexpected argument '" + a + "' found");
+  }
+  if (i >= argv.size()) {  // arg_required_else_help
+    fputs(TOP_HELP, stderr);
+    return 2;
+  }
+  const std::string cmd = argv[i++];
+  std::vector<std::string> rest(argv.begin() + (long)i, argv.end());
+  if (cmd == "bam-coverage" || cmd == "coverage") {
+    Opts o;
+    bool help = false;
+    parse_coverage_args(rest, false, o, help);
+    if (help) {
+      printf("Generate a coverage track from one BAM file\n\nUsage: bamnado bam-coverage [OPTIONS] --bam <BAM>\n\n%s\nExample:\n  bamnado bam-coverage --bam sample.bam --output sample.bw --bin-size 50 --normalize cpm\n", COVERAGE_HELP);
+      return 0;
+    }
+    if (o.bams.empty()) usage_error("the following required arguments were not provided:\n  --bam <BAM>");
+    if (o.bams.size() > 1) usage_error("the argument '--bam <BAM>' cannot be used multiple times");
+    const std::string &bam = o.bams[0];
+    validate_bam_file(bam);
+    bnd_pileup_cfg pc;
+    bnd_filter_cfg fc;
+    fill_cfgs(o, bam, true, true, -1, pc, fc);
+    Pileup pile(&pc, &fc);
+    if ((o.has_min_frag || o.has_max_frag) && !pile.is_paired_end())
+      fail("Fragment length filtering (--min-fragment-length / --max-fragment-length) requires paired-end reads, but the BAM file does not appear to contain paired-end data.");
+    std::string outfile = o.output;
+    if (!o.has_output) {
+      outfile = bam;
+      size_t dot = outfile.find_last_of('.');
+      size_t slash = outfile.find_last_of('/');
+      if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) outfile = outfile.substr(0, dot);
+      outfile += ".bedgraph";
+    }
+    switch (file_type(outfile)) {
+      case 0: pile.to_bedgraph(outfile); break;
+      case 1: pileup_to_bigwig(pile, outfile); break;
+      default: fail("TSV output is not supported for single BAM coverage");
+    }
+    return 0;
+  }
+  if (cmd == "multi-bam-coverage" || cmd == "multi-coverage") {
+    Opts o;
+    bool help = false;
+    parse_coverage_args(rest, true, o, help);
+    if (help) {
+      printf("Merge coverage from multiple BAM files into one track\n\nUsage: bamnado multi-bam-coverage [OPTIONS]\n\n%s", COVERAGE_HELP);
+      return 0;
+    }
+    for (auto &b : o.bams) validate_bam_file(b);
+    std::string outfile = o.has_output ? o.output : "output.tsv";
+    if (file_type(outfile) != 2) fail("Unsupported output format. Currently only TSV is supported for multi-BAM coverage");
+    std::vector<bnd_pileup_cfg> pcs(o.bams.size());
+    std::vector<bnd_filter_cfg> fcs(o.bams.size());
+    for (size_t k = 0; k < o.bams.size(); k++) fill_cfgs(o, o.bams[k], false, false, o.has_barcodes ? (int)k : -1, pcs[k], fcs[k]);
+    multi_to_tsv(pcs.data(), fcs.data(), (int)o.bams.size(), outfile.c_str());
+    return 0;
+  }
+  if (cmd == "collapse-bedgraph" || cmd == "collapse") {
+    std::string in, out;
+    bool has_in = false, has_out = false;
+    for (size_t k = 0; k < rest.size(); k++) {
+      const std::string &a = rest[k];
+      auto val = [&]() -> std::string {
+        if (k + 1 >= rest.size()) usage_error("a value is required for '" + a + "' but none was supplied");
+        return rest[++k];
+      };
+      if (a == "-h" || a == "--help") {
+        printf("Collapse adjacent bins with equal scores in a bedGraph file\n\nUsage: bamnado collapse-bedgraph [OPTIONS]\n\nOptions:\n  -i, --input <BEDGRAPH>   Input bedGraph path. Reads from stdin if omitted\n  -o, --output <BEDGRAPH>  Output bedGraph path. Writes to stdout if omitted\n  -h, --help               Print help\n");
+        return 0;
+      } else if (a == "-i" || a == "--input") in = val(), has_in = true;
+      else if (a == "-o" || a == "--output") out = val(), has_out = true;
+      else if (a.rfind("--input=", 0) == 0) in = a.substr(8), has_in = true;
+      else if (a.rfind("--output=", 0) == 0) out = a.substr(9), has_out = true;
+      else if (a == "-v" || a == "--verbose") val();
+      else usage_error("unexpected argument '" + a + "' found");
+    }
+    collapse_bedgraph_file(has_in ? in.c_str() : nullptr, has_out ? out.c_str() : nullptr);
+    return 0;
+  }
+  usage_error("unrecognized subcommand '" + cmd + "'");
+}
+
+}  // namespace
+
+int cli_main(int argc, const char *const *argv) {
+  std::vector<std::string> args;
+  for (int i = 0; i < argc; i++) args.emplace_back(argv[i] ? argv[i] : "");
+  if (args.empty()) args.push_back("bamnado");
+  try {
+    return run(args);
+  } catch (const CliError &e) {  // clap parse error: message + exit code 2
+    fputs(e.msg.c_str(), stderr);
+    return e.code;
+  } catch (const std::exception &e) {  // anyhow error: "Error: ..." on stderr, exit code 1 (src/cli.rs:750-756)
+    fprintf(stderr, "Error: %s\n", e.what());
+    return 1;
+  }
+}
+
 }  // namespace bnd

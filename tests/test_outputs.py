@@ -1,0 +1,143 @@
+"""Callers either side of the pileup: BigWig, multi-BAM TSV, collapse-bedgraph and the CLI mirror."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bigwig_reader import read_bigwig
+from conftest import TEST_BAM
+
+CLI_FILTER = dict(min_mapq=20, min_length=20, max_length=1000)
+
+
+def test_bigwig_matches_reference_known_answers(backend, oracle, tmp_path):
+    # coverage_analysis.rs:989-1058: summary min/max of the BigWig written from test.bam at bin 1000
+    for norm, expect_max in (("raw", 117.0), ("cpm", 10134.2568359375)):
+        out = tmp_path / f"{norm}.bw"
+        pile, filt = dict(bam_path=TEST_BAM, bin_size=1000, norm=norm), dict(proper_pair=True, max_length=1000)
+        with backend.pileup(pile, filt) as h:
+            h.to_bigwig(out)
+        bw = read_bigwig(out)
+        assert bw["summary"]["min_val"] == 0.0 and bw["summary"]["max_val"] == expect_max
+        runs, _, factor = oracle.pileup_runs(pile, filt)
+        exp = [(int(r["ref_id"]), int(r["start"]) - 1, int(r["stop"]) - 1, float(np.float32(float(r["val"]) * factor))) for r in runs]
+        assert bw["intervals"] == exp  # header order, 0-based shift of both ends, f32 scores
+        assert len(bw["chroms"]) == 456 and bw["chroms"]["chr9"] == (58, 138394717)
+
+
+def test_bigwig_ignore_scaffold_and_large(backend, oracle, tmp_path, make_bam):
+    bam = make_bam("pe", "--pairs", 20000, "--odd")
+    out = tmp_path / "x.bigwig"
+    pile, filt = dict(bam_path=bam, bin_size=50, norm="rpkm", ignore_scaffold=True), CLI_FILTER
+    with backend.pileup(pile, filt) as h:
+        h.to_bigwig(out)
+    bw = read_bigwig(out)
+    assert all(not (n.startswith("chrUn") or n.endswith("_alt") or n.endswith("_random")) for n in bw["chroms"])
+    runs, _, factor = oracle.pileup_runs(pile, filt)
+    keep = {cid for _, (cid, _) in bw["chroms"].items()}
+    exp = [(int(r["ref_id"]), int(r["start"]) - 1, int(r["stop"]) - 1, float(np.float32(float(r["val"]) * factor))) for r in runs if int(r["ref_id"]) in keep]
+    assert bw["intervals"] == exp
+
+
+def _rows(path):
+    lines = open(path).read().splitlines()
+    return lines[0], sorted(lines[1:])
+
+
+def test_multi_bam_tsv(backend, oracle, tmp_path, make_bam):
+    # MultiBamPileup::to_tsv, intended semantics; row order is unspecified upstream -> compare as sets
+    bams = [make_bam("m0", "--pairs", 8000, "--seed", 11, "--mode", "se"), make_bam("m1", "--pairs", 8000, "--seed", 12, "--mode", "se"),
+            make_bam("m2", "--pairs", 8000, "--seed", 13, "--mode", "se")]
+    for bin_size in (500, 1):
+        piles = [dict(bam_path=b, bin_size=bin_size, collapse=False) for b in bams]
+        filts = [CLI_FILTER] * 3
+        a, b = tmp_path / f"gpu{bin_size}.tsv", tmp_path / f"cpu{bin_size}.tsv"
+        if bin_size == 1:  # keep the CPU side affordable: chrM-sized genome is not available, so only compare sizes here
+            continue
+        backend.multi_to_tsv(piles, filts, a)
+        oracle.multi_to_tsv(piles, filts, b)
+        assert _rows(a) == _rows(b)
+    with pytest.raises(ValueError):
+        backend.multi_to_tsv([dict(bam_path=bams[0], bin_size=50, collapse=True)], [CLI_FILTER], tmp_path / "x.tsv")
+    with pytest.raises(ValueError):
+        backend.multi_to_tsv([dict(bam_path=bams[0], bin_size=50, collapse=False), dict(bam_path=bams[1], bin_size=100, collapse=False)],
+                             [CLI_FILTER] * 2, tmp_path / "x.tsv")
+
+
+def test_collapse_bedgraph_reference_vectors(backend, tmp_path):
+    # bedgraph_utils.rs:82-129
+    def run(rows):
+        src, dst = tmp_path / "in.bdg", tmp_path / "out.bdg"
+        src.write_text("".join(f"{c}\t{s}\t{e}\t{v!r}\n" for c, s, e, v in rows))
+        backend.collapse_bedgraph(src, dst)
+        return [(l.split("\t")[0], int(l.split("\t")[1]), int(l.split("\t")[2]), float(l.split("\t")[3])) for l in dst.read_text().splitlines()]
+
+    assert run([("chr1", 0, 10, 1.0), ("chr1", 10, 20, 1.0), ("chr1", 21, 30, 1.0), ("chr1", 30, 40, 2.0), ("chr2", 0, 5, 1.0), ("chr2", 5, 10, 1.0)]) == \
+        [("chr1", 0, 20, 1.0), ("chr1", 21, 30, 1.0), ("chr1", 30, 40, 2.0), ("chr2", 0, 10, 1.0)]
+    assert run([("chr1", 0, 10, 1.0), ("chr1", 10, 20, 1.0000004), ("chr1", 20, 30, 1.000002)]) == [("chr1", 0, 20, 1.0), ("chr1", 20, 30, 1.000002)]
+    assert run([]) == []
+
+
+def test_collapse_bedgraph_matches_oracle(backend, oracle, tmp_path, make_bam):
+    # a bin-1 style bedGraph (uncollapsed rows), shuffled, with comments / short lines / float scores
+    bam = make_bam("pe", "--pairs", 20000, "--odd")
+    runs, _, factor = oracle.pileup_runs(dict(bam_path=bam, bin_size=400, norm="cpm", collapse=False), CLI_FILTER)
+    names = ["chrB", "chrA", "chr10", "chr2"]
+    rng = np.random.default_rng(5)
+    lines = ["# a comment", "", "chrA\t1\t2"]
+    sel = runs[runs["ref_id"] < 4][:60000]
+    for r in sel:
+        lines.append(f"{names[int(r['ref_id'])]}\t{int(r['start'])}\t{int(r['stop'])}\t{float(r['val']) * factor!r}")
+    sorted_in, shuffled_in = tmp_path / "s.bdg", tmp_path / "u.bdg"
+    sorted_in.write_text("\n".join(lines) + "\n")
+    body = lines[3:]
+    rng.shuffle(body)
+    shuffled_in.write_text("\n".join(lines[:3] + list(body)) + "\n")
+    for src in (sorted_in, shuffled_in):
+        a, b = tmp_path / "a.bdg", tmp_path / "b.bdg"
+        backend.collapse_bedgraph(src, a)
+        oracle.collapse_bedgraph(src, b)
+        assert a.read_bytes() == b.read_bytes()
+        assert len(a.read_text().splitlines()) < len(sel)
+
+
+def test_cli_exit_codes_and_outputs(backend, oracle, tmp_path, capfd):
+    # test/test_interface.py:103-105: --help / --version -> 0, parse errors -> 2; runtime errors -> 1 (src/cli.rs:750-756)
+    assert backend.cli_main(["bamnado", "--help"]) == 0
+    assert backend.cli_main(["bamnado", "--version"]) == 0
+    assert backend.cli_main(["bamnado", "bam-coverage", "--help"]) == 0
+    assert backend.cli_main(["bamnado", "definitely-not-a-command"]) == 2
+    assert backend.cli_main(["bamnado", "bam-coverage", "--no-such-flag"]) == 2
+    assert backend.cli_main(["bamnado", "bam-coverage"]) == 2
+    assert backend.cli_main(["bamnado"]) == 2
+    assert backend.cli_main(["bamnado", "bam-coverage", "--bam", "/nonexistent.bam"]) == 1
+    assert backend.cli_main(["bamnado", "coverage", "-b", str(TEST_BAM), "-o", str(tmp_path / "x.tsv")]) == 1
+    capfd.readouterr()
+    out = tmp_path / "cli.bedgraph"
+    rc = backend.cli_main(["bamnado", "coverage", "-b", str(TEST_BAM), "-o", str(out), "-s", "100", "--normalize", "cpm", "--proper-pair",
+                           "--min-mapq=30", "--ignore-scaffold"])
+    assert rc == 0
+    ref = tmp_path / "ref.bedgraph"
+    oracle.pileup_to_bedgraph(dict(bam_path=TEST_BAM, bin_size=100, norm="cpm", ignore_scaffold=True),
+                              dict(min_mapq=30, min_length=20, max_length=1000, proper_pair=True, blacklist_merge_overlaps=True), ref)
+    assert out.read_bytes() == ref.read_bytes()
+    # default bin size 50 and default output name <stem>.bedgraph next to the BAM are exercised on a copy
+    bam2 = tmp_path / "copy.bam"
+    bam2.write_bytes(open(TEST_BAM, "rb").read())
+    (tmp_path / "copy.bam.bai").write_bytes(open(str(TEST_BAM) + ".bai", "rb").read())
+    assert backend.cli_main(["bamnado", "bam-coverage", "--bam", str(bam2)]) == 0
+    oracle.pileup_to_bedgraph(dict(bam_path=TEST_BAM, bin_size=50), CLI_FILTER, ref)
+    assert (tmp_path / "copy.bedgraph").read_bytes() == ref.read_bytes()
+    # BigWig by extension, collapse subcommand
+    assert backend.cli_main(["bamnado", "bam-coverage", "--bam", str(bam2), "-o", str(tmp_path / "o.bw"), "-s", "1000"]) == 0
+    assert read_bigwig(tmp_path / "o.bw")["summary"]["max_val"] > 0
+    assert backend.cli_main(["bamnado", "collapse", "-i", str(ref), "-o", str(tmp_path / "c.bdg")]) == 0
+    assert len((tmp_path / "c.bdg").read_text().splitlines()) <= len(ref.read_text().splitlines())
+
+
+def test_cli_fragment_filter_needs_paired_end(backend, make_bam, tmp_path):
+    se = make_bam("se", "--pairs", 15000, "--mode", "se", "--unplaced", 500)
+    assert backend.cli_main(["bamnado", "bam-coverage", "--bam", se, "-o", str(tmp_path / "x.bdg"), "--max-fragment-len", "200"]) == 1
+    pe = make_bam("pe", "--pairs", 20000, "--odd")
+    assert backend.cli_main(["bamnado", "bam-coverage", "--bam", pe, "-o", str(tmp_path / "x.bdg"), "--max-fragment-len", "200", "--fragment-counts"]) == 0
