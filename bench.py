@@ -106,15 +106,16 @@ class ClockSampler:
 
 
 def oracle_sample(bam: Path, threads: int = 0):
-    """CPU oracle on a bounded sample (a few chromosomes of the same BAM) -> (incidences processed, seconds)."""
+    """CPU oracle on a bounded sample (a few chromosomes of the same BAM, pileup + bedGraph written) -> (reads, seconds)."""
     from oracle import oracle_py as o
 
     pile = dict(PILE, bam_path=str(bam), n_threads=threads)
-    n, t0 = 0, time.perf_counter()
-    for c in SAMPLE_CHROMS:
-        _, st = o.pileup_chromosome(pile, FILT, c)
-        n += st["n_total"]
-    return n, time.perf_counter() - t0
+    out = workdir() / "oracle_sample.bedgraph"
+    t0 = time.perf_counter()
+    st, _ = o.pileup_chroms_to_bedgraph(pile, FILT, SAMPLE_CHROMS, out)  # open BAM -> bedGraph of the sample closed
+    dt = time.perf_counter() - t0
+    out.unlink(missing_ok=True)
+    return st["n_total"], dt
 
 
 def run_reference(args, bam: Path, meta: dict):
@@ -132,7 +133,7 @@ def run_reference(args, bam: Path, meta: dict):
         n_tot += n
         t_tot += t
     v = n_tot / t_tot
-    sample = f"pileup_chromosome over {'+'.join(SAMPLE_CHROMS)} of the same BAM per step ({n_tot // max(args.steps, 1)} reads/step)"
+    sample = f"bam-coverage (pileup + bedGraph written) over {'+'.join(SAMPLE_CHROMS)} of the same BAM per step ({n_tot // max(args.steps, 1)} reads/step)"
     line = {
         "impl": "reference", "metric": "bam-coverage reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
@@ -198,7 +199,7 @@ def main():
 
     N = _native.lib()
     pile = dict(PILE, bam_path=str(bam), device=local_rank, shard_rank=rank, shard_world=world)
-    out_path = workdir() / f"out_rank{rank}.bedgraph"
+    out_paths = []
 
     def allreduce_stats(h):
         st = h.stats()
@@ -209,6 +210,8 @@ def main():
 
     # ---- e2e leg: host file -> bedGraph file through the C ABI ----
     def e2e_step():
+        out_path = workdir() / f"out_rank{rank}_{len(out_paths)}.bedgraph"  # a fresh output file per job
+        out_paths.append(out_path)
         with N.pileup(pile, FILT) as h:
             h.accumulate()
             allreduce_stats(h)
@@ -218,6 +221,8 @@ def main():
 
     for _ in range(args.warmup):
         e2e_step()
+    for p in out_paths:
+        p.unlink(missing_ok=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -228,7 +233,9 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    out_bytes = out_path.stat().st_size
+    out_bytes = out_paths[-1].stat().st_size
+    for p in out_paths:
+        p.unlink(missing_ok=True)
 
     # ---- resident leg: compressed bytes already in HBM ----
     h = N.pileup(pile, FILT)
@@ -298,7 +305,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         n, t = oracle_sample(bam)
         cpu = {"value": n / t, "unit": "reads/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"CPU oracle (C++ port of the reference algorithm; Rust toolchain absent) over {'+'.join(SAMPLE_CHROMS)} of the same BAM: {n} reads in {t:.2f} s"}
+               "sample": f"CPU oracle (C++ port of the reference algorithm; Rust toolchain absent), pileup + bedGraph written, over {'+'.join(SAMPLE_CHROMS)} of the same BAM: {n} reads in {t:.2f} s"}
 
     if rank == 0:
         records = meta["records"]

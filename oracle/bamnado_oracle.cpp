@@ -1120,6 +1120,63 @@ int orc_signal_for_chromosome(const orc_pileup_cfg *cfg, const orc_filter_cfg *f
   });
 }
 
+// write_bedgraph (coverage_analysis.rs:43-75): optional scaffold drop, sort by (chrom string, start), one text row per
+// run.  polars serialises CSV chunks on its thread pool, so the rows are formatted in parallel here as well and written
+// in order.
+static void write_bedgraph_rows(const orc_pileup_cfg *cfg, const BamStats &st, const std::vector<Run> &runs, double factor, const char *out_path) {
+  size_t nref = st.header.names.size();
+  std::vector<int> order(nref);
+  for (size_t i = 0; i < nref; i++) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return st.header.names[a] < st.header.names[b]; });
+  std::vector<size_t> first(nref + 1, 0);
+  for (auto &r : runs) first[r.ref_id + 1]++;
+  for (size_t i = 0; i < nref; i++) first[i + 1] += first[i];
+  struct Piece {
+    int rid;
+    size_t lo, hi;
+  };
+  std::vector<Piece> pieces;
+  const size_t CH = 1 << 18;
+  for (int rid : order) {
+    if (cfg->ignore_scaffold && is_scaffold(st.header.names[rid])) continue;
+    for (size_t lo = first[rid]; lo < first[rid + 1]; lo += CH) pieces.push_back(Piece{rid, lo, std::min(first[rid + 1], lo + CH)});
+  }
+  std::vector<std::string> text(pieces.size());
+  int nt = cfg->n_threads > 0 ? cfg->n_threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min<int>(nt, (int)std::max<size_t>(pieces.size(), 1)));
+  std::atomic<size_t> next{0};
+  auto work = [&] {
+    for (;;) {
+      size_t k = next.fetch_add(1);
+      if (k >= pieces.size()) break;
+      const Piece &pc = pieces[k];
+      const std::string &name = st.header.names[pc.rid];
+      std::string &out = text[k];
+      out.reserve((pc.hi - pc.lo) * (name.size() + 32));
+      for (size_t i = pc.lo; i < pc.hi; i++) {
+        const Run &r = runs[i];
+        out += name;
+        out.push_back('\t');
+        out += std::to_string(r.start);
+        out.push_back('\t');
+        out += std::to_string(r.stop);
+        out.push_back('\t');
+        out += fmt_f64((double)r.val * factor);
+        out.push_back('\n');
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; t++) th.emplace_back(work);
+  work();
+  for (auto &t : th) t.join();
+  FileOut fo(out_path);
+  for (auto &t : text) {
+    fo.flush();
+    if (!t.empty()) fwrite(t.data(), 1, t.size(), fo.f);
+  }
+}
+
 int orc_pileup_to_bedgraph(const orc_pileup_cfg *cfg, const orc_filter_cfg *fc, const char *out_path,
                            uint64_t stats[ORC_N_COUNTERS], double *norm_factor) {
   return guarded([&] {
@@ -1127,32 +1184,29 @@ int orc_pileup_to_bedgraph(const orc_pileup_cfg *cfg, const orc_filter_cfg *fc, 
     auto runs = pileup_genome(cfg, fc, stats, &st);
     double factor = scale_factor(cfg->norm_method, cfg->scale_factor, cfg->bin_size, n_after_filtering(stats));
     if (norm_factor) *norm_factor = factor;
-    // write_bedgraph (coverage_analysis.rs:43-75): optional scaffold drop, sort by (chrom string, start)
-    size_t nref = st.header.names.size();
-    std::vector<int> order(nref);
-    for (size_t i = 0; i < nref; i++) order[i] = (int)i;
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return st.header.names[a] < st.header.names[b]; });
-    std::vector<size_t> first(nref + 1, 0);
-    for (auto &r : runs) first[r.ref_id + 1]++;
-    for (size_t i = 0; i < nref; i++) first[i + 1] += first[i];
-    FileOut fo(out_path);
-    std::string line;
-    for (int rid : order) {
-      const std::string &name = st.header.names[rid];
-      if (cfg->ignore_scaffold && is_scaffold(name)) continue;
-      for (size_t i = first[rid]; i < first[rid + 1]; i++) {
-        const Run &r = runs[i];
-        line = name;
-        line.push_back('\t');
-        line += std::to_string(r.start);
-        line.push_back('\t');
-        line += std::to_string(r.stop);
-        line.push_back('\t');
-        line += fmt_f64((double)r.val * factor);
-        line.push_back('\n');
-        fo.put(line);
-      }
+    write_bedgraph_rows(cfg, st, runs, factor, out_path);
+  });
+}
+
+// bench helper: the same job restricted to a few chromosomes (a bounded sample of a large BAM): pileup of their chunks,
+// normalisation from their counters, bedGraph written.
+int orc_pileup_chroms_to_bedgraph(const orc_pileup_cfg *cfg, const orc_filter_cfg *fc, const char *const *chroms, int32_t n_chroms,
+                                  const char *out_path, uint64_t stats[ORC_N_COUNTERS], double *norm_factor) {
+  return guarded([&] {
+    BamStats st = bam_stats_new(cfg->bam_path);
+    auto F = make_filter(fc, st.header);
+    uint64_t L = chunk_length(st, cfg->bin_size);
+    std::vector<Region> regions;
+    for (int i = 0; i < n_chroms; i++) {
+      auto it = st.header.name_to_id.find(chroms[i]);
+      if (it == st.header.name_to_id.end() || !st.in_stats[it->second]) fail(std::string("Chromosome ") + chroms[i] + " not found", 2);
+      chunks_for_ref(st, it->second, L, regions);
     }
+    auto runs = run_chunks(cfg, *F, st, regions);
+    snapshot(*F, stats);
+    double factor = scale_factor(cfg->norm_method, cfg->scale_factor, cfg->bin_size, n_after_filtering(stats));
+    if (norm_factor) *norm_factor = factor;
+    write_bedgraph_rows(cfg, st, runs, factor, out_path);
   });
 }
 

@@ -89,6 +89,9 @@ int orc_signal_for_chromosome(const orc_pileup_cfg *cfg, const orc_filter_cfg *f
 /* to_bedgraph (coverage_analysis.rs:618-632) */
 int orc_pileup_to_bedgraph(const orc_pileup_cfg *cfg, const orc_filter_cfg *f, const char *out_path,
                            uint64_t stats[ORC_N_COUNTERS], double *norm_factor);
+/* bench helper: to_bedgraph restricted to a few chromosomes (bounded sample of a large BAM) */
+int orc_pileup_chroms_to_bedgraph(const orc_pileup_cfg *cfg, const orc_filter_cfg *f, const char *const *chroms, int32_t n_chroms,
+                                  const char *out_path, uint64_t stats[ORC_N_COUNTERS], double *norm_factor);
 /* MultiBamPileup::to_tsv (coverage_analysis.rs:783-864), intended semantics */
 int orc_multi_to_tsv(const orc_pileup_cfg *cfgs, const orc_filter_cfg *filters, int32_t n_bams, const char *out_path);
 /* collapse-bedgraph subcommand (src/cli.rs:1149-1205 + bedgraph_utils.rs:5-45) */

@@ -200,6 +200,16 @@ def pileup_to_bedgraph(pileup: dict, filt: dict, out_path):
     return stats_dict(stats), factor.value
 
 
+def pileup_chroms_to_bedgraph(pileup: dict, filt: dict, chroms: list, out_path):
+    """bench helper: pileup + bedGraph of a few chromosomes only -> (stats dict, factor)"""
+    p, f = make_pileup_cfg(**pileup), make_filter_cfg(**filt)
+    arr = (C.c_char_p * len(chroms))(*[_b(c) for c in chroms])
+    stats = (C.c_uint64 * N_COUNTERS)()
+    factor = C.c_double()
+    _check(lib().orc_pileup_chroms_to_bedgraph(C.byref(p), C.byref(f), arr, len(chroms), _b(out_path), stats, C.byref(factor)))
+    return stats_dict(stats), factor.value
+
+
 def multi_to_tsv(pileups: list, filters: list, out_path):
     n = len(pileups)
     ps = (PileupCfg * n)(*[make_pileup_cfg(**p) for p in pileups])
