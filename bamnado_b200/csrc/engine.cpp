@@ -41,21 +41,85 @@ uint64_t env_u64(const char *name, uint64_t dflt) {
   return strtoull(e, nullptr, 10);
 }
 
+// Device allocations are recycled through a process-wide free list: a coverage job allocates the same few large
+// buffers every time (bin array, run arrays, text), and cudaMalloc / cudaFree of hundreds of MB cost milliseconds and
+// device-wide synchronisation.  Buffers are only released after the work using them has been synchronised.
+struct DevPool {
+  struct Entry {
+    void *p;
+    size_t cap;
+    int device;
+  };
+  std::mutex mu;
+  std::vector<Entry> free_list;
+  size_t held = 0;
+  size_t limit() {
+    static size_t v = env_u64("BND_POOL_BYTES", 32ull << 30);
+    return v;
+  }
+  void *take(size_t n, size_t &cap_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    int best = -1;
+    for (size_t i = 0; i < free_list.size(); i++) {
+      const Entry &e = free_list[i];
+      if (e.device == dev && e.cap >= n && e.cap <= 2 * n + (4u << 20) && (best < 0 || e.cap < free_list[best].cap)) best = (int)i;
+    }
+    if (best < 0) return nullptr;
+    Entry e = free_list[best];
+    free_list.erase(free_list.begin() + best);
+    held -= e.cap;
+    cap_out = e.cap;
+    return e.p;
+  }
+  void give(void *p, size_t cap) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (held + cap <= limit()) {
+        free_list.push_back(Entry{p, cap, dev});
+        held += cap;
+        return;
+      }
+    }
+    cudaFree(p);
+  }
+  void trim() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto &e : free_list) cudaFree(e.p);
+    free_list.clear();
+    held = 0;
+  }
+};
+DevPool g_pool;
+
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
   // grows (never shrinks); the caller guarantees no kernel still uses the old allocation
   void ensure(size_t n) {
     if (n <= cap) return;
-    if (p) CU(cudaFree(p));
-    p = nullptr;
-    cap = 0;
+    release();
+    size_t got = 0;
+    if (void *q = g_pool.take(n, got)) {
+      p = q;
+      cap = got;
+      return;
+    }
     size_t want = n + n / 8 + 256;
-    CU(cudaMalloc(&p, want));
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {  // give cached buffers back to the driver and retry once
+      p = nullptr;
+      cudaGetLastError();
+      g_pool.trim();
+      CU(cudaMalloc(&p, want));
+    }
     cap = want;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) g_pool.give(p, cap);
     p = nullptr;
     cap = 0;
   }

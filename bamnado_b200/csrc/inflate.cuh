@@ -1,22 +1,21 @@
 // inflate.cuh — K1: per-BGZF-block DEFLATE inflate + CRC32 check, hand-written for sm_100a.
 //
 // Replaces noodles-bgzf block decoding (the reference calls it through
-// bam::io::indexed_reader, bamnado/src/coverage_analysis.rs:456-466).  A tile of G lanes owns one BGZF block
-// (<= 64 KiB in, <= 64 KiB out); 32/G tiles share a warp, so 32/G Huffman streams advance per issued instruction.
-// Lane 0 of a tile walks the Huffman stream (funnel-shift bit window, shared-memory lookup tables, arithmetic
-// length/distance bases) and emits a batch of tokens; the whole tile then executes the batch (literal stores,
-// LZ77 copies), and at the end verifies ISIZE and the CRC32 with a lane-interleaved table CRC.
-// ncu (profiles/): the kernel is issue-bound on the serial decode chain, not HBM-bound; there is no GEMM shape in
-// it, so no tensor-core path.
+// bam::io::indexed_reader, bamnado/src/coverage_analysis.rs:456-466).  One warp owns one BGZF block (<= 64 KiB in,
+// <= 64 KiB out).  The Huffman walk is inherently serial, and ncu shows the kernel issue-bound on it (profiles/), so
+// the serial part is kept to the bare dependency chain: lane 0 looks symbols up (funnel-shift bit window, u16
+// shared-memory LUTs whose entries already carry the extra-bit counts), advances the bit position and stores the RAW
+// token (LUT entries + the bit windows holding the extra bits).  Everything else happens once per batch with one
+// token per lane: length/distance reconstruction, output positions by a warp scan, bounds checks, literal stores and
+// LZ77 copies (copies that do not depend on the batch's own matches run concurrently, one match per lane).
+// At the end the warp verifies ISIZE and the CRC32 with a lane-interleaved table CRC.  No GEMM shape, no tensor cores.
 #pragma once
 #include "common.cuh"
 #include "kernel_args.h"
 
 namespace bnd {
 
-constexpr int LIT_BITS = 10;   // primary lookup width for literal/length codes
-constexpr int DIST_BITS = 8;   // primary lookup width for distance codes
-constexpr int NMATCH = 32;     // LZ77 matches queued per batch (literals are stored directly by the decoding lane)
+constexpr int NTOK = 32;       // tokens decoded per batch: one per lane in the parallel half
 
 // Canonical description of one Huffman code, used to build the LUT and to decode codes longer than the LUT width.
 struct HuffCanon {
@@ -25,17 +24,23 @@ struct HuffCanon {
   uint16_t offset[16];  // index into sorted[] of the first symbol of each length
 };
 
-// LUT entries are u16: (symbol << 4) | code length; length 0 = "longer than the LUT width, or invalid".
-struct alignas(16) TileSmem {
-  uint16_t lit_lut[1 << LIT_BITS];
-  uint16_t dist_lut[1 << DIST_BITS];
+// LUT entries are u16.  literal/length: bits 0-3 code length (0 = longer than the LUT width, or invalid), bits 4-6
+// number of extra bits (length symbols), bits 7-15 symbol.  distance: bits 0-3 code length, bits 4-7 extra bits,
+// bits 8-12 symbol.
+// LB / DB: primary lookup widths for literal/length and distance codes.
+template <int LB, int DB>
+struct alignas(16) TileSmemT {
+  static constexpr int LIT_BITS = LB, DIST_BITS = DB;
+  uint16_t lit_lut[1 << LB];
+  uint16_t dist_lut[1 << DB];
   HuffCanon lit_canon, dist_canon;
   uint16_t lit_sorted[288];   // symbols ordered by (length, symbol)
   uint16_t dist_sorted[32];
   uint16_t codes[320];        // canonical code of each symbol (also scratch for the code-length code)
   uint8_t lens[320];          // code lengths of the block being set up (litlen, then distance at 288)
-  uint32_t mtok[NMATCH];      // queued matches: length << 16 | (distance - 1)
-  uint16_t mpos[NMATCH];      // output position of each queued match
+  uint32_t tok[NTOK];         // raw tokens of the batch: literal/length entry | distance entry << 16
+  uint32_t w1[NTOK];          // bit window at the length code (holds its extra bits)
+  uint32_t w2[NTOK];          // bit window at the distance code
 };
 
 // length / distance base values and extra-bit counts (RFC 1951 3.2.5): base | extra_bits << 16, one copy per CTA
@@ -98,10 +103,21 @@ __device__ __forceinline__ bool canon_decode(uint32_t w, int root, const HuffCan
   return false;
 }
 
+__device__ __forceinline__ uint32_t lit_entry(uint32_t sym, uint32_t len) {
+  const uint32_t s = sym - 257;
+  const uint32_t eb = sym < 265 || sym >= 285 ? 0u : (s - 4) >> 2;
+  return (sym << 7) | (eb << 4) | len;
+}
+__device__ __forceinline__ uint32_t dist_entry(uint32_t sym, uint32_t len) {
+  const uint32_t eb = sym < 4 || sym >= 30 ? 0u : (sym >> 1) - 1;
+  return (sym << 8) | (eb << 4) | len;
+}
+
 // Build LUT + canonical tables for `n` symbols whose lengths are in S.lens[base .. base+n).
 // Returns false on an over-subscribed code.
-template <int G>
+template <int G, class TileSmem>
 __device__ bool build_tables(const Tile<G> &tile, TileSmem &S, int base, int n, int kind) {
+  constexpr int LIT_BITS = TileSmem::LIT_BITS, DIST_BITS = TileSmem::DIST_BITS;
   const int lane = tile.lane;
   HuffCanon &C = kind == 0 ? S.lit_canon : S.dist_canon;
   uint16_t *sorted = kind == 0 ? S.lit_sorted : S.dist_sorted;
@@ -146,7 +162,7 @@ __device__ bool build_tables(const Tile<G> &tile, TileSmem &S, int base, int n, 
     int l = S.lens[base + s];
     if (l == 0 || l > bits) continue;
     uint32_t rev = __brev((uint32_t)S.codes[base + s]) >> (32 - l);
-    uint16_t e = (uint16_t)((s << 4) | l);
+    uint16_t e = (uint16_t)(kind == 0 ? lit_entry((uint32_t)s, (uint32_t)l) : dist_entry((uint32_t)s, (uint32_t)l));
     for (uint32_t i = rev; i < (1u << bits); i += (1u << l)) lut[i] = e;
   }
   tile.sync();
@@ -189,9 +205,10 @@ __device__ uint32_t tile_crc32(const Tile<G> &tile, const uint8_t *out, uint32_t
 }
 
 // Inflate one BGZF block with a tile of G lanes.  Returns a status code (same on every lane).
-template <int G>
+template <int G, class TileSmem>
 __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &T, const uint8_t *blk, uint32_t blk_size,
                              uint8_t *out, uint32_t isize_expected, const CrcTables *crcT, int verify_crc) {
+  constexpr int LIT_BITS = TileSmem::LIT_BITS, DIST_BITS = TileSmem::DIST_BITS;
   const int lane = tile.lane;
   if (blk_size < 26) return INF_BAD_HEADER;
   uint32_t xlen = blk[10] | ((uint32_t)blk[11] << 8);
@@ -348,72 +365,52 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
       }
       tile.sync();
     }
-    if (!build_tables<G>(tile, S, 0, 288, 0) || !build_tables<G>(tile, S, 288, 32, 1)) {
+    if (!build_tables<G, TileSmem>(tile, S, 0, 288, 0) || !build_tables<G, TileSmem>(tile, S, 288, 32, 1)) {
       status = INF_BAD_CODELEN;
       break;
     }
 
-    // ---- symbol loop: lane 0 decodes; it stores literals itself and queues matches, the tile executes the queue ----
+    // ---- symbol loop: lane 0 walks the stream and stores raw tokens; the warp finishes the batch, one token per lane ----
     bool eob = false;
     while (!eob && status == INF_OK) {
-      int nm = 0;
+      int ntok = 0;
       int st = INF_OK;
       if (lane == 0) {
-        uint32_t op = outpos;
-        // a token produces at most 258 bytes: `tmax` tokens need no per-token output bound checks; the last few
-        // hundred bytes of a block are decoded one token at a time with the checks on
-        uint32_t tmax = (isize - op) / 258u;
-        const bool careful = tmax == 0;
-        tmax = careful ? 1u : (tmax > (uint32_t)NMATCH ? (uint32_t)NMATCH : tmax);
-        uint32_t t = 0;
-        bool stop = false;
 #pragma unroll 1
         do {
           uint32_t w = br.window();
           uint32_t e = S.lit_lut[w & ((1u << LIT_BITS) - 1u)];
-          uint32_t len = e & 15u, sym = e >> 4;
-          if (len == 0 && !canon_decode(w, LIT_BITS, S.lit_canon, S.lit_sorted, sym, len)) {
-            st = INF_BAD_SYMBOL;
-            stop = true;
-          } else if (sym < 256) {
-            if (careful && op >= isize) {
-              st = INF_OUTPUT_OVERRUN;
-              stop = true;
-            } else {
-              out[op++] = (uint8_t)sym;
-              br.consume(len);
+          if ((e & 15u) == 0) {  // rare: code longer than the lookup width
+            uint32_t sym, len;
+            if (!canon_decode(w, LIT_BITS, S.lit_canon, S.lit_sorted, sym, len)) {
+              st = INF_BAD_SYMBOL;
+              break;
             }
-          } else if (sym == 256) {
-            br.consume(len);
-            eob = true;
-            stop = true;
-          } else {
-            const uint32_t lt = T.len_tab[(sym - 257) & 31u];  // 0 marks the invalid symbols 286, 287
-            uint32_t eb = lt >> 16;
-            uint32_t length = (lt & 0xffffu) + ((w >> len) & ~(0xffffffffu << eb));
-            br.consume(len + eb);
+            e = lit_entry(sym, len);
+          }
+          br.consume((e & 15u) + ((e >> 4) & 7u));
+          if (e >= (256u << 7)) {
+            if ((e >> 7) == 256u) {
+              eob = true;
+              break;
+            }
+            S.w1[ntok] = w;
             w = br.window();
             uint32_t d = S.dist_lut[w & ((1u << DIST_BITS) - 1u)];
-            uint32_t dl = d & 15u, ds = d >> 4;
-            bool ok = lt != 0;
-            if (dl == 0) ok = ok && canon_decode(w, DIST_BITS, S.dist_canon, S.dist_sorted, ds, dl);
-            const uint32_t dt = T.dist_tab[ds & 31u];  // 0 marks the invalid symbols 30, 31
-            uint32_t deb = dt >> 16;
-            uint32_t dist = (dt & 0xffffu) + ((w >> dl) & ~(0xffffffffu << deb));
-            br.consume(dl + deb);
-            ok = ok && dt != 0 && dist <= op && !(careful && op + length > isize);
-            if (!ok) {
-              st = lt == 0 ? INF_BAD_SYMBOL : (careful && op + length > isize && dt != 0 && dist <= op) ? INF_OUTPUT_OVERRUN : INF_BAD_DISTANCE;
-              stop = true;
-            } else {
-              S.mtok[nm] = (length << 16) | (dist - 1);  // dist - 1 fits 15 bits
-              S.mpos[nm] = (uint16_t)op;
-              op += length;
-              nm++;
+            if ((d & 15u) == 0) {  // rare
+              uint32_t ds, dl;
+              if (!canon_decode(w, DIST_BITS, S.dist_canon, S.dist_sorted, ds, dl)) {
+                st = INF_BAD_DISTANCE;
+                break;
+              }
+              d = dist_entry(ds, dl);
             }
+            S.w2[ntok] = w;
+            br.consume((d & 15u) + ((d >> 4) & 15u));
+            e |= d << 16;
           }
-        } while (!stop && ++t < tmax);
-        outpos = op;
+          S.tok[ntok] = e;
+        } while (++ntok < NTOK);
         if (st == INF_OK && br.overrun()) st = INF_INPUT_OVERRUN;
       }
       st = tile.shfl(st, 0);
@@ -421,38 +418,100 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
         status = st;
         break;
       }
-      nm = tile.shfl(nm, 0);
+      ntok = tile.shfl(ntok, 0);
       eob = tile.shfl((int)eob, 0) != 0;
-      outpos = tile.shfl(outpos, 0);
-      tile.sync();  // literals and the queue are visible to the whole tile
-      // ---- execute the queued matches in stream order ----
+      tile.sync();
+      // ---- parallel half: lane t finishes token t ----
+      for (int tbase = 0; tbase < ntok; tbase += G) {
+        const int ti = tbase + lane;
+        const bool mine = ti < ntok;
+        const uint32_t tk = mine ? S.tok[ti] : 0u;
+        const uint32_t sym = (tk >> 7) & 0x1ffu;
+        const bool is_match = mine && sym > 256;
+        uint32_t length = 0, dist = 1;
+        bool bad = false;
+        if (is_match) {
+          const uint32_t lt = T.len_tab[(sym - 257) & 31u];   // 0 marks the invalid symbols 286, 287
+          const uint32_t dt = T.dist_tab[(tk >> 24) & 31u];   // 0 marks the invalid symbols 30, 31
+          const uint32_t eb = (tk >> 4) & 7u, deb = (tk >> 20) & 15u;
+          length = (lt & 0xffffu) + ((S.w1[ti] >> (tk & 15u)) & ~(0xffffffffu << eb));
+          dist = (dt & 0xffffu) + ((S.w2[ti] >> ((tk >> 16) & 15u)) & ~(0xffffffffu << deb));
+          bad = lt == 0 || dt == 0;
+        }
+        const uint32_t olen = is_match ? length : (mine ? 1u : 0u);
+        uint32_t incl = olen;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+          uint32_t v = tile.shfl_up(incl, d);
+          if (lane >= d) incl += v;
+        }
+        const uint32_t total = tile.shfl(incl, G - 1);
+        const uint32_t mypos = outpos + incl - olen;
+        bad = bad || (is_match && dist > mypos);
+        const uint32_t badmask = tile.ballot(bad);
+        if (badmask) {
+          const uint32_t bsym = tile.shfl(sym, __ffs((int)badmask) - 1);
+          status = bsym > 285 ? INF_BAD_SYMBOL : INF_BAD_DISTANCE;
+          break;
+        }
+        if (outpos + total > isize) {
+          status = INF_OUTPUT_OVERRUN;
+          break;
+        }
+        if (mine && !is_match) out[mypos] = (uint8_t)sym;
+        const uint32_t mmask = tile.ballot(is_match);
+        if (mmask) {
+          // ~96 % of the matches of a batch read only bytes produced before the batch's first match, so they do not
+          // depend on each other: those (<= 16 bytes) are copied concurrently, one per lane, all loads before the
+          // stores, and their L2/DRAM round trips overlap.  The others follow in stream order, the whole tile per match.
+          const uint32_t first = tile.shfl(mypos, __ffs((int)mmask) - 1);
+          const bool par = is_match && length <= 16 && mypos - dist + length <= first;
+          tile.sync();  // this round's literals are visible
+          if (par) {
+            const uint8_t *src = out + mypos - dist;
+            uint8_t *dst = out + mypos;
+            uint8_t buf[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+              if ((uint32_t)i < length) buf[i] = src[i];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+              if ((uint32_t)i < length) dst[i] = buf[i];
+          }
+          uint32_t later = tile.ballot(is_match && !par);
+          tile.sync();
 #pragma unroll 1
-      for (int k = 0; k < nm; k++) {
-        const uint32_t mt = S.mtok[k];
-        const uint32_t mp = S.mpos[k];
-        const uint32_t len = mt >> 16, dist = (mt & 0x7fffu) + 1;
-        const uint8_t *src = out + mp - dist;
-        uint8_t *dst = out + mp;
-        if (dist >= len) {
-          // disjoint source and destination
-          for (uint32_t i = lane; i < len; i += G) dst[i] = src[i];
-        } else if (dist >= (uint32_t)G) {
-          // overlapping with a period of at least one pass: a pass only reads bytes of earlier passes
-          for (uint32_t b = 0; b < len; b += G) {
-            uint32_t i = b + lane;
-            if (i < len) dst[i] = src[i];
+          while (later) {
+            const int sl = __ffs((int)later) - 1;
+            later &= later - 1;
+            const uint32_t len = tile.shfl(length, sl), dd = tile.shfl(dist, sl), mp = tile.shfl(mypos, sl);
+            const uint8_t *src = out + mp - dd;
+            uint8_t *dst = out + mp;
+            if (dd >= len) {
+              // disjoint source and destination
+              for (uint32_t i = lane; i < len; i += G) dst[i] = src[i];
+            } else if (dd >= (uint32_t)G) {
+              // overlapping with a period of at least one pass: a pass only reads bytes of earlier passes
+              for (uint32_t b = 0; b < len; b += G) {
+                uint32_t i = b + lane;
+                if (i < len) dst[i] = src[i];
+                tile.sync();
+              }
+            } else {
+              // short period: every output byte i equals src[i % dist]
+              uint32_t r = (uint32_t)lane % dd, step = (uint32_t)G % dd;
+              for (uint32_t i = lane; i < len; i += G) {
+                dst[i] = src[r];
+                r += step;
+                if (r >= dd) r -= dd;
+              }
+            }
             tile.sync();
           }
         } else {
-          // short period: every output byte i equals src[i % dist]
-          uint32_t r = (uint32_t)lane % dist, step = (uint32_t)G % dist;
-          for (uint32_t i = lane; i < len; i += G) {
-            dst[i] = src[r];
-            r += step;
-            if (r >= dist) r -= dist;
-          }
+          tile.sync();
         }
-        tile.sync();
+        outpos += total;
       }
     }
   }
@@ -465,8 +524,9 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
   return status;
 }
 
-template <int G, int THREADS, int MIN_CTAS>
+template <int G, int THREADS, int MIN_CTAS, int LB, int DB>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) bgzf_inflate_kernel(InflateArgs a) {
+  using TileSmem = TileSmemT<LB, DB>;
   BND_DYN_SMEM(smem_raw);
   constexpr int GROUPS = THREADS / G;
   TileSmem *tiles = reinterpret_cast<TileSmem *>(smem_raw);
@@ -497,7 +557,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) bgzf_inflate_kernel(Inflate
     if (b >= a.n_blocks) break;
     uint64_t c0 = a.blk_coff[b], c1 = a.blk_coff[b + 1];
     uint64_t u0 = a.blk_uoff[b], u1 = a.blk_uoff[b + 1];
-    int st = inflate_block<G>(tile, S, *sym_s, a.comp + c0, (uint32_t)(c1 - c0), a.out + u0, (uint32_t)(u1 - u0), crc_s, a.verify_crc);
+    int st = inflate_block<G, TileSmem>(tile, S, *sym_s, a.comp + c0, (uint32_t)(c1 - c0), a.out + u0, (uint32_t)(u1 - u0), crc_s, a.verify_crc);
     if (tile.lane == 0) {
       if (a.status) a.status[b] = st;
       if (st != INF_OK) atomicCAS(a.error_flag, 0, st | ((int)(b & 0xffffff) << 8));
@@ -506,6 +566,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) bgzf_inflate_kernel(Inflate
   }
 }
 
-constexpr size_t inflate_smem_bytes(int groups) { return sizeof(TileSmem) * (size_t)groups + sizeof(CrcTables) + sizeof(SymTables); }
+template <int LB, int DB>
+constexpr size_t inflate_smem_bytes(int groups) {
+  return sizeof(TileSmemT<LB, DB>) * (size_t)groups + sizeof(CrcTables) + sizeof(SymTables);
+}
 
 }  // namespace bnd

@@ -39,8 +39,8 @@ namespace {
 struct InflateVariant {
   int g, threads, ctas_per_sm;
 };
-// lane-group width / CTA size / resident CTAs per SM; selected with BND_INFLATE_VARIANT (default 0)
-const InflateVariant kVariants[] = {{32, 128, 9}, {32, 256, 5}, {32, 512, 2}, {16, 256, 2}, {16, 128, 5}, {8, 384, 1}, {32, 192, 6}};
+// lane-group width / CTA size / resident CTAs per SM (and LUT widths below); selected with BND_INFLATE_VARIANT
+const InflateVariant kVariants[] = {{32, 128, 9}, {32, 256, 5}, {32, 128, 12}, {32, 256, 6}, {32, 128, 10}, {32, 512, 2}};
 int variant_index() {
   static int v = -1;
   if (v < 0) {
@@ -50,11 +50,11 @@ int variant_index() {
   }
   return v;
 }
-template <int G, int T, int MINB>
+template <int G, int T, int MINB, int LB, int DB>
 cudaError_t launch_inflate_t(const InflateArgs &a, int sm_count, int ctas_per_sm, cudaStream_t s) {
-  auto kern = bgzf_inflate_kernel<G, T, MINB>;
+  auto kern = bgzf_inflate_kernel<G, T, MINB, LB, DB>;
   constexpr int groups = T / G;
-  const size_t smem = inflate_smem_bytes(groups);
+  const size_t smem = inflate_smem_bytes<LB, DB>(groups);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -89,13 +89,12 @@ cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_blocks == 0) return cudaSuccess;
   const InflateVariant &v = kVariants[variant_index()];
   switch (variant_index()) {
-    case 1: return launch_inflate_t<32, 256, 5>(a, sm_count, v.ctas_per_sm, s);
-    case 2: return launch_inflate_t<32, 512, 2>(a, sm_count, v.ctas_per_sm, s);
-    case 3: return launch_inflate_t<16, 256, 2>(a, sm_count, v.ctas_per_sm, s);
-    case 4: return launch_inflate_t<16, 128, 5>(a, sm_count, v.ctas_per_sm, s);
-    case 5: return launch_inflate_t<8, 384, 1>(a, sm_count, v.ctas_per_sm, s);
-    case 6: return launch_inflate_t<32, 192, 6>(a, sm_count, v.ctas_per_sm, s);
-    default: return launch_inflate_t<32, 128, 9>(a, sm_count, v.ctas_per_sm, s);
+    case 1: return launch_inflate_t<32, 256, 5, 10, 8>(a, sm_count, v.ctas_per_sm, s);
+    case 2: return launch_inflate_t<32, 128, 12, 9, 7>(a, sm_count, v.ctas_per_sm, s);  // 48 warps / SM, <= 40 registers
+    case 3: return launch_inflate_t<32, 256, 6, 9, 7>(a, sm_count, v.ctas_per_sm, s);
+    case 4: return launch_inflate_t<32, 128, 10, 10, 8>(a, sm_count, v.ctas_per_sm, s);
+    case 5: return launch_inflate_t<32, 512, 2, 10, 8>(a, sm_count, v.ctas_per_sm, s);
+    default: return launch_inflate_t<32, 128, 9, 10, 8>(a, sm_count, v.ctas_per_sm, s);
   }
 }
 

@@ -52,9 +52,14 @@ struct Bar {
   unsigned gen = 0;
 };
 struct Warp {
-  uint64_t slot[2][32];
-  Bar bar[32];
+  uint64_t slot[6][2][32];
+  Bar bar[32][6];  // keyed by (lowest lane of the mask, log2 of its population): masks of different sizes may share a leader
 };
+inline int mask_class(unsigned mask) {
+  int n = __builtin_popcount(mask), c = 0;
+  while ((1 << c) < n) c++;
+  return c > 5 ? 5 : c;
+}
 struct Cta {
   uint3 bid;
   dim3 bdim, gdim;
@@ -107,12 +112,12 @@ inline T from_bits(uint64_t b) {
 template <class T>
 inline const uint64_t *exchange(unsigned mask, T v) {
   Warp &w = my_warp();
-  int leader = __builtin_ffs((int)mask) - 1;
-  Bar &b = w.bar[leader];
+  int leader = __builtin_ffs((int)mask) - 1, cls = mask_class(mask);
+  Bar &b = w.bar[leader][cls];
   int par = (int)(b.gen & 1);
-  w.slot[par][cur->lane] = to_bits(v);
+  w.slot[cls][par][cur->lane] = to_bits(v);
   bar_wait(b, __builtin_popcount(mask));
-  return w.slot[par];
+  return w.slot[cls][par];
 }
 }  // namespace emul
 
@@ -164,7 +169,7 @@ inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred
 inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) {
   emul::Warp &w = emul::my_warp();
-  emul::bar_wait(w.bar[__builtin_ffs((int)mask) - 1], __builtin_popcount(mask));
+  emul::bar_wait(w.bar[__builtin_ffs((int)mask) - 1][emul::mask_class(mask)], __builtin_popcount(mask));
 }
 
 // ---- CTA barriers ----------------------------------------------------------------------------------------------
