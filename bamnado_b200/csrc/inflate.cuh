@@ -24,9 +24,9 @@ struct HuffCanon {
   uint16_t offset[16];  // index into sorted[] of the first symbol of each length
 };
 
-// LUT entries are u16.  literal/length: bits 0-3 code length (0 = longer than the LUT width, or invalid), bits 4-6
-// number of extra bits (length symbols), bits 7-15 symbol.  distance: bits 0-3 code length, bits 4-7 extra bits,
-// bits 8-12 symbol.
+// LUT entries are u16: bits 0-4 = bits to consume (code length + extra bits; 0 = code longer than the LUT width, or
+// invalid), symbol from bit 7 (literal/length) or bit 8 (distance).  The serial walk only needs that sum; code length
+// and extra-bit count are separated again in the parallel half (the extra-bit count is a function of the symbol).
 // LB / DB: primary lookup widths for literal/length and distance codes.
 template <int LB, int DB>
 struct alignas(16) TileSmemT {
@@ -38,9 +38,9 @@ struct alignas(16) TileSmemT {
   uint16_t dist_sorted[32];
   uint16_t codes[320];        // canonical code of each symbol (also scratch for the code-length code)
   uint8_t lens[320];          // code lengths of the block being set up (litlen, then distance at 288)
-  uint32_t tok[NTOK];         // raw tokens of the batch: literal/length entry | distance entry << 16
-  uint32_t w1[NTOK];          // bit window at the length code (holds its extra bits)
-  uint32_t w2[NTOK];          // bit window at the distance code
+  // raw tokens of the batch: [0, NTOK) literal/length entry | distance entry << 16; [NTOK, 2 NTOK) bit window at the
+  // length code (holds its extra bits); [2 NTOK, 3 NTOK) bit window at the distance code
+  uint32_t raw[3 * NTOK];
 };
 
 // length / distance base values and extra-bit counts (RFC 1951 3.2.5): base | extra_bits << 16, one copy per CTA
@@ -106,11 +106,11 @@ __device__ __forceinline__ bool canon_decode(uint32_t w, int root, const HuffCan
 __device__ __forceinline__ uint32_t lit_entry(uint32_t sym, uint32_t len) {
   const uint32_t s = sym - 257;
   const uint32_t eb = sym < 265 || sym >= 285 ? 0u : (s - 4) >> 2;
-  return (sym << 7) | (eb << 4) | len;
+  return (sym << 7) | (len + eb);
 }
 __device__ __forceinline__ uint32_t dist_entry(uint32_t sym, uint32_t len) {
   const uint32_t eb = sym < 4 || sym >= 30 ? 0u : (sym >> 1) - 1;
-  return (sym << 8) | (eb << 4) | len;
+  return (sym << 8) | (len + eb);
 }
 
 // Build LUT + canonical tables for `n` symbols whose lengths are in S.lens[base .. base+n).
@@ -376,11 +376,13 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
       int ntok = 0;
       int st = INF_OK;
       if (lane == 0) {
+        uint32_t *tp = S.raw;
+        uint32_t *const tend = S.raw + NTOK;
 #pragma unroll 1
         do {
           uint32_t w = br.window();
           uint32_t e = S.lit_lut[w & ((1u << LIT_BITS) - 1u)];
-          if ((e & 15u) == 0) {  // rare: code longer than the lookup width
+          if ((e & 31u) == 0) {  // rare: code longer than the lookup width
             uint32_t sym, len;
             if (!canon_decode(w, LIT_BITS, S.lit_canon, S.lit_sorted, sym, len)) {
               st = INF_BAD_SYMBOL;
@@ -388,16 +390,16 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
             }
             e = lit_entry(sym, len);
           }
-          br.consume((e & 15u) + ((e >> 4) & 7u));
+          br.consume(e & 31u);
           if (e >= (256u << 7)) {
-            if ((e >> 7) == 256u) {
+            if (e < (257u << 7)) {
               eob = true;
               break;
             }
-            S.w1[ntok] = w;
+            tp[NTOK] = w;
             w = br.window();
             uint32_t d = S.dist_lut[w & ((1u << DIST_BITS) - 1u)];
-            if ((d & 15u) == 0) {  // rare
+            if ((d & 31u) == 0) {  // rare
               uint32_t ds, dl;
               if (!canon_decode(w, DIST_BITS, S.dist_canon, S.dist_sorted, ds, dl)) {
                 st = INF_BAD_DISTANCE;
@@ -405,12 +407,13 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
               }
               d = dist_entry(ds, dl);
             }
-            S.w2[ntok] = w;
-            br.consume((d & 15u) + ((d >> 4) & 15u));
+            tp[2 * NTOK] = w;
+            br.consume(d & 31u);
             e |= d << 16;
           }
-          S.tok[ntok] = e;
-        } while (++ntok < NTOK);
+          *tp++ = e;
+        } while (tp != tend);
+        ntok = (int)(tp - S.raw);
         if (st == INF_OK && br.overrun()) st = INF_INPUT_OVERRUN;
       }
       st = tile.shfl(st, 0);
@@ -425,7 +428,7 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
       for (int tbase = 0; tbase < ntok; tbase += G) {
         const int ti = tbase + lane;
         const bool mine = ti < ntok;
-        const uint32_t tk = mine ? S.tok[ti] : 0u;
+        const uint32_t tk = mine ? S.raw[ti] : 0u;
         const uint32_t sym = (tk >> 7) & 0x1ffu;
         const bool is_match = mine && sym > 256;
         uint32_t length = 0, dist = 1;
@@ -433,9 +436,10 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
         if (is_match) {
           const uint32_t lt = T.len_tab[(sym - 257) & 31u];   // 0 marks the invalid symbols 286, 287
           const uint32_t dt = T.dist_tab[(tk >> 24) & 31u];   // 0 marks the invalid symbols 30, 31
-          const uint32_t eb = (tk >> 4) & 7u, deb = (tk >> 20) & 15u;
-          length = (lt & 0xffffu) + ((S.w1[ti] >> (tk & 15u)) & ~(0xffffffffu << eb));
-          dist = (dt & 0xffffu) + ((S.w2[ti] >> ((tk >> 16) & 15u)) & ~(0xffffffffu << deb));
+          const uint32_t eb = lt >> 16, deb = dt >> 16;
+          const uint32_t len_bits = (tk & 31u) - eb, dist_bits = ((tk >> 16) & 31u) - deb;  // code lengths
+          length = (lt & 0xffffu) + ((S.raw[NTOK + ti] >> len_bits) & ~(0xffffffffu << eb));
+          dist = (dt & 0xffffu) + ((S.raw[2 * NTOK + ti] >> dist_bits) & ~(0xffffffffu << deb));
           bad = lt == 0 || dt == 0;
         }
         const uint32_t olen = is_match ? length : (mine ? 1u : 0u);
