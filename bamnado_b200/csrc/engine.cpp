@@ -196,7 +196,7 @@ DeviceCtx &ctx_for(int device) {
   c->seg_bytes = env_u64("BND_SEGMENT_BYTES", 96ull << 20);
   c->carry_cap = env_u64("BND_CARRY_BYTES", 8ull << 20);
   c->carry_cap = (c->carry_cap + REC_TILE - 1) / REC_TILE * REC_TILE;
-  c->n_readers = (int)env_u64("BND_READERS", 4);
+  c->n_readers = (int)env_u64("BND_READERS", 8);
   int n_slots = (int)env_u64("BND_STAGES", 4);
   if (n_slots < 2) n_slots = 2;
   c->slots.resize(n_slots);
@@ -222,10 +222,15 @@ struct Segment {
 };
 
 // ---- reader pool: file bytes -> pinned staging slots, plus the BGZF block table of each segment --------------------
+// A segment is read in pieces by all reader threads at once (a single pread stream out of the page cache runs at only
+// ~3 GB/s on the B200 hosts, far below the 55 GB/s of the H2D copy that follows); the thread that finishes a segment's
+// last piece walks its BGZF block chain.
 struct ReaderPool {
+  static constexpr uint64_t PIECE = 8ull << 20;
   struct Job {
     size_t seg;
     int slot;
+    uint64_t off, len;  // piece inside the segment
   };
   int fd;
   DeviceCtx &ctx;
@@ -233,11 +238,11 @@ struct ReaderPool {
   std::mutex mu;
   std::condition_variable cv_job, cv_done;
   std::deque<Job> jobs;
-  std::vector<char> done;  // per segment
+  std::vector<char> done;          // per segment
+  std::vector<uint32_t> remaining; // pieces still being read, per segment
   std::string error;
   bool stop = false;
   std::vector<std::thread> threads;
-  double read_ms = 0;
 
   ReaderPool(int fd_, DeviceCtx &c, const std::vector<Segment> &s, int n_threads) : fd(fd_), ctx(c), segs(s) {
     for (int i = 0; i < n_threads; i++) threads.emplace_back([this] { work(); });
@@ -251,12 +256,19 @@ struct ReaderPool {
     for (auto &t : threads) t.join();
   }
   void submit(size_t seg, int slot) {
+    const uint64_t len = segs[seg].end - segs[seg].begin;
     {
       std::lock_guard<std::mutex> g(mu);
-      if (done.size() <= seg) done.resize(seg + 1, 0);
-      jobs.push_back(Job{seg, slot});
+      if (done.size() <= seg) done.resize(seg + 1, 0), remaining.resize(seg + 1, 0);
+      uint32_t n = 0;
+      for (uint64_t off = 0; off < len || n == 0; off += PIECE) {
+        jobs.push_back(Job{seg, slot, off, std::min<uint64_t>(PIECE, len - off)});
+        n++;
+        if (len == 0) break;
+      }
+      remaining[seg] = n;
     }
-    cv_job.notify_one();
+    cv_job.notify_all();
   }
   void wait(size_t seg) {
     std::unique_lock<std::mutex> g(mu);
@@ -274,30 +286,42 @@ struct ReaderPool {
         jobs.pop_front();
       }
       std::string err;
-      double t0 = now_ms();
+      bool last = false;
+      const Segment &s = segs[j.seg];
+      StageSlot &slot = ctx.slots[j.slot];
       try {
-        const Segment &s = segs[j.seg];
-        StageSlot &slot = ctx.slots[j.slot];
-        const uint64_t len = s.end - s.begin;
         uint64_t got = 0;
-        while (got < len) {
-          ssize_t r = pread(fd, slot.pin + got, len - got, (off_t)(s.begin + got));
+        while (got < j.len) {
+          ssize_t r = pread(fd, slot.pin + j.off + got, j.len - got, (off_t)(s.begin + j.off + got));
           if (r < 0) fail("read error on BAM file");
           if (r == 0) fail("unexpected end of BAM file");
           got += (uint64_t)r;
         }
-        scan_bgzf_blocks(slot.pin, len, slot.tab);
-        if (slot.tab.coff.back() != len) fail("BAM segment does not end on a BGZF block boundary (corrupt file or index)");
       } catch (const std::exception &e) {
         err = e.what();
       }
       {
         std::lock_guard<std::mutex> g(mu);
         if (!err.empty() && error.empty()) error = err;
-        done[j.seg] = 1;
-        read_ms += now_ms() - t0;
+        last = --remaining[j.seg] == 0;
       }
-      cv_done.notify_all();
+      if (last) {
+        try {
+          const uint64_t len = s.end - s.begin;
+          scan_bgzf_blocks(slot.pin, len, slot.tab);
+          if (slot.tab.coff.back() != len) fail("BAM segment does not end on a BGZF block boundary (corrupt file or index)");
+        } catch (const std::exception &e) {
+          err = e.what();
+        }
+        {
+          std::lock_guard<std::mutex> g(mu);
+          if (!err.empty() && error.empty()) error = err;
+          done[j.seg] = 1;
+        }
+        cv_done.notify_all();
+      } else if (!err.empty()) {
+        cv_done.notify_all();
+      }
     }
   }
 };
@@ -668,8 +692,12 @@ void Pileup::run_pass(const Range &range, bool resident) {
   // ---- plan segments: cut at block starts known from the index ----
   std::vector<Segment> segs;
   const std::vector<uint64_t> &cp = im.cut_points;
-  auto next_cut = [&](uint64_t cur, uint64_t limit) -> uint64_t {  // a block start in (cur, limit], as far as seg_bytes allows
-    uint64_t target = cur + ctx.seg_bytes;
+  // optional ramp of the segment sizes (BND_FIRST_SEGMENT_BYTES, doubling up to seg_bytes); measured slower on B200
+  // than uniform segments because small launches leave the SMs latency-bound, so it is off by default
+  uint64_t ramp = std::min<uint64_t>(ctx.seg_bytes, env_u64("BND_FIRST_SEGMENT_BYTES", ctx.seg_bytes));
+  auto next_cut = [&](uint64_t cur, uint64_t limit) -> uint64_t {  // a block start in (cur, limit], as far as the target allows
+    uint64_t target = cur + ramp;
+    ramp = std::min<uint64_t>(ctx.seg_bytes, ramp * 2);
     if (target >= limit) return limit;
     auto it = std::upper_bound(cp.begin(), cp.end(), target);  // first > target
     if (it != cp.begin()) {
@@ -691,17 +719,20 @@ void Pileup::run_pass(const Range &range, bool resident) {
 
   const int n_slots = (int)ctx.slots.size();
   std::unique_ptr<ReaderPool> pool;
+  double dbg_wait_read = 0, dbg_wait_h2d = 0, dbg_sync = 0;
   auto submit = [&](size_t i) {
     StageSlot &slot = ctx.slots[i % n_slots];
     if (slot.h2d_pending) {
+      const double tw0 = now_ms();
       CU(cudaEventSynchronize(slot.ev_h2d));
+      dbg_wait_h2d += now_ms() - tw0;
       slot.h2d_pending = false;
     }
     slot.ensure(segs[i].end - segs[i].begin + 64);
     pool->submit(i, (int)(i % n_slots));
   };
   if (!resident) {
-    pool.reset(new ReaderPool(im.fd, ctx, segs, std::max(1, std::min(ctx.n_readers, n_slots))));
+    pool.reset(new ReaderPool(im.fd, ctx, segs, std::max(1, ctx.n_readers)));
     for (size_t i = 0; i < segs.size() && i < (size_t)n_slots; i++) submit(i);
   }
 
@@ -725,7 +756,9 @@ void Pileup::run_pass(const Range &range, bool resident) {
       if (resident) {
         tab = &im.res_tabs[i];
       } else {
+        const double tw0 = now_ms();
         pool->wait(i);
+        dbg_wait_read += now_ms() - tw0;
         StageSlot &slot = ctx.slots[i % n_slots];
         tab = &slot.tab;
         host_src = slot.pin;
@@ -838,7 +871,11 @@ void Pileup::run_pass(const Range &range, bool resident) {
       // refill the staging ring
       if (!resident && i + n_slots < segs.size()) submit(i + n_slots);
     }
-    for (auto &s : ctx.sets) CU(cudaStreamSynchronize(s.stream));
+    {
+      const double tw0 = now_ms();
+      for (auto &s : ctx.sets) CU(cudaStreamSynchronize(s.stream));
+      dbg_sync += now_ms() - tw0;
+    }
     // a bounded range ends where the index says it should; keep going while the last record seen is still inside it
     if (!range.bounded || segs.empty() || segs.back().end >= file_size_) break;
     CU(cudaMemcpy(probe_host, im.d_probe.p, 16, cudaMemcpyDeviceToHost));
@@ -880,6 +917,10 @@ void Pileup::run_pass(const Range &range, bool resident) {
     for (int k = 0; k < 5; k++) cudaEventDestroy(E.e[k]);
   }
   tm_.wall_ms = now_ms() - t_wall0;
+  tm_.read_ms = dbg_wait_read;
+  if (env_u64("BND_DEBUG_TIMING", 0))
+    fprintf(stderr, "[bnd] pass: %zu segments, wall %.2f ms, waited on readers %.2f ms, on staging reuse %.2f ms, final sync %.2f ms\n", segs.size(),
+            tm_.wall_ms, dbg_wait_read, dbg_wait_h2d, dbg_sync);
   shape_.launches = launch_count() - launches0;
   accumulated_ = true;
 }
