@@ -1609,6 +1609,7 @@ void Pileup::to_bedgraph(const std::string &path) {
   // fills; pwrite would serialise on the inode lock); anything unmappable falls back to positional writes
   char *map = nullptr;
   if (out_bytes && ftruncate(fd, (off_t)out_bytes) == 0) {
+    (void)posix_fallocate(fd, 0, (off_t)out_bytes);  // extents up front: page faults on ext4/xfs then only fill pages
     void *m = mmap(nullptr, out_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     if (m != MAP_FAILED) map = (char *)m;
   }

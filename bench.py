@@ -45,6 +45,14 @@ def workdir() -> Path:
     return base
 
 
+def outdir() -> Path:
+    """Output directory (BND_BENCH_OUT_DIR; default: the tmpfs work dir, the same for both arms — measured faster than the
+    VM's ext4 disk for the mmap writer on the B200 hosts)."""
+    base = Path(os.environ["BND_BENCH_OUT_DIR"]) / "bnd_bench_out" if os.environ.get("BND_BENCH_OUT_DIR") else workdir()
+    base.mkdir(parents=True, exist_ok=True)
+    return base
+
+
 def synth_tool() -> Path:
     out = ROOT / "tools" / "_build" / "synth_bam"
     src = ROOT / "tools" / "synth_bam.cpp"
@@ -110,7 +118,7 @@ def oracle_sample(bam: Path, threads: int = 0):
     from oracle import oracle_py as o
 
     pile = dict(PILE, bam_path=str(bam), n_threads=threads)
-    out = workdir() / "oracle_sample.bedgraph"
+    out = outdir() / "oracle_sample.bedgraph"
     t0 = time.perf_counter()
     st, _ = o.pileup_chroms_to_bedgraph(pile, FILT, SAMPLE_CHROMS, out)  # open BAM -> bedGraph of the sample closed
     dt = time.perf_counter() - t0
@@ -210,7 +218,7 @@ def main():
 
     # ---- e2e leg: host file -> bedGraph file through the C ABI ----
     def e2e_step():
-        out_path = workdir() / f"out_rank{rank}_{len(out_paths)}.bedgraph"  # a fresh output file per job
+        out_path = outdir() / f"out_rank{rank}_{len(out_paths)}.bedgraph"  # a fresh output file per job
         out_paths.append(out_path)
         with N.pileup(pile, FILT) as h:
             h.accumulate()
