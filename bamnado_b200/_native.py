@@ -29,7 +29,8 @@ EXPORTS = [
     "bnd_pileup_destroy", "bnd_pileup_to_bedgraph", "bnd_pileup_to_bigwig", "bnd_pileup_chromosome", "bnd_pileup_runs",
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
-    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_collapse_bedgraph",
+    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_multi_prepare",
+    "bnd_multi_change_flags", "bnd_multi_compact", "bnd_collapse_bedgraph",
     "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
 ]
 
@@ -151,6 +152,9 @@ class Native:
         L.bnd_signal_for_chromosome.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg), C.c_char_p,
                                                 C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_uint64)]
         L.bnd_multi_to_tsv.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg), C.c_int32, C.c_char_p]
+        L.bnd_multi_prepare.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.bnd_multi_change_flags.argtypes = [C.c_void_p, C.c_void_p]
+        L.bnd_multi_compact.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(Run)), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
         L.bnd_collapse_bedgraph.argtypes = [C.c_char_p, C.c_char_p]
         L.bnd_scale_factor.restype = C.c_double
         L.bnd_scale_factor.argtypes = [C.c_int32, C.c_float, C.c_uint64, C.c_uint64]
@@ -316,6 +320,22 @@ class PileupHandle:
         data = C.string_at(ptr, n.value)
         self.n.L.bnd_free(ptr)
         return data
+
+    # ---- one BAM per rank (multi-bam-coverage across GPUs) ----
+    def multi_prepare(self) -> int:
+        n = C.c_uint64()
+        self.n.check(self.n.L.bnd_multi_prepare(self.h, C.byref(n)))
+        return n.value
+
+    def multi_change_flags(self, dev_ptr: int):
+        self.n.check(self.n.L.bnd_multi_change_flags(self.h, C.c_void_p(dev_ptr)))
+
+    def multi_compact(self, dev_ptr: int):
+        ptr, vals, n = C.POINTER(Run)(), C.POINTER(C.c_uint32)(), C.c_uint64()
+        self.n.check(self.n.L.bnd_multi_compact(self.h, C.c_void_p(dev_ptr), C.byref(ptr), C.byref(vals), C.byref(n)))
+        v = np.ctypeslib.as_array(vals, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+        self.n.L.bnd_free(vals)
+        return self._rows(ptr, n.value), v
 
     def timings(self) -> dict:
         ms = (C.c_double * 8)()

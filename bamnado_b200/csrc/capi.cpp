@@ -160,6 +160,24 @@ int bnd_multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, 
   return guarded([&] { bnd::multi_to_tsv(cfgs, filters, n_bams, out_path); });
 }
 
+int bnd_multi_prepare(bnd_pileup *p, uint64_t *n_bins) {
+  return guarded([&] { *n_bins = P(p)->multi_prepare(); });
+}
+int bnd_multi_change_flags(bnd_pileup *p, void *dev_flags) {
+  return guarded([&] { P(p)->multi_change_flags((uint8_t *)dev_flags); });
+}
+int bnd_multi_compact(bnd_pileup *p, const void *dev_flags, bnd_run **rows, uint32_t **vals, uint64_t *n_rows) {
+  return guarded([&] {
+    std::vector<bnd::RunRow> r;
+    std::vector<uint32_t> v;
+    P(p)->multi_compact((const uint8_t *)dev_flags, r, v);
+    rows_out(r, rows, n_rows);
+    *vals = (uint32_t *)malloc(std::max<size_t>(v.size(), 1) * sizeof(uint32_t));
+    if (!*vals) throw std::bad_alloc();
+    if (!v.empty()) memcpy(*vals, v.data(), v.size() * sizeof(uint32_t));
+  });
+}
+
 int bnd_collapse_bedgraph(const char *in_path, const char *out_path) {
   return guarded([&] { bnd::collapse_bedgraph_file(in_path, out_path); });
 }

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(COL_THREADS) bdg_emit_kernel(BdgArgs a) {
 
 // ---- multi-BAM equal-bin collapse --------------------------------------------------------------------------------
 __device__ __forceinline__ bool multi_is_head(const MultiArgs &a, uint64_t i, bool ref_start) {
+  if (a.flags) return a.flags[i] != 0;
   if (ref_start) return true;
   for (int b = 0; b < a.n_bams; b++)
     if (a.counts[b][i] != a.counts[b][i - 1]) return true;
@@ -90,6 +91,15 @@ __device__ __forceinline__ bool multi_is_head(const MultiArgs &a, uint64_t i, bo
 __device__ __forceinline__ bool bin_is_ref_start(const GeomDev &g, uint64_t gbin) {
   int32_t r = ref_of_bin(g, gbin);
   return __ldg(g.ref_first_bin + r) == gbin;
+}
+
+// per-bin head flags of the BAMs held by this rank; ranks OR them together (all-reduce MAX) to get the shared run heads
+__global__ void __launch_bounds__(COL_THREADS) multi_flags_kernel(MultiArgs a) {
+  for (uint64_t i = blockIdx.x * (uint64_t)COL_THREADS + threadIdx.x; i < a.n_bins; i += (uint64_t)gridDim.x * COL_THREADS) {
+    bool h = i == 0 || bin_is_ref_start(a.g, i + a.g.bin_lo);
+    for (int b = 0; b < a.n_bams && !h; b++) h = a.counts[b][i] != a.counts[b][i - 1];
+    a.flags_out[i] = h ? 1 : 0;
+  }
 }
 
 __global__ void __launch_bounds__(COL_THREADS) multi_count_kernel(MultiArgs a) {

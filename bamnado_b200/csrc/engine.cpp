@@ -1251,6 +1251,86 @@ void Pileup::multi_collapse(std::vector<Pileup *> &bams, std::vector<RunRow> &ro
   release();
 }
 
+uint64_t Pileup::multi_prepare() {
+  if (cfg_.collapse) fail("All BAM pileups must have collapse set to false", ERR_INVALID);
+  run_pass(shard_, false);
+  finalize_range(true, false);
+  return im_->gdev.bin_hi - im_->gdev.bin_lo;
+}
+
+void Pileup::multi_change_flags(uint8_t *dev_flags) {
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  if (!finalized_ || !im.d_counts.p) fail("multi_change_flags called before multi_prepare", ERR_INVALID);
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  MultiArgs a{};
+  a.n_bams = 1;
+  a.counts[0] = im.d_counts.as<uint32_t>();
+  a.g = im.gdev;
+  a.n_bins = a.g.bin_hi - a.g.bin_lo;
+  a.flags_out = dev_flags;
+  CU(launch_multi_flags(a, ctx.sm_count, ctx.sets[0].stream));
+  CU(cudaStreamSynchronize(ctx.sets[0].stream));
+}
+
+void Pileup::multi_compact(const uint8_t *dev_flags, std::vector<RunRow> &rows, std::vector<uint32_t> &vals) {
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  if (!finalized_ || !im.d_counts.p) fail("multi_compact called before multi_prepare", ERR_INVALID);
+  rows.clear();
+  vals.clear();
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  cudaStream_t st = ctx.sets[0].stream;
+  MultiArgs a{};
+  a.n_bams = 1;
+  a.counts[0] = im.d_counts.as<uint32_t>();
+  a.g = im.gdev;
+  a.n_bins = a.g.bin_hi - a.g.bin_lo;
+  a.flags = dev_flags;
+  if (a.n_bins == 0) return;
+  a.n_tiles = (uint32_t)((a.n_bins + 255) / 256);
+  DevBuf d_tiles, d_total, d_run_bin, d_vals, d_rows;
+  auto release = [&] {
+    for (DevBuf *b : {&d_tiles, &d_total, &d_run_bin, &d_vals, &d_rows}) b->release();
+  };
+  try {
+    d_tiles.ensure((size_t)a.n_tiles * 8 + 16);
+    d_total.ensure(16);
+    a.tile_heads = d_tiles.as<uint64_t>();
+    CU(launch_multi_count(a, ctx.sm_count, st));
+    CU(launch_u64_scan(a.tile_heads, a.n_tiles, d_total.as<unsigned long long>(), st));
+    unsigned long long n_runs = 0;
+    CU(cudaMemcpyAsync(&n_runs, d_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    d_run_bin.ensure(n_runs * 8 + 16);
+    d_vals.ensure(n_runs * 4 + 16);
+    d_rows.ensure(n_runs * sizeof(RunRow) + 16);
+    a.run_bin = d_run_bin.as<uint64_t>();
+    a.out_vals = d_vals.as<uint32_t>();
+    a.n_runs_cap = n_runs;
+    CU(launch_multi_emit(a, ctx.sm_count, st));
+    RunArgs ra{};
+    ra.run_bin = a.run_bin;
+    ra.n_runs = n_runs;
+    ra.g = a.g;
+    ra.rows = d_rows.as<RunRow>();
+    CU(launch_multi_rows(ra, ctx.sm_count, st));
+    rows.resize(n_runs);
+    vals.resize(n_runs);
+    if (n_runs) {
+      CU(cudaMemcpyAsync(rows.data(), d_rows.p, n_runs * sizeof(RunRow), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(vals.data(), d_vals.p, n_runs * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+  } catch (...) {
+    release();
+    throw;
+  }
+  release();
+}
+
 // ---- collapse-bedgraph ------------------------------------------------------------------------------------------------------
 void collapse_rows_device(const BdgRows &in, BdgRows &out, int device) {
   out = BdgRows();

@@ -58,6 +58,11 @@ class Pileup {
   bool is_paired_end();
   // MultiBamPileup (coverage_analysis.rs:783-848): raw per-bin counts of every BAM, collapsed where all samples agree
   static void multi_collapse(std::vector<Pileup *> &bams, std::vector<RunRow> &rows, std::vector<uint32_t> &vals);
+  // one BAM per rank: raw dense counts stay on the device, the ranks OR their per-bin change flags together
+  // (NCCL all-reduce MAX over device memory owned by the caller), then every rank compacts its own column
+  uint64_t multi_prepare();
+  void multi_change_flags(uint8_t *dev_flags);
+  void multi_compact(const uint8_t *dev_flags, std::vector<RunRow> &rows, std::vector<uint32_t> &vals);
 
  private:
   struct Range {  // what part of the file / genome a pass covers

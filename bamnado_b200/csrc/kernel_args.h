@@ -244,6 +244,8 @@ struct MultiArgs {
   uint64_t *run_bin;
   uint32_t *out_vals;  // [n_bams][n_runs_cap]
   uint64_t n_runs_cap;
+  const uint8_t *flags;  // optional: precomputed head flags (OR-reduced over ranks when every rank holds one BAM)
+  uint8_t *flags_out;    // multi_flags_kernel output
 };
 
 }  // namespace bnd

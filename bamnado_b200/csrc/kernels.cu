@@ -187,6 +187,11 @@ cudaError_t launch_u64_scan(uint64_t *v, uint32_t n, unsigned long long *total_o
   BND_LAUNCH(k, dim3(1), dim3(1024), 0, s, v, n, total_out);
   return launched();
 }
+cudaError_t launch_multi_flags(const MultiArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_bins == 0) return cudaSuccess;
+  BND_LAUNCH(multi_flags_kernel, dim3(grid_for(a.n_bins, COL_THREADS, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
 cudaError_t launch_multi_count(const MultiArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_tiles == 0) return cudaSuccess;
   BND_LAUNCH(multi_count_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);

@@ -135,6 +135,13 @@ int bnd_signal_for_chromosome(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *f
 /* ---- MultiBamPileup::to_tsv (coverage_analysis.rs:766-865) ------------------------------------------------ */
 int bnd_multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int32_t n_bams, const char *out_path);
 
+/* ---- MultiBamPileup with one BAM per GPU: the pileups run independently, the ranks OR their per-bin change
+ * flags together with one all-reduce(MAX) over NVLink on memory the caller owns (e.g. a torch CUDA tensor), and every rank
+ * compacts its own column at the shared run heads.  `dev_flags` are DEVICE pointers to n_bins bytes. ------------------------ */
+int bnd_multi_prepare(bnd_pileup *p, uint64_t *n_bins);
+int bnd_multi_change_flags(bnd_pileup *p, void *dev_flags);
+int bnd_multi_compact(bnd_pileup *p, const void *dev_flags, bnd_run **rows, uint32_t **vals, uint64_t *n_rows);
+
 /* ---- collapse-bedgraph (src/cli.rs:1149-1205 + bedgraph_utils.rs:5-45) ------------------------------------ */
 int bnd_collapse_bedgraph(const char *in_path, const char *out_path);
 

@@ -57,3 +57,19 @@ def test_two_rank_gloo_sharded_coverage(oracle, make_bam, tmp_path, native_emul)
     oracle.pileup_to_bedgraph(pile, filt, ref)
     got = sorted(open(out + ".text0", "rb").read().splitlines() + open(out + ".text1", "rb").read().splitlines())
     assert got == sorted(ref.read_bytes().splitlines())
+
+
+def test_multi_bam_one_bam_per_rank_gloo(oracle, make_bam, tmp_path, native_emul):
+    # §8(e): one BAM per rank, all-reduce(MAX) of the change flags, gather of the compacted columns -> MultiBamPileup TSV
+    bams = [make_bam("m0", "--pairs", 8000, "--seed", 11, "--mode", "se"), make_bam("m1", "--pairs", 8000, "--seed", 12, "--mode", "se")]
+    out = tmp_path / "dist.tsv"
+    env = dict(os.environ, BND_EMUL_WORKERS="2", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29519", str(ROOT / "scripts" / "multi_bam_dist.py"), "--bams", *bams, "--bin-size", "500", "-o", str(out),
+                        "--backend", "gloo", "--emul"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    ref = tmp_path / "oracle.tsv"
+    filt = dict(min_mapq=20, min_length=20, max_length=1000)
+    oracle.multi_to_tsv([dict(bam_path=b, bin_size=500, collapse=False) for b in bams], [filt, filt], ref)
+    a, b = out.read_text().splitlines(), ref.read_text().splitlines()
+    assert a[0] == b[0] and sorted(a[1:]) == sorted(b[1:])
