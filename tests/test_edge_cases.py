@@ -1,0 +1,119 @@
+"""Edge cases of the coverage path: empty inputs, a BAI without the metadata pseudo-bin (chunk length degenerates to the
+bin size), tiny contigs, bins larger than contigs, deep pile-ups, and a larger file checked both against
+the oracle and through size-independent properties."""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+CLI_FILTER = dict(min_mapq=20, min_length=20, max_length=1000)
+
+
+def same(backend, oracle, pile, filt):
+    with backend.pileup(pile, filt) as h:
+        runs, stats, factor = h.runs(), h.stats(), h.norm_factor()
+    oruns, ostats, ofactor = oracle.pileup_runs(pile, filt)
+    assert stats == ostats and factor == ofactor
+    assert len(runs) == len(oruns) and (runs == oruns).all()
+    return runs, stats
+
+
+def strip_bai_metadata(src, dst):
+    """Rewrites a .bai without the 37450 pseudo-bins (and without the trailing n_no_coor)."""
+    d = open(src, "rb").read()
+    n_ref = struct.unpack_from("<I", d, 4)[0]
+    p, out = 8, [d[:8]]
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from("<I", d, p)[0]
+        p += 4
+        bins = []
+        for _ in range(n_bin):
+            b, n_chunk = struct.unpack_from("<II", d, p)
+            raw = d[p: p + 8 + 16 * n_chunk]
+            p += 8 + 16 * n_chunk
+            if b != 37450:
+                bins.append(raw)
+        out.append(struct.pack("<I", len(bins)) + b"".join(bins))
+        n_intv = struct.unpack_from("<I", d, p)[0]
+        out.append(d[p: p + 4 + 8 * n_intv])
+        p += 4 + 8 * n_intv
+    open(dst, "wb").write(b"".join(out))
+
+
+def test_small_genome_many_shapes(backend, oracle, make_bam):
+    bam = make_bam("tiny", "--pairs", 6000, "--contigs", "c1:120000,c2:777,c3:50,c4:1,c5:300000,c6_random:4000", "--odd", "--peaks", 20)
+    for bin_size in (1, 7, 50, 1000, 500000):
+        for collapse in (True, False):
+            same(backend, oracle, dict(bam_path=bam, bin_size=bin_size, collapse=collapse), CLI_FILTER)
+    same(backend, oracle, dict(bam_path=bam, bin_size=25, use_fragment=True, norm="rpkm"), dict(proper_pair=True, **CLI_FILTER))
+
+
+def test_bai_without_metadata_degenerate_chunks(backend, oracle, make_bam, tmp_path):
+    # n_mapped = 0 -> chunk length = bin size -> one (bin - 1)-wide bin per chunk and reads counted once per chunk they touch
+    src = make_bam("tiny", "--pairs", 6000, "--contigs", "c1:120000,c2:777,c3:50,c4:1,c5:300000,c6_random:4000", "--odd", "--peaks", 20)
+    bam = tmp_path / "nometa.bam"
+    bam.write_bytes(open(src, "rb").read())
+    strip_bai_metadata(src + ".bai", str(bam) + ".bai")
+    assert oracle.bam_stats(bam, 40)["chunk_len"] == 40
+    for bin_size in (40, 3):
+        runs, stats = same(backend, oracle, dict(bam_path=str(bam), bin_size=bin_size, norm="cpm"), CLI_FILTER)
+        assert stats["n_total"] > 12000  # reads are visited once per (tiny) chunk they overlap
+
+
+def test_header_only_bam(backend, oracle, make_bam):
+    bam = make_bam("empty", "--pairs", 0, "--contigs", "c1:100000,c2:2000")
+    runs, stats = same(backend, oracle, dict(bam_path=bam, bin_size=100, norm="cpm"), CLI_FILTER)
+    assert stats["n_total"] == 0
+    with backend.pileup(dict(bam_path=bam, bin_size=100, norm="cpm"), CLI_FILTER) as h:
+        assert h.norm_factor() == 0.0  # n == 0 -> factor 0, an all-zero track, not an error
+        text = h.bedgraph_text()
+    assert text.count(b"\n") == len(runs)
+
+
+def test_deep_pileup_hot_spot(backend, oracle, make_bam):
+    # every read in a handful of peaks: shared-memory window + global atomics under heavy contention
+    bam = make_bam("deep", "--pairs", 30000, "--contigs", "c1:5000000,c2:100000", "--peaks", 3)
+    runs, _ = same(backend, oracle, dict(bam_path=bam, bin_size=10), dict())
+    assert runs["val"].max() > 500
+
+
+@pytest.mark.gpu
+def test_two_million_pairs_properties_and_oracle(native_gpu, oracle, make_bam, tmp_path):
+    """4 M records / 865 MB inflated: full comparison with the oracle plus size-independent properties
+    (idempotence, resident == streaming, shards == whole, collapsed rows expand to the uncollapsed ones)."""
+    N = native_gpu
+    bam = make_bam("pe2m", "--pairs", 2000000)
+    pile, filt = dict(bam_path=bam, bin_size=50, norm="rpkm"), dict(min_mapq=30, proper_pair=True)
+    with N.pileup(pile, filt) as h:
+        a, stats = h.runs(), h.stats()
+        text1 = h.bedgraph_text()
+        h.accumulate()
+        h.finalize()
+        assert (h.runs() == a).all() and h.bedgraph_text() == text1          # idempotent
+        h.stage()
+        h.accumulate_resident()
+        h.finalize()
+        assert (h.runs() == a).all() and h.stats() == stats                   # resident == streaming
+    out = tmp_path / "o.bdg"
+    ostats, _ = oracle.pileup_to_bedgraph(pile, filt, out)
+    assert stats == ostats and text1 == out.read_bytes()                      # byte-identical bedGraph
+    parts, total = [], None
+    hs = [N.pileup(dict(pile, shard_rank=r, shard_world=5), filt) for r in range(5)]
+    for h in hs:
+        h.accumulate()
+        s = h.stats()
+        total = s if total is None else {k: total[k] + s[k] for k in s}
+    for h in hs:
+        h.set_total_stats(list(total.values()))
+        h.finalize()
+        parts.append(h.runs())
+        h.close()
+    assert total == stats and (np.concatenate(parts) == a).all()             # shards == whole
+    with N.pileup(dict(pile, collapse=False), filt) as h:
+        b = h.runs()
+    # expanding collapsed runs bin by bin gives the uncollapsed rows (checksum of value x bins and row count)
+    assert int(b["val"].sum()) == int((a["val"].astype(np.int64) * np.ceil((a["stop"] - a["start"]) / 50).astype(np.int64)).sum())
+    heads = np.ones(len(b), bool)
+    heads[1:] = (b["val"][1:] != b["val"][:-1]) | (b["ref_id"][1:] != b["ref_id"][:-1]) | (b["start"][1:] != b["stop"][:-1])
+    assert heads.sum() == len(a)
