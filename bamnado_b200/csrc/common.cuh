@@ -60,6 +60,31 @@ struct Tile {
   __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 
+// ---- shared-memory window addresses --------------------------------------------------------------------------------
+// Hot loops address shared memory through 32-bit window addresses and ld/st.shared PTX: the compiler otherwise keeps
+// re-deriving 64-bit generic pointers (S2R + IMAD chains in the SASS of the inflate walk, profiles/).
+#if defined(BND_EMUL)
+typedef uintptr_t saddr_t;
+__device__ __forceinline__ saddr_t smem_addr(const void *p) { return (saddr_t)p; }
+__device__ __forceinline__ uint32_t lds_u16(saddr_t a) { return *(const uint16_t *)a; }
+__device__ __forceinline__ uint32_t lds_u32(saddr_t a) { return *(const uint32_t *)a; }
+__device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v) { *(uint32_t *)a = v; }
+#else
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t smem_addr(const void *p) { return (saddr_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u16(saddr_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(saddr_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+#endif
+
 // ---- unaligned little-endian loads (BAM records sit at arbitrary byte offsets) ---------------------------------
 __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) {
   uintptr_t a = (uintptr_t)p;

@@ -129,11 +129,11 @@ struct DevBuf {
   }
 };
 
-constexpr int NSET = 3;
+constexpr int MAX_SETS = 8;  // segments in flight (BND_SETS, default 6): enough queued K1 work to cover the K2/K3 tails
 
 struct SegSet {
   cudaStream_t stream = nullptr;
-  DevBuf comp, coff, uoff, infl, t_entry, t_exit, t_count, t_base, t_slots, rec_off;
+  DevBuf comp, coff, uoff, infl, t_entry, t_exit, t_count, t_base, t_slots, t_flag, rec_off;
   SegState *st = nullptr;
   uint32_t *work = nullptr;
   cudaEvent_t ev_idx = nullptr, ev_carry = nullptr;
@@ -162,7 +162,8 @@ struct DeviceCtx {
   int device = 0;
   int sm_count = 1;
   CrcTables *d_crc = nullptr;
-  SegSet sets[NSET];
+  SegSet sets[MAX_SETS];
+  int n_sets = 6;
   std::vector<StageSlot> slots;
   uint64_t seg_bytes = 0, carry_cap = 0;
   int n_readers = 4;
@@ -197,6 +198,7 @@ DeviceCtx &ctx_for(int device) {
   c->carry_cap = env_u64("BND_CARRY_BYTES", 8ull << 20);
   c->carry_cap = (c->carry_cap + REC_TILE - 1) / REC_TILE * REC_TILE;
   c->n_readers = (int)env_u64("BND_READERS", 8);
+  c->n_sets = (int)std::min<uint64_t>(MAX_SETS, std::max<uint64_t>(2, env_u64("BND_SETS", 6)));
   int n_slots = (int)env_u64("BND_STAGES", 4);
   if (n_slots < 2) n_slots = 2;
   c->slots.resize(n_slots);
@@ -750,7 +752,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
   for (;;) {
     for (; i < segs.size(); i++) {
       const Segment &sg = segs[i];
-      SegSet &S = ctx.sets[i % NSET];
+      SegSet &S = ctx.sets[i % ctx.n_sets];
       const BlockTable *tab;
       const uint8_t *host_src = nullptr;
       if (resident) {
@@ -784,6 +786,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
         S.t_entry.ensure((size_t)n_tiles * 8);
         S.t_exit.ensure((size_t)n_tiles * 8);
         S.t_count.ensure((size_t)n_tiles * 4);
+        S.t_flag.ensure((size_t)n_tiles + 16);
         S.t_base.ensure((size_t)n_tiles * 8);
         S.t_slots.ensure((size_t)n_tiles * REC_SLOTS * 2);
         S.rec_off.ensure((ulen / 36 + 2) * 8);
@@ -828,7 +831,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
         s0.entry_off = ctx.carry_cap + range.entry_uoff;
         CU(cudaMemcpyAsync(S.st, &s0, sizeof s0, cudaMemcpyHostToDevice, st));
       } else {
-        SegSet &P = ctx.sets[(i - 1) % NSET];
+        SegSet &P = ctx.sets[(i - 1) % ctx.n_sets];
         CU(cudaStreamWaitEvent(st, P.ev_idx, 0));
         CU(launch_carry_copy(P.infl.as<uint8_t>(), S.infl.as<uint8_t>(), P.st, S.st, ctx.carry_cap, st));
         CU(cudaEventRecord(P.ev_carry, st));
@@ -843,6 +846,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
       ra.tile_entry = S.t_entry.as<uint64_t>();
       ra.tile_exit = S.t_exit.as<uint64_t>();
       ra.tile_count = S.t_count.as<uint32_t>();
+      ra.tile_flag = S.t_flag.as<uint8_t>();
       ra.tile_base = S.t_base.as<uint64_t>();
       ra.tile_slots = S.t_slots.as<uint16_t>();
       ra.rec_off = S.rec_off.as<uint64_t>();
@@ -895,10 +899,12 @@ void Pileup::run_pass(const Range &range, bool resident) {
     fail("BGZF inflate failed on the device (status " + std::to_string(err[0] & 0xff) + ", block " + std::to_string((unsigned)err[0] >> 8) + " of its segment)");
   if (!segs.empty()) {
     SegState last;
-    CU(cudaMemcpy(&last, ctx.sets[(segs.size() - 1) % NSET].st, sizeof last, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&last, ctx.sets[(segs.size() - 1) % ctx.n_sets].st, sizeof last, cudaMemcpyDeviceToHost));
     if (last.error == SEG_ERR_BAD_RECORD) fail("invalid BAM record (block_size < 32)");
     if (last.error == SEG_ERR_CARRY_TOO_LARGE) fail("a BAM record larger than BND_CARRY_BYTES straddles two segments");
     shape_.records = last.total_records;
+    if (env_u64("BND_DEBUG_TIMING", 0))
+      fprintf(stderr, "[bnd] record index: %u fix rounds, %u tiles re-walked over %zu segments\n", last.fix_rounds, last.rewalked, segs.size());
     if (!range.bounded && last.carry_len != 0) fail("truncated BAM record at end of file");
   }
   unsigned long long st[ST_N_COUNTERS];

@@ -376,12 +376,13 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
       int ntok = 0;
       int st = INF_OK;
       if (lane == 0) {
-        uint32_t *tp = S.raw;
-        uint32_t *const tend = S.raw + NTOK;
+        const saddr_t raw0 = smem_addr(S.raw), lit0 = smem_addr(S.lit_lut), dist0 = smem_addr(S.dist_lut);
+        saddr_t tp = raw0;
+        const saddr_t tend = raw0 + 4 * NTOK;
 #pragma unroll 1
         do {
           uint32_t w = br.window();
-          uint32_t e = S.lit_lut[w & ((1u << LIT_BITS) - 1u)];
+          uint32_t e = lds_u16(lit0 + 2 * (w & ((1u << LIT_BITS) - 1u)));
           if ((e & 31u) == 0) {  // rare: code longer than the lookup width
             uint32_t sym, len;
             if (!canon_decode(w, LIT_BITS, S.lit_canon, S.lit_sorted, sym, len)) {
@@ -396,9 +397,9 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
               eob = true;
               break;
             }
-            tp[NTOK] = w;
+            sts_u32(tp + 4 * NTOK, w);
             w = br.window();
-            uint32_t d = S.dist_lut[w & ((1u << DIST_BITS) - 1u)];
+            uint32_t d = lds_u16(dist0 + 2 * (w & ((1u << DIST_BITS) - 1u)));
             if ((d & 31u) == 0) {  // rare
               uint32_t ds, dl;
               if (!canon_decode(w, DIST_BITS, S.dist_canon, S.dist_sorted, ds, dl)) {
@@ -407,13 +408,14 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
               }
               d = dist_entry(ds, dl);
             }
-            tp[2 * NTOK] = w;
+            sts_u32(tp + 8 * NTOK, w);
             br.consume(d & 31u);
             e |= d << 16;
           }
-          *tp++ = e;
+          sts_u32(tp, e);
+          tp += 4;
         } while (tp != tend);
-        ntok = (int)(tp - S.raw);
+        ntok = (int)((tp - raw0) >> 2);
         if (st == INF_OK && br.overrun()) st = INF_INPUT_OVERRUN;
       }
       st = tile.shfl(st, 0);
@@ -442,6 +444,13 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
           dist = (dt & 0xffffu) + ((S.raw[2 * NTOK + ti] >> dist_bits) & ~(0xffffffffu << deb));
           bad = lt == 0 || dt == 0;
         }
+#ifdef BND_EMUL_STATS
+        if (mine) {
+          extern unsigned long long g_dbg[8];
+          __atomic_fetch_add(&g_dbg[5], 1ull, __ATOMIC_RELAXED);
+          if (lane == 0) __atomic_fetch_add(&g_dbg[6], 1ull, __ATOMIC_RELAXED);
+        }
+#endif
         const uint32_t olen = is_match ? length : (mine ? 1u : 0u);
         uint32_t incl = olen;
 #pragma unroll
@@ -483,6 +492,19 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
               if ((uint32_t)i < length) dst[i] = buf[i];
           }
           uint32_t later = tile.ballot(is_match && !par);
+#ifdef BND_EMUL_STATS
+          if (lane == 0) {
+            extern unsigned long long g_dbg[8];
+            __atomic_fetch_add(&g_dbg[0], (unsigned long long)__builtin_popcount(mmask), __ATOMIC_RELAXED);
+            __atomic_fetch_add(&g_dbg[1], (unsigned long long)__builtin_popcount(later), __ATOMIC_RELAXED);
+          }
+          if (is_match) {
+            extern unsigned long long g_dbg[8];
+            __atomic_fetch_add(&g_dbg[2], (unsigned long long)length, __ATOMIC_RELAXED);
+            if (!par && length > 16) __atomic_fetch_add(&g_dbg[3], 1ull, __ATOMIC_RELAXED);
+            if (!par && dist < length) __atomic_fetch_add(&g_dbg[4], 1ull, __ATOMIC_RELAXED);
+          }
+#endif
           tile.sync();
 #pragma unroll 1
           while (later) {

@@ -73,6 +73,7 @@ struct RecArgs {
   uint64_t *tile_entry;    // [n_tiles]
   uint64_t *tile_exit;     // [n_tiles]
   uint32_t *tile_count;    // [n_tiles]
+  uint8_t *tile_flag;      // [n_tiles] scratch of the fix pass
   uint64_t *tile_base;     // [n_tiles] first record index of the tile (after the scan)
   uint16_t *tile_slots;    // [n_tiles][REC_SLOTS]
   uint64_t *rec_off;       // [capacity] buffer offsets of the records, in stream order

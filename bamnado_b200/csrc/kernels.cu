@@ -40,7 +40,7 @@ struct InflateVariant {
   int g, threads, ctas_per_sm;
 };
 // lane-group width / CTA size / resident CTAs per SM (and LUT widths below); selected with BND_INFLATE_VARIANT
-const InflateVariant kVariants[] = {{32, 256, 5}, {32, 128, 9}, {32, 128, 12}, {32, 256, 6}, {32, 128, 10}, {32, 512, 2}};
+const InflateVariant kVariants[] = {{32, 256, 5}, {32, 128, 9}, {32, 128, 12}, {32, 256, 6}, {32, 256, 4}, {32, 128, 8}};
 int variant_index() {
   static int v = -1;
   if (v < 0) {
@@ -92,8 +92,8 @@ cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
     case 1: return launch_inflate_t<32, 128, 9, 10, 8>(a, sm_count, v.ctas_per_sm, s);
     case 2: return launch_inflate_t<32, 128, 12, 9, 7>(a, sm_count, v.ctas_per_sm, s);  // 48 warps / SM, <= 40 registers
     case 3: return launch_inflate_t<32, 256, 6, 9, 7>(a, sm_count, v.ctas_per_sm, s);
-    case 4: return launch_inflate_t<32, 128, 10, 10, 8>(a, sm_count, v.ctas_per_sm, s);
-    case 5: return launch_inflate_t<32, 512, 2, 10, 8>(a, sm_count, v.ctas_per_sm, s);
+    case 4: return launch_inflate_t<32, 256, 4, 10, 8>(a, sm_count, v.ctas_per_sm, s);  // 32 warps / SM, <= 64 registers
+    case 5: return launch_inflate_t<32, 128, 8, 10, 8>(a, sm_count, v.ctas_per_sm, s);
     default: return launch_inflate_t<32, 256, 5, 10, 8>(a, sm_count, v.ctas_per_sm, s);
   }
 }

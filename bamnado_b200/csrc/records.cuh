@@ -119,18 +119,32 @@ __global__ void __launch_bounds__(THREADS) rec_fix_scan_kernel(RecArgs a) {
   const int tid = (int)threadIdx.x;
   const uint64_t seg_entry = a.st->entry_off;
   uint32_t rounds = 0, rewalked = 0;
+  // Fixed point without cascades: a tile whose entry differs from its predecessor's exit is re-walked only when the
+  // predecessor itself is consistent in this round (its exit will not change under our feet); the thread that owns
+  // the head of a run of inconsistent tiles walks the whole run.  A wrong guess therefore costs a couple of rounds
+  // instead of rippling through the rest of the segment one tile per round.
   for (;;) {
-    int changed = 0;
+    int any = 0;
     for (uint32_t k = (uint32_t)tid; k < a.n_tiles; k += THREADS) {
       uint64_t expected = k == 0 ? seg_entry : a.tile_exit[k - 1];
-      if (a.tile_entry[k] != expected) {
-        rec_walk_tile(a, k, expected);
-        changed = 1;
-        rewalked++;
-      }
+      uint8_t f = a.tile_entry[k] != expected;
+      a.tile_flag[k] = f;
+      any |= f;
     }
     rounds++;
-    if (!__syncthreads_or(changed)) break;
+    if (!__syncthreads_or(any)) break;
+    for (uint32_t k = (uint32_t)tid; k < a.n_tiles; k += THREADS) {
+      if (a.tile_flag[k] && (k == 0 || !a.tile_flag[k - 1])) {
+        // head of a run of inconsistent tiles: walk the whole run from the predecessor's (stable) exit
+        uint32_t j = k;
+        do {
+          rec_walk_tile(a, j, j == 0 ? seg_entry : a.tile_exit[j - 1]);
+          rewalked++;
+          j++;
+        } while (j < a.n_tiles && a.tile_flag[j]);
+      }
+    }
+    __syncthreads();
   }
   // exclusive scan of the per-tile record counts
   if (tid == 0) running = 0;

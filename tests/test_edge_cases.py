@@ -117,3 +117,62 @@ def test_two_million_pairs_properties_and_oracle(native_gpu, oracle, make_bam, t
     heads = np.ones(len(b), bool)
     heads[1:] = (b["val"][1:] != b["val"][:-1]) | (b["ref_id"][1:] != b["ref_id"][:-1]) | (b["start"][1:] != b["stop"][:-1])
     assert heads.sum() == len(a)
+
+
+def _bgzf(payload: bytes) -> bytes:
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(payload) + co.flush()
+    return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", 18 + len(comp) + 8 - 1) + comp
+            + struct.pack("<II", zlib.crc32(payload), len(payload)))
+
+
+def write_adversarial_bam(path, n_records=3000, contig_len=400000, seed=1):
+    """One contig; every record carries a B:C aux array filled with back-to-back byte patterns that look exactly like
+    minimal BAM records, so most speculative record-start guesses of K2 land inside a fake chain."""
+    rng = np.random.default_rng(seed)
+    fake = struct.pack("<IiiBBHHHIiii", 33, 0, 5, 1, 0, 4680, 0, 4, 0, -1, -1, 0) + b"\0"  # 37 bytes: block_size 33 + payload
+    text = b"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:c1\tLN:%d\n" % contig_len
+    stream = b"BAM\1" + struct.pack("<I", len(text)) + text + struct.pack("<I", 1) + struct.pack("<I", 3) + b"c1\0" + struct.pack("<I", contig_len)
+    header_len = len(stream)
+    pos = np.sort(rng.integers(0, contig_len - 200, n_records))
+    recs = []
+    for i, p in enumerate(pos):
+        name = b"q%06d\0" % i
+        l_seq = 50
+        cigar = struct.pack("<I", (l_seq << 4) | 0)
+        seq = bytes(rng.integers(0, 256, (l_seq + 1) // 2, dtype=np.uint8))
+        qual = bytes(rng.integers(0, 40, l_seq, dtype=np.uint8))
+        n_fake = int(rng.integers(5, 90))
+        aux = b"XFBC" + struct.pack("<I", 37 * n_fake) + fake * n_fake + b"NMC\x01"
+        body = struct.pack("<iiBBHHHIiii", 0, int(p), len(name), int(rng.integers(0, 61)), 4680, 1, 0, l_seq, -1, -1, 0) + name + cigar + seq + qual + aux
+        recs.append(struct.pack("<I", len(body)) + body)
+    stream += b"".join(recs)
+    blocks, coffs, off = [], [], 0
+    for i in range(0, len(stream), 65280):
+        b = _bgzf(stream[i:i + 65280])
+        coffs.append(off)
+        off += len(b)
+        blocks.append(b)
+    eof = _bgzf(b"")
+    open(path, "wb").write(b"".join(blocks) + eof)
+    first_voff = (coffs[header_len // 65280] << 16) | (header_len % 65280)
+    end_voff = off << 16
+    n_intv = (contig_len + 16383) // 16384
+    bai = b"BAI\1" + struct.pack("<I", 1) + struct.pack("<I", 2)
+    bai += struct.pack("<II", 0, 1) + struct.pack("<QQ", first_voff, end_voff)
+    bai += struct.pack("<II", 37450, 2) + struct.pack("<QQQQ", first_voff, end_voff, n_records, 0)
+    bai += struct.pack("<I", n_intv) + struct.pack("<Q", first_voff) * n_intv + struct.pack("<Q", 0)
+    open(str(path) + ".bai", "wb").write(bai)
+    return pos
+
+
+def test_record_discovery_survives_fake_record_chains(backend, oracle, tmp_path, small_segments):
+    bam = tmp_path / "adversarial.bam"
+    pos = write_adversarial_bam(bam)
+    runs, stats = same(backend, oracle, dict(bam_path=str(bam), bin_size=100), dict())
+    assert stats["n_total"] == len(pos)
+    # independent check of the pile-up itself: every record covers [pos + 1, pos + 51)
+    cov = np.zeros(400001, np.int64)
+    np.add.at(cov, pos + 1, 1)
+    np.add.at(cov, pos + 51, -1)
+    assert runs["val"].max() > 0 and int((runs["val"].astype(np.int64) > 0).sum()) > 100
