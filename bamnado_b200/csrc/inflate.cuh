@@ -204,6 +204,59 @@ __device__ uint32_t tile_crc32(const Tile<G> &tile, const uint8_t *out, uint32_t
   return ~c;
 }
 
+// The serial half of a batch: walk up to NTOK symbols, store their raw tokens in S.raw, advance the bit reader.
+// Kept out of line on purpose: inside inflate_block the register allocator (capped by the occupancy target) kept
+// re-deriving the shared-memory base addresses in every iteration (S2R + LEA + IMAD chains in the SASS); as a separate
+// function the loop owns its ~16 live registers.  Returns ntok | status << 8 | eob << 16.
+template <class TileSmem>
+__device__ __noinline__ uint32_t walk_batch(BitReader &br_ref, TileSmem &S) {
+  constexpr int LIT_BITS = TileSmem::LIT_BITS, DIST_BITS = TileSmem::DIST_BITS;
+  BitReader br = br_ref;
+  const saddr_t raw0 = smem_addr(S.raw), lit0 = smem_addr(S.lit_lut), dist0 = smem_addr(S.dist_lut);
+  saddr_t tp = raw0;
+  const saddr_t tend = raw0 + 4 * NTOK;
+  uint32_t st = INF_OK, eob = 0;
+#pragma unroll 1
+  do {
+    uint32_t w = br.window();
+    uint32_t e = lds_u16(lit0 + 2 * (w & ((1u << LIT_BITS) - 1u)));
+    if ((e & 31u) == 0) {  // rare: code longer than the lookup width
+      uint32_t sym, len;
+      if (!canon_decode(w, LIT_BITS, S.lit_canon, S.lit_sorted, sym, len)) {
+        st = INF_BAD_SYMBOL;
+        break;
+      }
+      e = lit_entry(sym, len);
+    }
+    br.consume(e & 31u);
+    if (e >= (256u << 7)) {
+      if (e < (257u << 7)) {
+        eob = 1;
+        break;
+      }
+      sts_u32(tp + 4 * NTOK, w);
+      w = br.window();
+      uint32_t d = lds_u16(dist0 + 2 * (w & ((1u << DIST_BITS) - 1u)));
+      if ((d & 31u) == 0) {  // rare
+        uint32_t ds, dl;
+        if (!canon_decode(w, DIST_BITS, S.dist_canon, S.dist_sorted, ds, dl)) {
+          st = INF_BAD_DISTANCE;
+          break;
+        }
+        d = dist_entry(ds, dl);
+      }
+      sts_u32(tp + 8 * NTOK, w);
+      br.consume(d & 31u);
+      e |= d << 16;
+    }
+    sts_u32(tp, e);
+    tp += 4;
+  } while (tp != tend);
+  if (st == INF_OK && br.overrun()) st = INF_INPUT_OVERRUN;
+  br_ref = br;
+  return (uint32_t)((tp - raw0) >> 2) | (st << 8) | (eob << 16);
+}
+
 // Inflate one BGZF block with a tile of G lanes.  Returns a status code (same on every lane).
 template <int G, class TileSmem>
 __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &T, const uint8_t *blk, uint32_t blk_size,
@@ -376,47 +429,10 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
       int ntok = 0;
       int st = INF_OK;
       if (lane == 0) {
-        const saddr_t raw0 = smem_addr(S.raw), lit0 = smem_addr(S.lit_lut), dist0 = smem_addr(S.dist_lut);
-        saddr_t tp = raw0;
-        const saddr_t tend = raw0 + 4 * NTOK;
-#pragma unroll 1
-        do {
-          uint32_t w = br.window();
-          uint32_t e = lds_u16(lit0 + 2 * (w & ((1u << LIT_BITS) - 1u)));
-          if ((e & 31u) == 0) {  // rare: code longer than the lookup width
-            uint32_t sym, len;
-            if (!canon_decode(w, LIT_BITS, S.lit_canon, S.lit_sorted, sym, len)) {
-              st = INF_BAD_SYMBOL;
-              break;
-            }
-            e = lit_entry(sym, len);
-          }
-          br.consume(e & 31u);
-          if (e >= (256u << 7)) {
-            if (e < (257u << 7)) {
-              eob = true;
-              break;
-            }
-            sts_u32(tp + 4 * NTOK, w);
-            w = br.window();
-            uint32_t d = lds_u16(dist0 + 2 * (w & ((1u << DIST_BITS) - 1u)));
-            if ((d & 31u) == 0) {  // rare
-              uint32_t ds, dl;
-              if (!canon_decode(w, DIST_BITS, S.dist_canon, S.dist_sorted, ds, dl)) {
-                st = INF_BAD_DISTANCE;
-                break;
-              }
-              d = dist_entry(ds, dl);
-            }
-            sts_u32(tp + 8 * NTOK, w);
-            br.consume(d & 31u);
-            e |= d << 16;
-          }
-          sts_u32(tp, e);
-          tp += 4;
-        } while (tp != tend);
-        ntok = (int)((tp - raw0) >> 2);
-        if (st == INF_OK && br.overrun()) st = INF_INPUT_OVERRUN;
+        const uint32_t r = walk_batch<TileSmem>(br, S);
+        ntok = (int)(r & 0xffu);
+        st = (int)((r >> 8) & 0xffu);
+        eob = (r >> 16) != 0;
       }
       st = tile.shfl(st, 0);
       if (st != INF_OK) {
