@@ -85,6 +85,7 @@ class Pileup {
   uint64_t finalize_range(bool dense_counts, bool emit_runs = true);
   void fetch_rows(std::vector<RunRow> &out);
   void ensure_finalized();
+  uint64_t shard_bins_upper() const { return geo_.first_bin_of_chunk(shard_.chunk_hi) - geo_.first_bin_of_chunk(shard_.chunk_lo); }
 
   bnd_pileup_cfg cfg_;
   std::string bam_path_;

@@ -221,10 +221,11 @@ def main():
         out_path = outdir() / f"out_rank{rank}_{len(out_paths)}.bedgraph"  # a fresh output file per job
         out_paths.append(out_path)
         with N.pileup(pile, FILT) as h:
-            h.accumulate()
-            allreduce_stats(h)
-            h.finalize()
-            h.to_bedgraph(out_path)
+            if world > 1:  # sharded: the ranks meet once to sum the 13 filter counters before normalising
+                h.accumulate()
+                allreduce_stats(h)
+                h.finalize()
+            h.to_bedgraph(out_path)  # single GPU: one call = BamPileup::to_bedgraph (pile-up, normalise, write)
             return h.shape(), h.timings()
 
     for _ in range(args.warmup):
