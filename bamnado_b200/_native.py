@@ -30,7 +30,7 @@ EXPORTS = [
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
     "bnd_pileup_timings", "bnd_pileup_shape", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_multi_prepare",
-    "bnd_multi_change_flags", "bnd_multi_compact", "bnd_collapse_bedgraph",
+    "bnd_multi_change_flags", "bnd_multi_compact", "bnd_pileup_refs", "bnd_collapse_bedgraph",
     "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
 ]
 
@@ -155,6 +155,7 @@ class Native:
         L.bnd_multi_prepare.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.bnd_multi_change_flags.argtypes = [C.c_void_p, C.c_void_p]
         L.bnd_multi_compact.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(Run)), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
+        L.bnd_pileup_refs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
         L.bnd_collapse_bedgraph.argtypes = [C.c_char_p, C.c_char_p]
         L.bnd_scale_factor.restype = C.c_double
         L.bnd_scale_factor.argtypes = [C.c_int32, C.c_float, C.c_uint64, C.c_uint64]
@@ -320,6 +321,16 @@ class PileupHandle:
         data = C.string_at(ptr, n.value)
         self.n.L.bnd_free(ptr)
         return data
+
+    def refs(self):
+        """-> (names, lengths) of the BAM's reference dictionary, header order"""
+        names, lens, n = C.c_void_p(), C.POINTER(C.c_uint64)(), C.c_uint64()
+        self.n.check(self.n.L.bnd_pileup_refs(self.h, C.byref(names), C.byref(lens), C.byref(n)))
+        text = C.string_at(names).decode()
+        out = (text.split("\n") if n.value else [], [int(lens[i]) for i in range(n.value)])
+        self.n.L.bnd_free(names)
+        self.n.L.bnd_free(lens)
+        return out
 
     # ---- one BAM per rank (multi-bam-coverage across GPUs) ----
     def multi_prepare(self) -> int:

@@ -193,6 +193,23 @@ double bnd_scale_factor(int32_t method, float base_scale, uint64_t bin_size, uin
   return base * rpm * per_kb;
 }
 
+int bnd_pileup_refs(bnd_pileup *p, char **names, uint64_t **lens, uint64_t *n_refs) {
+  return guarded([&] {
+    const bnd::BamHeader &h = P(p)->header();
+    std::string joined;
+    for (size_t i = 0; i < h.names.size(); i++) {
+      if (i) joined.push_back('\n');
+      joined += h.names[i];
+    }
+    *n_refs = h.names.size();
+    *names = (char *)malloc(joined.size() + 1);
+    *lens = (uint64_t *)malloc(std::max<size_t>(h.lens.size(), 1) * sizeof(uint64_t));
+    if (!*names || !*lens) throw std::bad_alloc();
+    memcpy(*names, joined.c_str(), joined.size() + 1);
+    for (size_t i = 0; i < h.lens.size(); i++) (*lens)[i] = h.lens[i];
+  });
+}
+
 int bnd_bam_stats(const char *bam_path, uint64_t bin_size, uint64_t out[6]) {
   return guarded([&] {
     bnd_pileup_cfg c;

@@ -148,6 +148,10 @@ int bnd_collapse_bedgraph(const char *in_path, const char *out_path);
 /* ---- NormalizationMethod::scale_factor (signal_normalization.rs:50-74) ------------------------------------ */
 double bnd_scale_factor(int32_t method, float base_scale, uint64_t bin_size, uint64_t n_reads);
 
+/* reference dictionary of the BAM behind a handle (BamStats::chromsizes_ref_id, bam_utils.rs:495-502): names joined by '\n'
+ * and lengths in header order; free both with bnd_free */
+int bnd_pileup_refs(bnd_pileup *p, char **names, uint64_t **lens, uint64_t *n_refs);
+
 /* ---- BamStats (bam_utils.rs:311-436): [n_mapped, n_unmapped, genome_len, chunk_len, n_chunks, n_refs] ----- */
 int bnd_bam_stats(const char *bam_path, uint64_t bin_size, uint64_t out[6]);
 

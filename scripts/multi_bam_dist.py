@@ -55,31 +55,12 @@ with N.pileup(pile, filt) as h:
     if use_cuda:
         torch.cuda.synchronize()
     rows, vals = h.multi_compact(flags.data_ptr())
+    ref_names, _ = h.refs()
 vals_t = torch.from_numpy(vals.astype(np.int64)).to(dev)
 gathered = [torch.empty_like(vals_t) for _ in range(world)] if rank == 0 else None
 dist.gather(vals_t, gathered, dst=0)
 if rank == 0:
     cols = [g.cpu().numpy() for g in gathered]
-    # chromosome names: header of the first BAM (read through the library: tiny host parse of bnd_bam_stats is not enough,
-    # so take them from a bedGraph-free route: the reference ids are header order, names come from the BAM header text)
-    import struct, zlib
-    raw = open(args.bams[0], "rb").read(1 << 22)
-    off, data = 0, b""
-    while off + 18 <= len(raw) and len(data) < (1 << 21):
-        bs = struct.unpack_from("<H", raw, off + 16)[0] + 1
-        if off + bs > len(raw):
-            break
-        data += zlib.decompress(raw[off + 18: off + bs - 8], -15)
-        off += bs
-    l_text = struct.unpack_from("<I", data, 4)[0]
-    p = 8 + l_text
-    n_ref = struct.unpack_from("<I", data, p)[0]
-    p += 4
-    ref_names = []
-    for _ in range(n_ref):
-        l = struct.unpack_from("<I", data, p)[0]
-        ref_names.append(data[p + 4: p + 4 + l - 1].decode())
-        p += 4 + l + 4
     order = np.lexsort((rows["start"], np.array([ref_names[r] for r in rows["ref_id"]], dtype=object)))
     with open(args.output, "w") as f:
         f.write("chrom\tstart\tend\t" + "\t".join(args.bams) + "\n")
