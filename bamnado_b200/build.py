@@ -83,6 +83,8 @@ def build_emul(force: bool = False) -> Path:
         return EMUL_LIB
     EMUL_LIB.parent.mkdir(parents=True, exist_ok=True)
     common = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-pthread", "-DBND_EMUL", "-I", str(EMUL_DIR), "-I", str(CSRC), "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function"]
+    if os.environ.get("BND_EMUL_STATS"):
+        common.append("-DBND_EMUL_STATS")  # walk statistics of the inflate kernels (scripts/spec_stats.py)
     objs, procs = [], []
     for src in DEVICE_SOURCES + HOST_SOURCES:
         o = EMUL_LIB.parent / (src + ".o")

@@ -69,6 +69,8 @@ __device__ __forceinline__ saddr_t smem_addr(const void *p) { return (saddr_t)p;
 __device__ __forceinline__ uint32_t lds_u16(saddr_t a) { return *(const uint16_t *)a; }
 __device__ __forceinline__ uint32_t lds_u32(saddr_t a) { return *(const uint32_t *)a; }
 __device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v) { *(uint32_t *)a = v; }
+__device__ __forceinline__ void cp_async_u32(saddr_t dst, const void *src) { *(uint32_t *)dst = *(const uint32_t *)src; }
+__device__ __forceinline__ void cp_async_wait_all() {}
 #else
 typedef uint32_t saddr_t;
 __device__ __forceinline__ saddr_t smem_addr(const void *p) { return (saddr_t)__cvta_generic_to_shared(p); }
@@ -83,6 +85,11 @@ __device__ __forceinline__ uint32_t lds_u32(saddr_t a) {
   return v;
 }
 __device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// asynchronous 4-byte global -> shared copy (LDGSTS): no register staging, completion awaited with cp_async_wait_all
+__device__ __forceinline__ void cp_async_u32(saddr_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
 // ---- unaligned little-endian loads (BAM records sit at arbitrary byte offsets) ---------------------------------

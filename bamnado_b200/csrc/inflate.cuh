@@ -67,6 +67,17 @@ struct BitReader {
     wp += 3;
     end = pend;
   }
+  // start at bit `bit` of the word array `base` (the speculative decoder addresses the payload by bit offset)
+  __device__ __forceinline__ void init_bits(const uint32_t *base, uint32_t bit, const uint8_t *pend) {
+    wp = base + (bit >> 5);
+    pos = bit & 31u;
+    lo = __ldg(wp);
+    hi = __ldg(wp + 1);
+    nxt = __ldg(wp + 2);
+    wp += 3;
+    end = pend;
+  }
+  __device__ __forceinline__ uint32_t bit_pos(const uint32_t *base) const { return (uint32_t)((wp - 3 - base) << 5) + pos; }
   __device__ __forceinline__ uint32_t window() const { return __funnelshift_r(lo, hi, pos); }  // next 32 bits
   __device__ __forceinline__ void consume(uint32_t n) {  // n <= 32
     pos += n;
@@ -204,6 +215,94 @@ __device__ uint32_t tile_crc32(const Tile<G> &tile, const uint8_t *out, uint32_t
   return ~c;
 }
 
+// Dynamic block header (RFC 1951 3.2.7), read by ONE lane: HLIT/HDIST/HCLEN, the code-length code, then the literal/
+// length and distance code lengths into lens[0..288) and lens[288..320).  Returns an INF_* status.
+__device__ inline int read_dynamic_lengths(BitReader &br, uint16_t *cl_lut, uint8_t *lens) {
+  int st = INF_OK;
+  int hlit = (int)br.take(5) + 257;
+  int hdist = (int)br.take(5) + 1;
+  int hclen = (int)br.take(4) + 4;
+  if (hlit > 286 || hdist > 30) st = INF_BAD_CODELEN;
+  uint8_t cl[19];
+#pragma unroll
+  for (int i = 0; i < 19; i++) cl[i] = 0;
+  for (int i = 0; i < hclen; i++) cl[c_cl_order[i]] = (uint8_t)br.take(3);
+  // cl_lut: 7-bit LUT for the code-length code (128 x u16 of scratch not yet in use for this block)
+  for (int i = 0; i < 128; i++) cl_lut[i] = 0;
+  {
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 19; i++) cnt[cl[i]]++;
+    cnt[0] = 0;
+    int left = 1;
+    uint32_t code = 0, next[8];
+    next[0] = 0;
+    for (int l = 1; l <= 7; l++) {
+      left <<= 1;
+      left -= cnt[l];
+      if (left < 0) st = INF_BAD_CODELEN;
+      code = (code + cnt[l - 1]) << 1;
+      next[l] = code;
+    }
+    if (st == INF_OK)
+      for (int s = 0; s < 19; s++) {
+        int l = cl[s];
+        if (!l) continue;
+        uint32_t rev = __brev(next[l]++) >> (32 - l);
+        for (uint32_t i = rev; i < 128; i += (1u << l)) cl_lut[i] = (uint16_t)((s << 4) | l);
+      }
+  }
+  int n = 0, total = hlit + hdist;
+  int prev = 0;
+  while (st == INF_OK && n < total) {
+    uint32_t w = br.window();
+    uint32_t e = cl_lut[w & 127];
+    int l = e & 15, s = e >> 4;
+    if (l == 0) {
+      st = INF_BAD_CODELEN;
+      break;
+    }
+    if (s < 16) {
+      br.consume(l);
+      lens[n++] = (uint8_t)s;
+      prev = s;
+    } else {
+      int rep, val;
+      if (s == 16) {
+        if (n == 0) {
+          st = INF_BAD_CODELEN;
+          break;
+        }
+        rep = 3 + (int)((w >> l) & 3);
+        br.consume(l + 2);
+        val = prev;
+      } else if (s == 17) {
+        rep = 3 + (int)((w >> l) & 7);
+        br.consume(l + 3);
+        val = 0;
+        prev = 0;
+      } else {
+        rep = 11 + (int)((w >> l) & 127);
+        br.consume(l + 7);
+        val = 0;
+        prev = 0;
+      }
+      if (n + rep > total) {
+        st = INF_BAD_CODELEN;
+        break;
+      }
+      for (int k = 0; k < rep; k++) lens[n++] = (uint8_t)val;
+    }
+  }
+  if (st == INF_OK && lens[256] == 0) st = INF_BAD_CODELEN;  // no end-of-block code
+  if (st == INF_OK) {
+    // move the distance lengths to their fixed slot at 288 (hlit <= 286 < 288: moving up, copy from the top)
+    for (int k = hdist - 1; k >= 0; k--) lens[288 + k] = lens[hlit + k];
+    for (int k = hlit; k < 288; k++) lens[k] = 0;
+    for (int k = hdist; k < 32; k++) lens[288 + k] = 0;
+  }
+  return st;
+}
+
 // The serial half of a batch: walk up to NTOK symbols, store their raw tokens in S.raw, advance the bit reader.
 // Kept out of line on purpose: inside inflate_block the register allocator (capped by the occupancy target) kept
 // re-deriving the shared-memory base addresses in every iteration (S2R + LEA + IMAD chains in the SASS); as a separate
@@ -261,7 +360,6 @@ __device__ __noinline__ uint32_t walk_batch(BitReader &br_ref, TileSmem &S) {
 template <int G, class TileSmem>
 __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &T, const uint8_t *blk, uint32_t blk_size,
                              uint8_t *out, uint32_t isize_expected, const CrcTables *crcT, int verify_crc) {
-  constexpr int LIT_BITS = TileSmem::LIT_BITS, DIST_BITS = TileSmem::DIST_BITS;
   const int lane = tile.lane;
   if (blk_size < 26) return INF_BAD_HEADER;
   uint32_t xlen = blk[10] | ((uint32_t)blk[11] << 8);
@@ -328,88 +426,7 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
       // dynamic: read code-length code, then HLIT + HDIST lengths (lane 0)
       int st = INF_OK;
       if (lane == 0) {
-        int hlit = (int)br.take(5) + 257;
-        int hdist = (int)br.take(5) + 1;
-        int hclen = (int)br.take(4) + 4;
-        if (hlit > 286 || hdist > 30) st = INF_BAD_CODELEN;
-        uint8_t cl[19];
-#pragma unroll
-        for (int i = 0; i < 19; i++) cl[i] = 0;
-        for (int i = 0; i < hclen; i++) cl[c_cl_order[i]] = (uint8_t)br.take(3);
-        // 7-bit LUT for the code-length code, kept in S.codes (not yet in use for this block): 128 x u16
-        uint16_t *cl_lut = S.codes;
-        for (int i = 0; i < 128; i++) cl_lut[i] = 0;
-        {
-          int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          for (int i = 0; i < 19; i++) cnt[cl[i]]++;
-          cnt[0] = 0;
-          int left = 1;
-          uint32_t code = 0, next[8];
-          next[0] = 0;
-          for (int l = 1; l <= 7; l++) {
-            left <<= 1;
-            left -= cnt[l];
-            if (left < 0) st = INF_BAD_CODELEN;
-            code = (code + cnt[l - 1]) << 1;
-            next[l] = code;
-          }
-          if (st == INF_OK)
-            for (int s = 0; s < 19; s++) {
-              int l = cl[s];
-              if (!l) continue;
-              uint32_t rev = __brev(next[l]++) >> (32 - l);
-              for (uint32_t i = rev; i < 128; i += (1u << l)) cl_lut[i] = (uint16_t)((s << 4) | l);
-            }
-        }
-        int n = 0, total = hlit + hdist;
-        int prev = 0;
-        while (st == INF_OK && n < total) {
-          uint32_t w = br.window();
-          uint32_t e = cl_lut[w & 127];
-          int l = e & 15, s = e >> 4;
-          if (l == 0) {
-            st = INF_BAD_CODELEN;
-            break;
-          }
-          if (s < 16) {
-            br.consume(l);
-            S.lens[n++] = (uint8_t)s;
-            prev = s;
-          } else {
-            int rep, val;
-            if (s == 16) {
-              if (n == 0) {
-                st = INF_BAD_CODELEN;
-                break;
-              }
-              rep = 3 + (int)((w >> l) & 3);
-              br.consume(l + 2);
-              val = prev;
-            } else if (s == 17) {
-              rep = 3 + (int)((w >> l) & 7);
-              br.consume(l + 3);
-              val = 0;
-              prev = 0;
-            } else {
-              rep = 11 + (int)((w >> l) & 127);
-              br.consume(l + 7);
-              val = 0;
-              prev = 0;
-            }
-            if (n + rep > total) {
-              st = INF_BAD_CODELEN;
-              break;
-            }
-            for (int k = 0; k < rep; k++) S.lens[n++] = (uint8_t)val;
-          }
-        }
-        if (st == INF_OK && S.lens[256] == 0) st = INF_BAD_CODELEN;  // no end-of-block code
-        if (st == INF_OK) {
-          // move the distance lengths to their fixed slot at 288 (hlit <= 286 < 288: moving up, copy from the top)
-          for (int k = hdist - 1; k >= 0; k--) S.lens[288 + k] = S.lens[hlit + k];
-          for (int k = hlit; k < 288; k++) S.lens[k] = 0;
-          for (int k = hdist; k < 32; k++) S.lens[288 + k] = 0;
-        }
+        st = read_dynamic_lengths(br, S.codes, S.lens);
       }
       st = tile.shfl(st, 0);
       if (st != INF_OK) {
@@ -460,13 +477,6 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
           dist = (dt & 0xffffu) + ((S.raw[2 * NTOK + ti] >> dist_bits) & ~(0xffffffffu << deb));
           bad = lt == 0 || dt == 0;
         }
-#ifdef BND_EMUL_STATS
-        if (mine) {
-          extern unsigned long long g_dbg[8];
-          __atomic_fetch_add(&g_dbg[5], 1ull, __ATOMIC_RELAXED);
-          if (lane == 0) __atomic_fetch_add(&g_dbg[6], 1ull, __ATOMIC_RELAXED);
-        }
-#endif
         const uint32_t olen = is_match ? length : (mine ? 1u : 0u);
         uint32_t incl = olen;
 #pragma unroll
@@ -508,19 +518,6 @@ __device__ int inflate_block(const Tile<G> &tile, TileSmem &S, const SymTables &
               if ((uint32_t)i < length) dst[i] = buf[i];
           }
           uint32_t later = tile.ballot(is_match && !par);
-#ifdef BND_EMUL_STATS
-          if (lane == 0) {
-            extern unsigned long long g_dbg[8];
-            __atomic_fetch_add(&g_dbg[0], (unsigned long long)__builtin_popcount(mmask), __ATOMIC_RELAXED);
-            __atomic_fetch_add(&g_dbg[1], (unsigned long long)__builtin_popcount(later), __ATOMIC_RELAXED);
-          }
-          if (is_match) {
-            extern unsigned long long g_dbg[8];
-            __atomic_fetch_add(&g_dbg[2], (unsigned long long)length, __ATOMIC_RELAXED);
-            if (!par && length > 16) __atomic_fetch_add(&g_dbg[3], 1ull, __ATOMIC_RELAXED);
-            if (!par && dist < length) __atomic_fetch_add(&g_dbg[4], 1ull, __ATOMIC_RELAXED);
-          }
-#endif
           tile.sync();
 #pragma unroll 1
           while (later) {

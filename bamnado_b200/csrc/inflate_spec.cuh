@@ -1,0 +1,574 @@
+// inflate_spec.cuh — K1, second generation: the Huffman walk itself runs 32 lanes wide.
+//
+// profiles/r1_inflate_v10_outofline_walk.txt: with one lane walking the stream, 68 % of the warp instructions of K1 are
+// executed with ONE active thread (≈ 42 instructions per token).  A prefix code re-synchronises by itself: a decoder
+// started at a wrong bit offset falls onto true code boundaries after a few codes and stays on them.  So a round cuts
+// the next 32 * SPAN bits of the stream into 32 spans, one per lane:
+//   pass 1   every lane decodes its span from the span's first bit (lane 0 from the true position) and keeps only where
+//            it left the span (`exit`: the first code boundary at or beyond the span's end);
+//   fix-up   lane i restarts from the exit of lane i-1 whenever that differs from where it started; repeated until
+//            nothing changes.  Lane 0 is right by construction and every iteration makes at least one more lane right,
+//            so the loop ends after <= 32 iterations (typically 2: synchronisation happens well inside one span);
+//   store    the token counts are now exact: a warp scan places every lane's tokens in one compact shared-memory array
+//            and a last pass decodes them for good (length/distance reconstruction included).
+// The warp then finishes the tokens 32 at a time exactly as before (output positions by a scan, literal stores,
+// independent LZ77 copies concurrently, dependent ones in stream order).  Results are bit-identical to a serial inflate
+// by construction: only spans that start on a verified code boundary contribute tokens.
+#pragma once
+#include "inflate.cuh"
+
+namespace bnd {
+
+// Per-warp shared memory.  The code-length scratch (codes/lens) is only live while a block's tables are being built
+// and shares the token array.
+template <int LB, int DB, int NT, int SPAN_BITS>
+struct alignas(16) SpecSmemT {
+  static constexpr int LIT_BITS = LB, DIST_BITS = DB, MAX_TOKENS = NT, SPAN = SPAN_BITS;
+  static constexpr int LIT_SUB = 344;              // second-level entries: zlib's bound for 286 symbols is 308 (root 10) / 340 (root 9), + 2 reserved
+  static constexpr int STAGE_WORDS = SPAN_BITS + 8;  // one round of input: 32 spans + the longest token + the reader's look-ahead
+  // literal/length code: root table of 2^LB entries, then the second-level tables of the codes longer than LB bits.
+  // entry: bits 0-4 = bits to consume (code + extra bits), symbol from bit 7; bits 0-4 == 0: second-level pointer with
+  // bits 5-7 = index width, bits 8-15 = (offset / 2) into the second level (0 = the reserved all-zero entry = no code)
+  uint16_t lit_lut[(1 << LB) + LIT_SUB];
+  uint16_t dist_lut[1 << DB];
+  HuffCanon dist_canon;
+  uint16_t dist_sorted[32];
+  uint32_t stage[STAGE_WORDS];  // this round's compressed words
+  // token: literal = its byte; match = 1 << 31 | (length - 3) << 16 | (distance - 1)
+  uint32_t tokens[NT];
+  __device__ __forceinline__ uint16_t *codes() { return reinterpret_cast<uint16_t *>(tokens); }     // 320 x u16
+  __device__ __forceinline__ uint8_t *lens() { return reinterpret_cast<uint8_t *>(tokens) + 640; }  // 320 x u8
+  static_assert(NT * 4 >= 960, "token array must hold the table-building scratch");
+};
+
+enum : uint32_t { SPAN_OK = 0, SPAN_EOB = 1, SPAN_BAD_SYMBOL = 2, SPAN_BAD_DISTANCE = 3, SPAN_PAST_END = 4 };
+
+// Literal/length tables from lens[0..288): canonical codes, root LUT, second-level tables.  False on an over-subscribed
+// code or one whose second level does not fit (impossible for a complete code).
+template <class Smem>
+__device__ bool build_lit_two_level(const Tile<32> &tile, Smem &S) {
+  constexpr int ROOT = Smem::LIT_BITS, SUB = Smem::LIT_SUB;
+  const int lane = tile.lane;
+  uint16_t *lut = S.lit_lut;
+  uint16_t *codes = S.codes();
+  const uint8_t *lens = S.lens();
+  for (int i = lane; i < (1 << ROOT) + SUB; i += 32) lut[i] = 0;
+  tile.sync();
+  bool ok = true;
+  if (lane == 0) {
+    uint16_t count[16], first[16], next_code[16];
+    for (int l = 0; l < 16; l++) count[l] = 0;
+    for (int s = 0; s < 288; s++) count[lens[s]]++;
+    count[0] = 0;
+    int left = 1;
+    uint32_t code = 0;
+    first[0] = 0;
+    for (int l = 1; l <= 15; l++) {
+      left <<= 1;
+      left -= count[l];
+      if (left < 0) ok = false;
+      code = (code + count[l - 1]) << 1;
+      next_code[l] = (uint16_t)code;
+      first[l] = (uint16_t)code;
+    }
+    if (ok) {
+      for (int s = 0; s < 288; s++) {
+        const int l = lens[s];
+        if (l) codes[s] = next_code[l]++;
+      }
+      // second-level tables, longest codes first: the first code length that reaches a root prefix is its longest
+      uint32_t off = 2;  // entries 0, 1 stay zero: "no code"
+      for (int l = 15; l > ROOT && ok; l--) {
+        if (!count[l]) continue;
+        const uint32_t plo = (uint32_t)first[l] >> (l - ROOT), phi = ((uint32_t)first[l] + count[l] - 1u) >> (l - ROOT);
+        for (uint32_t p = plo; p <= phi; p++) {
+          const uint32_t rp = __brev(p) >> (32 - ROOT);
+          if (lut[rp] != 0) continue;
+          const uint32_t sb = (uint32_t)(l - ROOT);
+          if (off + (1u << sb) > (uint32_t)SUB) {
+            ok = false;
+            break;
+          }
+          lut[rp] = (uint16_t)((sb << 5) | ((off >> 1) << 8));
+          off += 1u << sb;
+        }
+      }
+    }
+  }
+  ok = tile.shfl((int)ok, 0) != 0;
+  tile.sync();
+  if (!ok) return false;
+  for (int s = lane; s < 288; s += 32) {
+    const int l = lens[s];
+    if (l == 0) continue;
+    const uint32_t code = codes[s];
+    const uint16_t e = (uint16_t)lit_entry((uint32_t)s, (uint32_t)l);
+    if (l <= ROOT) {
+      const uint32_t rev = __brev(code) >> (32 - l);
+      for (uint32_t i = rev; i < (1u << ROOT); i += (1u << l)) lut[i] = e;
+    } else {
+      const int k = l - ROOT;
+      const uint32_t pe = lut[__brev(code >> k) >> (32 - ROOT)];
+      const uint32_t sb = (pe >> 5) & 7u, sub0 = (1u << ROOT) + ((pe >> 8) << 1);
+      const uint32_t rlow = __brev(code & ((1u << k) - 1u)) >> (32 - k);
+      for (uint32_t i = rlow; i < (1u << sb); i += (1u << k)) lut[sub0 + i] = e;
+    }
+  }
+  tile.sync();
+  return true;
+}
+
+// Distance tables from lens[288..320): LUT of 2^DB entries + canonical ranges for the (rare) longer codes.
+template <class Smem>
+__device__ bool build_dist_tables(const Tile<32> &tile, Smem &S) {
+  constexpr int BITS = Smem::DIST_BITS;
+  const int lane = tile.lane;
+  uint16_t *codes = S.codes() + 288;
+  const uint8_t *lens = S.lens() + 288;
+  HuffCanon &C = S.dist_canon;
+  for (int i = lane; i < (1 << BITS); i += 32) S.dist_lut[i] = 0;
+  bool ok = true;
+  if (lane == 0) {
+    for (int l = 0; l < 16; l++) C.count[l] = 0;
+    for (int s = 0; s < 32; s++) C.count[lens[s]]++;
+    C.count[0] = 0;
+    uint16_t next_code[16], offs[16];
+    int left = 1;
+    uint32_t code = 0;
+    uint16_t off = 0;
+    C.first[0] = 0;
+    C.offset[0] = 0;
+    for (int l = 1; l <= 15; l++) {
+      left <<= 1;
+      left -= C.count[l];
+      if (left < 0) ok = false;
+      code = (code + C.count[l - 1]) << 1;
+      next_code[l] = (uint16_t)code;
+      C.first[l] = (uint16_t)code;
+      offs[l] = off;
+      C.offset[l] = off;
+      off += C.count[l];
+    }
+    if (ok)
+      for (int s = 0; s < 32; s++) {
+        const int l = lens[s];
+        if (l) {
+          codes[s] = next_code[l]++;
+          S.dist_sorted[offs[l]++] = (uint16_t)s;
+        }
+      }
+  }
+  ok = tile.shfl((int)ok, 0) != 0;
+  tile.sync();
+  if (!ok) return false;
+  {
+    const int l = lens[lane];
+    if (l != 0 && l <= BITS) {
+      const uint32_t rev = __brev((uint32_t)codes[lane]) >> (32 - l);
+      const uint16_t e = (uint16_t)dist_entry((uint32_t)lane, (uint32_t)l);
+      for (uint32_t i = rev; i < (1u << BITS); i += (1u << l)) S.dist_lut[i] = e;
+    }
+  }
+  tile.sync();
+  return true;
+}
+
+// Decode tokens from bit `start` until the position reaches `limit` (> start), an end-of-block code or an undecodable
+// code.  Bits are addressed from the first bit of the staged words.  Returns {bit position after the last token,
+// tokens | flag << 16}.  STORE: also rebuild lengths/distances and write the tokens to shared memory at `tok`.
+// The loop body has one shape for literals and matches (the distance lookup runs for every token and counts only for
+// matches): lanes on different token kinds do not diverge, so an iteration costs one pass through the body.
+template <bool STORE, class Smem>
+__device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &S, const SymTables &T, saddr_t tok) {
+  constexpr int LIT_BITS = Smem::LIT_BITS, DIST_BITS = Smem::DIST_BITS;
+  const saddr_t lit0 = smem_addr(S.lit_lut), dist0 = smem_addr(S.dist_lut);
+  saddr_t wa = smem_addr(S.stage) + 4 * (start >> 5);
+  uint32_t pos = start & 31u;
+  uint32_t lo = lds_u32(wa), hi = lds_u32(wa + 4), nxt = lds_u32(wa + 8);
+  wa += 12;
+  int32_t remain = (int32_t)(limit - start);
+  uint32_t n = 0, flag = SPAN_OK;
+#pragma unroll 1
+  do {
+    const uint32_t w = __funnelshift_r(lo, hi, pos);
+    uint32_t e = lds_u16(lit0 + 2 * (w & ((1u << LIT_BITS) - 1u)));
+    if ((e & 31u) == 0)  // second level (or the reserved zero entry)
+      e = lds_u16(lit0 + 2 * ((1u << LIT_BITS) + ((e >> 8) << 1) + ((w >> LIT_BITS) & ~(0xffffffffu << ((e >> 5) & 7u)))));
+    const uint32_t nb = e & 31u;
+    if (nb == 0) {
+      flag = SPAN_BAD_SYMBOL;
+      break;
+    }
+    pos += nb;
+    if (pos >= 32) {
+      lo = hi;
+      hi = nxt;
+      nxt = lds_u32(wa);
+      wa += 4;
+      pos -= 32;
+    }
+    const uint32_t sym = e >> 7;
+    if (sym == 256) {
+      remain -= (int32_t)nb;
+      flag = SPAN_EOB;
+      break;
+    }
+    const bool is_match = sym > 256;
+    const uint32_t w2 = __funnelshift_r(lo, hi, pos);
+    uint32_t d = lds_u16(dist0 + 2 * (w2 & ((1u << DIST_BITS) - 1u)));
+    if (is_match && (d & 31u) == 0) {  // rare: distance code longer than the lookup width
+      uint32_t ds, dl;
+      if (!canon_decode(w2, DIST_BITS, S.dist_canon, S.dist_sorted, ds, dl)) {
+        flag = SPAN_BAD_DISTANCE;
+        break;
+      }
+      d = dist_entry(ds, dl);
+    }
+    const uint32_t db = is_match ? (d & 31u) : 0u;
+    pos += db;
+    if (pos >= 32) {
+      lo = hi;
+      hi = nxt;
+      nxt = lds_u32(wa);
+      wa += 4;
+      pos -= 32;
+    }
+    remain -= (int32_t)(nb + db);
+    if (STORE) {
+      const uint32_t lt = T.len_tab[(sym - 257u) & 31u];  // 0 marks the invalid symbols 286, 287
+      const uint32_t dt = T.dist_tab[(d >> 8) & 31u];     // 0 marks the invalid symbols 30, 31
+      if (is_match && (lt == 0 || dt == 0)) {
+        flag = lt == 0 ? SPAN_BAD_SYMBOL : SPAN_BAD_DISTANCE;
+        break;
+      }
+      const uint32_t eb = lt >> 16, deb = dt >> 16;
+      const uint32_t length = (lt & 0xffffu) + ((w >> (nb - eb)) & ~(0xffffffffu << eb));
+      const uint32_t dist = (dt & 0xffffu) + ((w2 >> (db - deb)) & ~(0xffffffffu << deb));
+      sts_u32(tok, is_match ? (0x80000000u | ((length - 3u) << 16) | (dist - 1u)) : sym);
+      tok += 4;
+    }
+    n++;
+  } while (remain > 0);
+  return make_uint2((uint32_t)((int32_t)limit - remain), n | (flag << 16));
+}
+
+#ifdef BND_EMUL_STATS
+extern unsigned long long g_dbg[16];
+#define BND_STAT(i, v) __atomic_fetch_add(&g_dbg[i], (unsigned long long)(v), __ATOMIC_RELAXED)
+#else
+#define BND_STAT(i, v) ((void)0)
+#endif
+
+// Inflate one BGZF block with one warp.  Returns a status code (same on every lane).
+template <class Smem>
+__device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables &T, const uint8_t *blk, uint32_t blk_size, uint8_t *out,
+                                  uint32_t isize_expected, const CrcTables *crcT, int verify_crc) {
+  constexpr int NT = Smem::MAX_TOKENS, SPAN = Smem::SPAN, STAGE_WORDS = Smem::STAGE_WORDS;
+  static_assert(SPAN >= 64 && SPAN + 64 <= NT, "a span's tokens must fit the token array");
+  const int lane = tile.lane;
+  if (blk_size < 26) return INF_BAD_HEADER;
+  const uint32_t xlen = blk[10] | ((uint32_t)blk[11] << 8);
+  if (12 + xlen + 8 > blk_size) return INF_BAD_HEADER;
+  const uint8_t *payload = blk + 12 + xlen;
+  const uint8_t *pend = blk + blk_size - 8;
+  const uint32_t crc_expected = pend[0] | ((uint32_t)pend[1] << 8) | ((uint32_t)pend[2] << 16) | ((uint32_t)pend[3] << 24);
+  const uint32_t isize = pend[4] | ((uint32_t)pend[5] << 8) | ((uint32_t)pend[6] << 16) | ((uint32_t)pend[7] << 24);
+  if (isize != isize_expected) return INF_SIZE_MISMATCH;
+
+  // the payload as a bit-addressed array of aligned words
+  const uint32_t *base = (const uint32_t *)((uintptr_t)payload & ~(uintptr_t)3);
+  uint32_t p0 = (uint32_t)((uintptr_t)payload & 3) * 8;
+  const uint32_t end_bit = p0 + (uint32_t)(pend - payload) * 8;
+  const saddr_t tok0 = smem_addr(S.tokens), stage0 = smem_addr(S.stage);
+  const uint32_t word_limit = ((end_bit + 31u) >> 5) + 2u;  // words holding payload bits, + 2 inside the block's 8-byte trailer
+  // asynchronous copy of one round of input, starting at the word holding bit p: global -> shared, zeros past the payload
+  auto stage_issue = [&](uint32_t p) {
+    const uint32_t w0 = p >> 5;
+    for (uint32_t k = (uint32_t)lane; k < (uint32_t)STAGE_WORDS; k += 32) {
+      if (w0 + k < word_limit)
+        cp_async_u32(stage0 + 4 * k, base + w0 + k);
+      else
+        sts_u32(stage0 + 4 * k, 0u);
+    }
+  };
+  uint32_t outpos = 0;
+  int status = INF_OK;
+  bool final_block = false;
+
+  while (!final_block && status == INF_OK) {
+    // ---- block header (lane 0), broadcast ----
+    int btype = 0, st = INF_OK;
+    uint32_t np = p0, stored_len = 0;
+    if (lane == 0) {
+      if (p0 + 3 > end_bit) {
+        st = INF_INPUT_OVERRUN;
+      } else {
+        BitReader br;
+        br.init_bits(base, p0, pend);
+        final_block = br.take(1) != 0;
+        btype = (int)br.take(2);
+        if (btype == 0) {
+          br.align_byte();
+          const uint32_t l = br.take(16), nl = br.take(16);
+          if ((l ^ nl) != 0xffffu) st = INF_BAD_STORED;
+          stored_len = l;
+        } else if (btype == 2) {
+          st = read_dynamic_lengths(br, S.codes(), S.lens());
+        } else if (btype == 3) {
+          st = INF_BAD_BTYPE;
+        }
+        np = br.bit_pos(base);
+      }
+    }
+    st = tile.shfl(st, 0);
+    if (st != INF_OK) {
+      status = st;
+      break;
+    }
+    btype = tile.shfl(btype, 0);
+    final_block = tile.shfl((int)final_block, 0) != 0;
+    p0 = tile.shfl(np, 0);
+    if (btype == 0) {
+      stored_len = tile.shfl(stored_len, 0);
+      const uint8_t *src = (const uint8_t *)base + (p0 >> 3);
+      if (p0 + stored_len * 8 > end_bit) {
+        status = INF_INPUT_OVERRUN;
+        break;
+      }
+      if (outpos + stored_len > isize) {
+        status = INF_OUTPUT_OVERRUN;
+        break;
+      }
+      for (uint32_t i = lane; i < stored_len; i += 32) out[outpos + i] = src[i];
+      outpos += stored_len;
+      p0 += stored_len * 8;
+      tile.sync();
+      continue;
+    }
+    if (btype == 1) {
+      uint8_t *lens = S.lens();
+      for (int s = lane; s < 288; s += 32) lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+      lens[288 + lane] = lane < 30 ? 5 : 0;
+    }
+    tile.sync();
+    if (!build_lit_two_level<Smem>(tile, S) || !build_dist_tables<Smem>(tile, S)) {
+      status = INF_BAD_CODELEN;
+      break;
+    }
+
+    bool eob = false, staged = false;
+    while (!eob && status == INF_OK) {
+      if (p0 >= end_bit) {
+        status = INF_INPUT_OVERRUN;
+        break;
+      }
+      if (!staged) stage_issue(p0);
+      cp_async_wait_all();
+      tile.sync();
+      const uint32_t sbit0 = p0 & ~31u;  // bit address of the first staged word
+      // ---- pass 1: every lane decodes its span from the span's first bit ----
+      uint32_t start = p0 + (uint32_t)lane * SPAN;
+      const uint32_t limit = tmin(p0 + (uint32_t)(lane + 1) * SPAN, end_bit);
+      uint32_t exitb = start, nf = SPAN_PAST_END << 16;
+      if (start < end_bit) {
+        const uint2 r = span_decode<false>(start - sbit0, limit - sbit0, S, T, 0);
+        exitb = r.x + sbit0;
+        nf = r.y;
+      }
+      BND_STAT(0, lane == 0);
+      // ---- fix-up: restart from the predecessor's exit until every live lane starts where its predecessor stopped ----
+      int first_term;
+      for (;;) {
+        uint32_t want = tile.shfl_up(exitb, 1);
+        if (lane == 0) want = p0;
+        const uint32_t term = tile.ballot((nf >> 16) != SPAN_OK);
+        first_term = term ? __ffs((int)term) - 1 : 32;
+        const bool need = lane <= first_term && want != start;
+        if (tile.ballot(need) == 0) break;
+        BND_STAT(1, lane == 0);
+        BND_STAT(2, need);
+        if (need) {
+          start = want;
+          if (start < end_bit) {
+            const uint2 r = span_decode<false>(start - sbit0, limit - sbit0, S, T, 0);
+            exitb = r.x + sbit0;
+            nf = r.y;
+          } else {
+            exitb = start;
+            nf = SPAN_PAST_END << 16;
+          }
+        }
+      }
+      // ---- place the tokens: lanes 0..first_term hold true tokens; take as many whole lanes as the array holds ----
+      const int nvalid = first_term < 32 ? first_term + 1 : 32;
+      const uint32_t n = lane < nvalid ? (nf & 0xffffu) : 0u;
+      uint32_t incl = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = tile.shfl_up(incl, d);
+        if (lane >= d) incl += v;
+      }
+      const bool taken = lane < nvalid && incl <= (uint32_t)NT;
+      const int m = __popc(tile.ballot(taken));  // >= 1: one span never holds more than NT tokens
+      BND_STAT(3, lane == 0 ? nvalid - m : 0);
+      // ---- store pass ----
+      bool bad = false;
+      uint32_t flag = nf >> 16;
+      if (taken && start < end_bit) {
+        const uint2 r = span_decode<true>(start - sbit0, limit - sbit0, S, T, tok0 + 4 * (incl - n));
+        bad = r.x + sbit0 != exitb || (r.y & 0xffffu) != n;  // only an invalid length/distance symbol ends the store pass early
+        if (bad) flag = r.y >> 16;
+      }
+      const uint32_t badmask = tile.ballot(taken && (bad || flag >= SPAN_BAD_SYMBOL));
+      if (badmask) {
+        const uint32_t f = tile.shfl(flag, __ffs((int)badmask) - 1);
+        status = f == SPAN_BAD_SYMBOL ? INF_BAD_SYMBOL : f == SPAN_BAD_DISTANCE ? INF_BAD_DISTANCE : INF_INPUT_OVERRUN;
+        break;
+      }
+      const uint32_t ntok = tile.shfl(incl, m - 1);
+      p0 = tile.shfl(exitb, m - 1);
+      eob = tile.shfl(flag, m - 1) == SPAN_EOB;
+      if (eob && p0 > end_bit) {
+        status = INF_INPUT_OVERRUN;
+        break;
+      }
+      BND_STAT(4, lane == 0 ? ntok : 0);
+      tile.sync();  // tokens visible to the whole warp; nobody reads the staged words any more
+      staged = !eob && p0 < end_bit;
+      if (staged) stage_issue(p0);  // the next round's input arrives while this round's tokens are finished
+      // ---- finish: lane t places token tbase + t ----
+      for (uint32_t tbase = 0; tbase < ntok; tbase += 32) {
+        const uint32_t ti = tbase + (uint32_t)lane;
+        const bool mine = ti < ntok;
+        const uint32_t tk = mine ? S.tokens[ti] : 0u;
+        const bool is_match = (tk >> 31) != 0;
+        const uint32_t length = ((tk >> 16) & 0xffu) + 3u, dist = (tk & 0x7fffu) + 1u;
+        const uint32_t olen = is_match ? length : (mine ? 1u : 0u);
+        uint32_t pin = olen;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t v = tile.shfl_up(pin, d);
+          if (lane >= d) pin += v;
+        }
+        const uint32_t total = tile.shfl(pin, 31);
+        const uint32_t mypos = outpos + pin - olen;
+        if (tile.ballot(is_match && dist > mypos)) {
+          status = INF_BAD_DISTANCE;
+          break;
+        }
+        if (outpos + total > isize) {
+          status = INF_OUTPUT_OVERRUN;
+          break;
+        }
+        if (mine && !is_match) out[mypos] = (uint8_t)tk;
+        const uint32_t mmask = tile.ballot(is_match);
+        if (mmask) {
+          // matches that only read bytes produced before the batch's first match do not depend on each other: those
+          // (<= 16 bytes) are copied concurrently, one per lane, loads before stores; the others follow in stream order
+          const uint32_t first = tile.shfl(mypos, __ffs((int)mmask) - 1);
+          const bool par = is_match && length <= 16 && mypos - dist + length <= first;
+          tile.sync();  // this batch's literals are visible
+          if (par) {
+            const uint8_t *src = out + mypos - dist;
+            uint8_t *dst = out + mypos;
+            uint8_t buf[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+              if ((uint32_t)i < length) buf[i] = src[i];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+              if ((uint32_t)i < length) dst[i] = buf[i];
+          }
+          uint32_t later = tile.ballot(is_match && !par);
+          tile.sync();
+#pragma unroll 1
+          while (later) {
+            const int sl = __ffs((int)later) - 1;
+            later &= later - 1;
+            const uint32_t len = tile.shfl(length, sl), dd = tile.shfl(dist, sl), mp = tile.shfl(mypos, sl);
+            const uint8_t *src = out + mp - dd;
+            uint8_t *dst = out + mp;
+            if (dd >= len) {
+              for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+            } else if (dd >= 32u) {
+              // overlapping with a period of at least one pass: a pass only reads bytes of earlier passes
+              for (uint32_t b = 0; b < len; b += 32) {
+                const uint32_t i = b + lane;
+                if (i < len) dst[i] = src[i];
+                tile.sync();
+              }
+            } else {
+              // short period: every output byte i equals src[i % dist]
+              uint32_t r = (uint32_t)lane % dd;
+              const uint32_t step = 32u % dd;
+              for (uint32_t i = lane; i < len; i += 32) {
+                dst[i] = src[r];
+                r += step;
+                if (r >= dd) r -= dd;
+              }
+            }
+            tile.sync();
+          }
+        } else {
+          tile.sync();
+        }
+        outpos += total;
+      }
+    }
+  }
+  if (status == INF_OK && outpos != isize) status = INF_SIZE_MISMATCH;
+  tile.sync();
+  if (status == INF_OK && verify_crc && isize > 0) {
+    const uint32_t c = tile_crc32<32>(tile, out, isize, crcT);
+    if (c != crc_expected) status = INF_CRC_MISMATCH;
+  }
+  return status;
+}
+
+template <int THREADS, int MIN_CTAS, int LB, int DB, int SPAN, int NT>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) bgzf_inflate_spec_kernel(InflateArgs a) {
+  using Smem = SpecSmemT<LB, DB, NT, SPAN>;
+  BND_DYN_SMEM(smem_raw);
+  constexpr int WARPS = THREADS / 32;
+  Smem *warps = reinterpret_cast<Smem *>(smem_raw);
+  CrcTables *crc_s = reinterpret_cast<CrcTables *>(smem_raw + sizeof(Smem) * WARPS);
+  SymTables *sym_s = reinterpret_cast<SymTables *>(smem_raw + sizeof(Smem) * WARPS + sizeof(CrcTables));
+  if (threadIdx.x < 32) {
+    const uint32_t s = threadIdx.x;
+    const uint32_t eb = s < 8 ? 0u : s == 28 ? 0u : (s - 4) >> 2;
+    const uint32_t lbase = s < 8 ? s + 3 : s == 28 ? 258u : ((4 + (s & 3)) << eb) + 3;
+    sym_s->len_tab[s] = s < 29 ? (lbase | (eb << 16)) : 0u;
+    const uint32_t deb = s < 4 ? 0u : (s >> 1) - 1;
+    const uint32_t dbase = s < 4 ? s + 1 : ((2 + (s & 1)) << deb) + 1;
+    sym_s->dist_tab[s] = s < 30 ? (dbase | (deb << 16)) : 0u;
+  }
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(a.crc);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(crc_s);
+    for (int i = threadIdx.x; i < (int)(sizeof(CrcTables) / 4); i += THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  Tile<32> tile;
+  Smem &S = warps[threadIdx.x / 32];
+  for (;;) {
+    uint32_t b = 0;
+    if (tile.lane == 0) b = atomicAdd(a.work_counter, 1u);
+    b = tile.shfl(b, 0);
+    if (b >= a.n_blocks) break;
+    const uint64_t c0 = a.blk_coff[b], c1 = a.blk_coff[b + 1];
+    const uint64_t u0 = a.blk_uoff[b], u1 = a.blk_uoff[b + 1];
+    const int st = inflate_block_spec<Smem>(tile, S, *sym_s, a.comp + c0, (uint32_t)(c1 - c0), a.out + u0, (uint32_t)(u1 - u0), crc_s, a.verify_crc);
+    if (tile.lane == 0) {
+      if (a.status) a.status[b] = st;
+      if (st != INF_OK) atomicCAS(a.error_flag, 0, st | ((int)(b & 0xffffff) << 8));
+    }
+    tile.sync();
+  }
+}
+
+template <int LB, int DB, int NT, int SPAN>
+constexpr size_t inflate_spec_smem_bytes(int warps) {
+  return sizeof(SpecSmemT<LB, DB, NT, SPAN>) * (size_t)warps + sizeof(CrcTables) + sizeof(SymTables);
+}
+
+}  // namespace bnd

@@ -14,6 +14,7 @@
 #include "collapse.cuh"
 #include "finalize.cuh"
 #include "inflate.cuh"
+#include "inflate_spec.cuh"
 #include "pileup.cuh"
 #include "records.cuh"
 
@@ -40,13 +41,16 @@ struct InflateVariant {
   int g, threads, ctas_per_sm;
 };
 // lane-group width / CTA size / resident CTAs per SM (and LUT widths below); selected with BND_INFLATE_VARIANT
-const InflateVariant kVariants[] = {{32, 256, 5}, {32, 128, 9}, {32, 128, 12}, {32, 256, 6}, {32, 256, 4}, {32, 128, 8}};
+const InflateVariant kVariants[] = {{32, 256, 5}, {32, 128, 9}, {32, 128, 12}, {32, 256, 6}, {32, 256, 4}, {32, 128, 8},
+                                    // 6..: speculative 32-lane walk (inflate_spec.cuh)
+                                    {32, 256, 3}, {32, 128, 5}, {32, 256, 2}, {32, 192, 4}};
+constexpr int kDefaultVariant = 6;  // speculative walk, 256 threads, 3 CTAs / SM (profiles/r1_sweeps.md)
 int variant_index() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("BND_INFLATE_VARIANT");
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v >= (int)(sizeof(kVariants) / sizeof(kVariants[0]))) v = 0;
+    v = e ? atoi(e) : kDefaultVariant;
+    if (v < 0 || v >= (int)(sizeof(kVariants) / sizeof(kVariants[0]))) v = kDefaultVariant;
   }
   return v;
 }
@@ -65,7 +69,27 @@ cudaError_t launch_inflate_t(const InflateArgs &a, int sm_count, int ctas_per_sm
   BND_LAUNCH(kern, dim3(grid), dim3(T), smem, s, a);
   return launched();
 }
+template <int T, int MINB, int LB, int DB, int SPAN, int NT>
+cudaError_t launch_inflate_spec_t(const InflateArgs &a, int sm_count, int ctas_per_sm, cudaStream_t s) {
+  auto kern = bgzf_inflate_spec_kernel<T, MINB, LB, DB, SPAN, NT>;
+  constexpr int warps = T / 32;
+  const size_t smem = inflate_spec_smem_bytes<LB, DB, NT, SPAN>(warps);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  unsigned grid = grid_for(a.n_blocks, warps, (uint64_t)sm_count * ctas_per_sm);
+  BND_LAUNCH(kern, dim3(grid), dim3(T), smem, s, a);
+  return launched();
+}
 }  // namespace
+
+#ifdef BND_EMUL_STATS
+unsigned long long g_dbg[16];
+extern "C" unsigned long long bnd_dbg_counter(int i) { return g_dbg[i & 15]; }
+#endif
 
 int inflate_ctas_per_sm() { return kVariants[variant_index()].ctas_per_sm; }
 
@@ -94,7 +118,11 @@ cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
     case 3: return launch_inflate_t<32, 256, 6, 9, 7>(a, sm_count, v.ctas_per_sm, s);
     case 4: return launch_inflate_t<32, 256, 4, 10, 8>(a, sm_count, v.ctas_per_sm, s);  // 32 warps / SM, <= 64 registers
     case 5: return launch_inflate_t<32, 128, 8, 10, 8>(a, sm_count, v.ctas_per_sm, s);
-    default: return launch_inflate_t<32, 256, 5, 10, 8>(a, sm_count, v.ctas_per_sm, s);
+    case 7: return launch_inflate_spec_t<128, 5, 10, 8, 256, 1024>(a, sm_count, v.ctas_per_sm, s);
+    case 8: return launch_inflate_spec_t<256, 2, 11, 8, 256, 1024>(a, sm_count, v.ctas_per_sm, s);
+    case 9: return launch_inflate_spec_t<192, 4, 10, 8, 192, 768>(a, sm_count, v.ctas_per_sm, s);
+    case 0: return launch_inflate_t<32, 256, 5, 10, 8>(a, sm_count, v.ctas_per_sm, s);  // single-lane walk (round-1 v10)
+    default: return launch_inflate_spec_t<256, 3, 10, 8, 256, 1024>(a, sm_count, v.ctas_per_sm, s);
   }
 }
 

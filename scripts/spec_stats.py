@@ -1,0 +1,43 @@
+"""Walk statistics of the speculative inflate kernel on the CPU emulator (tests/emul), to pick SPAN / NT.
+
+    BND_EMUL_STATS=1 python -m bamnado_b200.build --emul --force
+    BND_INFLATE_VARIANT=6 python scripts/spec_stats.py [pairs]
+Counters (inflate_spec.cuh, BND_STAT): 0 rounds, 1 fix-up iterations, 2 lanes re-decoded in fix-ups, 3 valid lanes
+dropped because the token array was full, 4 tokens.
+"""
+import ctypes, os, subprocess, sys, zlib
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from bamnado_b200._native import Native  # noqa: E402
+from bamnado_b200.build import EMUL_LIB  # noqa: E402
+
+pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+work = Path("/tmp/spec_stats")
+work.mkdir(exist_ok=True)
+bam = work / f"s{pairs}.bam"
+if not bam.exists():
+    synth = ROOT / "tools" / "_build" / "synth_bam"
+    if not synth.exists():
+        synth.parent.mkdir(exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", str(synth), str(ROOT / "tools" / "synth_bam.cpp"), "-lz", "-pthread"])
+    subprocess.check_call([str(synth), "--out", str(bam), "--pairs", str(pairs), "--seed", "20260219"])
+nat = Native(ctypes.CDLL(str(EMUL_LIB)))
+data = bam.read_bytes()
+out, st = nat.bgzf_inflate(data)
+assert (st == 0).all(), st
+d = zlib.decompressobj(31)
+ref = b""
+buf = data
+while buf:
+    d = zlib.decompressobj(31)
+    ref += d.decompress(buf)
+    buf = d.unused_data
+assert out == ref, "inflate mismatch"
+f = nat.L.bnd_dbg_counter
+f.restype = ctypes.c_ulonglong
+c = [f(i) for i in range(8)]
+print(f"blocks {len(st)}  inflated {len(out)} B  compressed {len(data)} B")
+print(f"rounds {c[0]}  tokens {c[4]}  tokens/round {c[4] / max(c[0], 1):.1f}  bits/token {8 * len(data) / max(c[4], 1):.2f}")
+print(f"fix-up iterations/round {c[1] / max(c[0], 1):.2f}  lanes re-decoded/round {c[2] / max(c[0], 1):.2f}  dropped lanes/round {c[3] / max(c[0], 1):.2f}")
