@@ -194,7 +194,17 @@ __device__ uint32_t tile_crc32(const Tile<G> &tile, const uint8_t *out, uint32_t
   uint32_t rounds = nwords / G;  // full rounds of G words
   uint32_t acc = 0;
   if (rounds) {
-    for (uint32_t r = 0; r < rounds; r++) {
+    uint32_t r = 0;
+    for (; r + 4 <= rounds; r += 4) {  // four loads in flight ahead of the table chain
+      uint32_t v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = w[(r + k) * G + lane];
+      if (r == 0 && lane == 0) v[0] ^= c;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        acc = T->z[0][acc & 0xff] ^ T->z[1][(acc >> 8) & 0xff] ^ T->z[2][(acc >> 16) & 0xff] ^ T->z[3][acc >> 24] ^ v[k];
+    }
+    for (; r < rounds; r++) {
       uint32_t v = w[r * G + lane];
       if (r == 0 && lane == 0) v ^= c;
       acc = T->z[0][acc & 0xff] ^ T->z[1][(acc >> 8) & 0xff] ^ T->z[2][(acc >> 16) & 0xff] ^ T->z[3][acc >> 24] ^ v;

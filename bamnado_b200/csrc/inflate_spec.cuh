@@ -462,24 +462,63 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
         }
         if (mine && !is_match) out[mypos] = (uint8_t)tk;
         const uint32_t mmask = tile.ballot(is_match);
+#ifdef BND_EMUL_STATS
+        if (is_match) {
+          BND_STAT(5, 1);
+          BND_STAT(6, length);
+          int b = 8;
+          while (b < 15 && (1u << b) < dist) b++;
+          BND_STAT(b, 1);  // 8: dist <= 256, 9: <= 512, ... 15: <= 32768
+        }
+#endif
         if (mmask) {
-          // matches that only read bytes produced before the batch's first match do not depend on each other: those
-          // (<= 16 bytes) are copied concurrently, one per lane, loads before stores; the others follow in stream order
+          // matches that only read bytes produced before the batch's first match do not depend on each other.  Short ones
+          // (<= 16 bytes) are copied one per lane, up to three longer ones (<= 64 bytes) by the whole warp, and all of
+          // these loads are issued before the first store so that their L2 round trips overlap.  The rest follow in
+          // stream order.
           const uint32_t first = tile.shfl(mypos, __ffs((int)mmask) - 1);
-          const bool par = is_match && length <= 16 && mypos - dist + length <= first;
+          const bool indep = is_match && mypos - dist + length <= first;
+          const bool par = indep && length <= 16;
+          uint32_t wide = tile.ballot(indep && !par && length <= 64);
+          uint32_t later = tile.ballot(is_match && !par);
           tile.sync();  // this batch's literals are visible
+          uint8_t buf[16];
           if (par) {
             const uint8_t *src = out + mypos - dist;
-            uint8_t *dst = out + mypos;
-            uint8_t buf[16];
 #pragma unroll
             for (int i = 0; i < 16; i++)
               if ((uint32_t)i < length) buf[i] = src[i];
+          }
+          uint32_t wlen[3], wpos[3];
+          uint8_t wa[3], wb[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            wlen[k] = 0;
+            wpos[k] = 0;
+            wa[k] = wb[k] = 0;
+            if (wide) {  // uniform
+              const int sl = __ffs((int)wide) - 1;
+              wide &= wide - 1;
+              later &= ~(1u << sl);
+              wlen[k] = tile.shfl(length, sl);
+              wpos[k] = tile.shfl(mypos, sl);
+              const uint8_t *src = out + wpos[k] - tile.shfl(dist, sl);
+              if ((uint32_t)lane < wlen[k]) wa[k] = src[lane];
+              if ((uint32_t)lane + 32u < wlen[k]) wb[k] = src[lane + 32];
+            }
+          }
+          if (par) {
+            uint8_t *dst = out + mypos;
 #pragma unroll
             for (int i = 0; i < 16; i++)
               if ((uint32_t)i < length) dst[i] = buf[i];
           }
-          uint32_t later = tile.ballot(is_match && !par);
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            uint8_t *dst = out + wpos[k];
+            if ((uint32_t)lane < wlen[k]) dst[lane] = wa[k];
+            if ((uint32_t)lane + 32u < wlen[k]) dst[lane + 32] = wb[k];
+          }
           tile.sync();
 #pragma unroll 1
           while (later) {

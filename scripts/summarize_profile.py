@@ -45,7 +45,8 @@ for r in csv.reader(io.StringIO(src)):
 if agg:
     lines.append(f"## source hot spots (warp instructions executed: {tot_i}, stall samples: {tot_s})")
     lines.append("  %inst  %samples  threads/inst  file:line  source")
-    for inst, samp, thr, f, ln, s in sorted(agg, reverse=True)[:40]:
+    top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    for inst, samp, thr, f, ln, s in sorted(agg, reverse=True)[:top]:
         lines.append(f"  {100*inst/max(tot_i,1):5.1f}  {100*samp/max(tot_s,1):5.1f}  {thr/max(inst,1):5.1f}  {f}:{ln}  {s}")
 open(out + ".txt", "w").write("\n".join(lines) + "\n")
 print("wrote", out + ".txt", len(lines), "lines")
