@@ -425,14 +425,20 @@ Pileup::Pileup(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter) : im_(ne
   bam_path_ = cfg->bam_path;
   cfg_.bam_path = nullptr;
   if (cfg_.bin_size == 0) fail("bin size must be greater than 0", ERR_INVALID);
+  const double t_c0 = now_ms();
   im_->ctx = &ctx_for(cfg_.device);
+  const double t_c1 = now_ms();
   open();
+  const double t_c2 = now_ms();
   bnd_filter_cfg dflt;
   memset(&dflt, 0, sizeof dflt);
   dflt.max_length = 0xffffffffu;
   dflt.barcode_csv_column = -1;
   filt_ = make_filter_host(filter ? filter : &dflt, hdr_);
   geo_ = make_geometry(hdr_, bai_, cfg_.bin_size);
+  if (env_u64("BND_DEBUG_TIMING", 0))
+    fprintf(stderr, "[bnd] create: device context %.2f ms, open (index, header, cut points) %.2f ms, filter + geometry %.2f ms\n", t_c1 - t_c0, t_c2 - t_c1,
+            now_ms() - t_c2);
 
   // device copies of geometry and filter tables
   Impl &im = *im_;
@@ -553,7 +559,9 @@ void Pileup::open() {
   struct stat st;
   if (fstat(im.fd, &st) != 0) fail("cannot stat " + bam_path_);
   file_size_ = (uint64_t)st.st_size;
+  const double t_o0 = now_ms();
   bai_ = read_bai(bam_path_ + ".bai");
+  const double t_o1 = now_ms();
   // header: inflate leading BGZF blocks on the device until the header parses
   uint64_t want = 1u << 18;
   std::vector<uint8_t> raw, inflated;
@@ -592,19 +600,31 @@ void Pileup::open() {
     if (want == file_size_) fail("truncated BAM header: " + bam_path_);
     want *= 4;
   }
+  const double t_o2 = now_ms();
   // block starts known from the index: segment cut points
   std::vector<uint64_t> &cp = im.cut_points;
-  for (const BaiRef &R : bai_.refs) {
-    for (const BaiChunk &c : R.chunks) {
-      cp.push_back(c.beg >> 16);
-      cp.push_back(c.end >> 16);
+  // The linear index alone is dense (one entry per 16 kb window) and already in file order for a sorted BAM: take it
+  // with repeats dropped.  Sparse or unordered indexes also contribute their bin chunks and are sorted.
+  bool ordered = true;
+  for (const BaiRef &R : bai_.refs)
+    for (uint64_t v : R.linear) {
+      const uint64_t c = v >> 16;
+      if (!v || (!cp.empty() && cp.back() == c)) continue;
+      if (!cp.empty() && c < cp.back()) ordered = false;
+      cp.push_back(c);
     }
-    for (uint64_t v : R.linear)
-      if (v) cp.push_back(v >> 16);
+  if (!ordered || cp.size() < 1024) {
+    for (const BaiRef &R : bai_.refs)
+      for (const BaiChunk &c : R.chunks) {
+        cp.push_back(c.beg >> 16);
+        cp.push_back(c.end >> 16);
+      }
+    std::sort(cp.begin(), cp.end());
+    cp.erase(std::unique(cp.begin(), cp.end()), cp.end());
   }
-  std::sort(cp.begin(), cp.end());
-  cp.erase(std::unique(cp.begin(), cp.end()), cp.end());
   while (!cp.empty() && cp.back() >= file_size_) cp.pop_back();
+  if (env_u64("BND_DEBUG_TIMING", 0))
+    fprintf(stderr, "[bnd] open: index %.2f ms, header %.2f ms, cut points %.2f ms (%zu)\n", t_o1 - t_o0, t_o2 - t_o1, now_ms() - t_o2, cp.size());
 }
 
 Pileup::Range Pileup::range_for_chunks(uint64_t lo, uint64_t hi) const {
@@ -1702,9 +1722,10 @@ void Pileup::to_bedgraph(const std::string &path) {
         bins_total += nb;
       }
       const double per_row = bins_total > 0 ? bytes / bins_total : 64.0;
-      // 85 % of the upper bound (rows rarely reach it), and never more than the pile-up can hide: it moves ~18 GB/s of
+      // 72 % of the upper bound (rows rarely reach it and are shorter than the longest possible: 2.1 GB of 2.9 GB at the
+      // BASELINE size), and never more than the pile-up can hide: it moves ~30 GB/s of
       // BAM, fallocate ~14 GB/s of pages.  The thread allocates in 64 MiB steps and stops when the pile-up is done.
-      uint64_t want = (uint64_t)((double)rows_cap * per_row * 0.85);
+      uint64_t want = (uint64_t)((double)rows_cap * per_row * 0.72);
       want = std::min<uint64_t>(want, (shard_.byte_end - shard_.byte_begin) * 6 / 10);
       want &= ~(uint64_t)4095;
       if (want > (8ull << 20)) {
