@@ -1,0 +1,125 @@
+"""K1 (speculative 32-lane inflate, bamnado_b200/csrc/inflate_spec.cuh) against zlib on streams chosen to hit its corner cases.
+
+The walk cuts the stream into 32 spans per round and trusts only spans that start on a verified code boundary, so the
+cases here vary what a span can contain: one-bit codes (hundreds of tokens per span, token array full), 15-bit codes
+(second-level table), fixed and stored blocks, several deflate blocks inside one BGZF block (end-of-block inside a
+round), streams shorter than one span, and corrupted streams (every error must surface as a status, never as wrong
+bytes).  Replaces noodles-bgzf block decoding (bamnado/src/coverage_analysis.rs:456-466).
+"""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+
+def bgzf_block(payload: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem_level=9, flush_every=0) -> bytes:
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, mem_level, strategy)
+    if flush_every:  # Z_FULL_FLUSH ends the deflate block: several blocks (and empty stored ones) per BGZF block
+        comp = b""
+        for i in range(0, len(payload), flush_every):
+            comp += co.compress(payload[i:i + flush_every]) + co.flush(zlib.Z_FULL_FLUSH)
+        comp += co.flush()
+    else:
+        comp = co.compress(payload) + co.flush()
+    assert len(comp) + 26 <= 65536, "payload does not fit one BGZF block"
+    return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", 18 + len(comp) + 8 - 1) + comp
+            + struct.pack("<II", zlib.crc32(payload), len(payload)))
+
+
+def payload_zoo(seed=11):
+    rng = np.random.default_rng(seed)
+    zoo = {}
+    zoo["two_symbols"] = bytes(rng.integers(0, 2, 65000, dtype=np.uint8) + 65)          # ~1-bit literal codes
+    zoo["skewed"] = bytes(rng.choice(np.arange(64, dtype=np.uint8), 60000, p=np.r_[0.6, np.full(63, 0.4 / 63)]))
+    zoo["zipf"] = bytes(np.minimum(rng.zipf(1.3, 60000), 255).astype(np.uint8))          # long tail -> 13-15 bit codes
+    zoo["all_bytes_once_then_run"] = bytes(range(256)) + b"\x07" * 60000
+    zoo["random"] = bytes(rng.integers(0, 256, 50000, dtype=np.uint8))
+    zoo["long_matches"] = (bytes(rng.integers(0, 256, 300, dtype=np.uint8)) * 220)[:65000]
+    zoo["period_1_to_40"] = b"".join(bytes(rng.integers(0, 256, p, dtype=np.uint8)) * (1500 // p) for p in range(1, 41))
+    rec = bytes(rng.integers(0, 256, 220, dtype=np.uint8))
+    zoo["bam_like"] = b"".join(bytes(a ^ (rng.integers(0, 256) if rng.random() < 0.08 else 0) for a in rec) for _ in range(280))
+    zoo["tiny_1"] = b"x"
+    zoo["tiny_31"] = bytes(range(31))
+    zoo["empty"] = b""
+    return zoo
+
+
+def test_spec_inflate_matches_zlib_over_payload_zoo(backend):
+    zoo = payload_zoo()
+    blocks, expected, names = [], [], []
+    for name, p in zoo.items():
+        for level, strategy in [(6, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED),
+                                (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE), (6, zlib.Z_FILTERED)]:
+            if strategy == zlib.Z_HUFFMAN_ONLY and name == "random":
+                p_use = p[:40000]  # incompressible + Huffman-only would overflow one BGZF block
+            else:
+                p_use = p
+            try:
+                blocks.append(bgzf_block(p_use, level, strategy))
+            except AssertionError:
+                continue
+            expected.append(p_use)
+            names.append((name, level, strategy))
+    out, status = backend.bgzf_inflate(b"".join(blocks))
+    bad = [n for n, s in zip(names, status) if s != 0]
+    assert not bad, f"non-zero status for {bad}"
+    assert out == b"".join(expected)
+
+
+def test_spec_inflate_many_deflate_blocks_per_bgzf_block(backend):
+    # end-of-block codes, block headers and empty stored blocks in the middle of rounds; small mem_level = short blocks
+    zoo = payload_zoo(5)
+    blocks, expected = [], []
+    for name in ("bam_like", "skewed", "zipf", "two_symbols", "long_matches"):
+        for flush_every in (97, 1000, 4096):
+            p = zoo[name][:30000]
+            blocks.append(bgzf_block(p, 6, flush_every=flush_every))
+            expected.append(p)
+        blocks.append(bgzf_block(zoo[name][:60000], 6, mem_level=1))  # 128-token deflate blocks
+        expected.append(zoo[name][:60000])
+    out, status = backend.bgzf_inflate(b"".join(blocks))
+    assert list(status) == [0] * len(blocks)
+    assert out == b"".join(expected)
+
+
+def test_spec_inflate_corruption_is_detected_not_decoded(backend):
+    # flip one bit at many places of a valid block: the status must be non-zero (CRC at the very least) or the bytes equal
+    rng = np.random.default_rng(17)
+    zoo = payload_zoo(23)
+    for name in ("bam_like", "zipf"):
+        payload = zoo[name][:40000]
+        good = bytearray(bgzf_block(payload))
+        variants = []
+        for _ in range(24):
+            b = bytearray(good)
+            pos = int(rng.integers(18, len(b) - 8))
+            b[pos] ^= 1 << int(rng.integers(0, 8))
+            variants.append(bytes(b))
+        # each corrupted block is followed by a good one: an error must not leak into the neighbour
+        stream = b"".join(v + bytes(good) for v in variants)
+        out, status = backend.bgzf_inflate(stream)
+        assert len(status) == 2 * len(variants)
+        off = 0
+        for i, s in enumerate(status):
+            chunk = out[off:off + len(payload)]
+            off += len(payload)
+            if i % 2 == 1:
+                assert s == 0 and chunk == payload
+            else:
+                assert s != 0 or chunk == payload
+
+
+@pytest.mark.gpu
+def test_spec_inflate_zoo_on_gpu_many_copies(native_gpu):
+    # the same zoo, every block repeated so that all resident warps decode different streams side by side
+    zoo = payload_zoo(31)
+    blocks, expected = [], []
+    for rep in range(40):
+        for name, p in zoo.items():
+            q = p[rep:] if len(p) > rep else p
+            blocks.append(bgzf_block(q, 1 + rep % 9))
+            expected.append(q)
+    out, status = native_gpu.bgzf_inflate(b"".join(blocks))
+    assert int(np.count_nonzero(status)) == 0
+    assert out == b"".join(expected)
