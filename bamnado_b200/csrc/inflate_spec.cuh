@@ -9,21 +9,26 @@
 //   fix-up   lane i restarts from the exit of lane i-1 whenever that differs from where it started; repeated until
 //            nothing changes.  Lane 0 is right by construction and every iteration makes at least one more lane right,
 //            so the loop ends after <= 32 iterations (typically 2: synchronisation happens well inside one span);
-//   store    the token counts are now exact: a warp scan places every lane's tokens in one compact shared-memory array
-//            and a last pass decodes them for good (length/distance reconstruction included).
-// The warp then finishes the tokens 32 at a time exactly as before (output positions by a scan, literal stores,
-// independent LZ77 copies concurrently, dependent ones in stream order).  Results are bit-identical to a serial inflate
-// by construction: only spans that start on a verified code boundary contribute tokens.
+//   store    every lane now knows how many bytes and matches the lanes before it produce (a warp scan), so a last pass
+//            writes the literals straight to their place in the output and appends the matches (position, length,
+//            distance) to one list in shared memory.
+// The warp then resolves the round's matches 32 at a time: those whose source lies before the first unfinished match
+// are copied concurrently (their L2 round trips overlap), the rest follow wave by wave.  Results are bit-identical
+// to a serial inflate by construction: only spans that start on a verified code boundary contribute tokens.
 #pragma once
 #include "inflate.cuh"
 
 namespace bnd {
 
+#ifndef BND_SPEC_RUNIN
+#define BND_SPEC_RUNIN 0
+#endif
+
 // Per-warp shared memory.  The code-length scratch (codes/lens) is only live while a block's tables are being built
 // and shares the token array.
 template <int LB, int DB, int NT, int SPAN_BITS>
 struct alignas(16) SpecSmemT {
-  static constexpr int LIT_BITS = LB, DIST_BITS = DB, MAX_TOKENS = NT, SPAN = SPAN_BITS;
+  static constexpr int LIT_BITS = LB, DIST_BITS = DB, MAX_MATCHES = NT, SPAN = SPAN_BITS;
   static constexpr int LIT_SUB = 344;              // second-level entries: zlib's bound for 286 symbols is 308 (root 10) / 340 (root 9), + 2 reserved
   static constexpr int STAGE_WORDS = SPAN_BITS + 8;  // one round of input: 32 spans + the longest token + the reader's look-ahead
   // literal/length code: root table of 2^LB entries, then the second-level tables of the codes longer than LB bits.
@@ -34,11 +39,11 @@ struct alignas(16) SpecSmemT {
   HuffCanon dist_canon;
   uint16_t dist_sorted[32];
   uint32_t stage[STAGE_WORDS];  // this round's compressed words
-  // token: literal = its byte; match = 1 << 31 | (length - 3) << 16 | (distance - 1)
-  uint32_t tokens[NT];
-  __device__ __forceinline__ uint16_t *codes() { return reinterpret_cast<uint16_t *>(tokens); }     // 320 x u16
-  __device__ __forceinline__ uint8_t *lens() { return reinterpret_cast<uint8_t *>(tokens) + 640; }  // 320 x u8
-  static_assert(NT * 4 >= 960, "token array must hold the table-building scratch");
+  // the round's matches in stream order: {output position | (length - 3) << 16, distance}
+  uint2 matches[NT];
+  __device__ __forceinline__ uint16_t *codes() { return reinterpret_cast<uint16_t *>(matches); }     // 320 x u16
+  __device__ __forceinline__ uint8_t *lens() { return reinterpret_cast<uint8_t *>(matches) + 640; }  // 320 x u8
+  static_assert(NT * 8 >= 960, "match list must hold the table-building scratch");
 };
 
 enum : uint32_t { SPAN_OK = 0, SPAN_EOB = 1, SPAN_BAD_SYMBOL = 2, SPAN_BAD_DISTANCE = 3, SPAN_PAST_END = 4 };
@@ -174,12 +179,13 @@ __device__ bool build_dist_tables(const Tile<32> &tile, Smem &S) {
 }
 
 // Decode tokens from bit `start` until the position reaches `limit` (> start), an end-of-block code or an undecodable
-// code.  Bits are addressed from the first bit of the staged words.  Returns {bit position after the last token,
-// tokens | flag << 16}.  STORE: also rebuild lengths/distances and write the tokens to shared memory at `tok`.
+// code.  Bits are addressed from the first bit of the staged words.  Returns {bit position after the last token |
+// flag << 24, matches | output bytes << 12}.  STORE: the span is known to be a true one and `opos` is the output position
+// of its first byte: literals go straight to out[], matches are appended to the list at `ml`.
 // The loop body has one shape for literals and matches (the distance lookup runs for every token and counts only for
 // matches): lanes on different token kinds do not diverge, so an iteration costs one pass through the body.
 template <bool STORE, class Smem>
-__device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &S, const SymTables &T, saddr_t tok) {
+__device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &S, const SymTables &T, uint8_t *out, uint32_t opos, saddr_t ml) {
   constexpr int LIT_BITS = Smem::LIT_BITS, DIST_BITS = Smem::DIST_BITS;
   const saddr_t lit0 = smem_addr(S.lit_lut), dist0 = smem_addr(S.dist_lut);
   saddr_t wa = smem_addr(S.stage) + 4 * (start >> 5);
@@ -187,7 +193,7 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
   uint32_t lo = lds_u32(wa), hi = lds_u32(wa + 4), nxt = lds_u32(wa + 8);
   wa += 12;
   int32_t remain = (int32_t)(limit - start);
-  uint32_t n = 0, flag = SPAN_OK;
+  uint32_t nm = 0, bytes = 0, flag = SPAN_OK;
 #pragma unroll 1
   do {
     const uint32_t w = __funnelshift_r(lo, hi, pos);
@@ -214,10 +220,16 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
       break;
     }
     const bool is_match = sym > 256;
+    // length base | extra bits << 16 (0 marks the invalid symbols 286, 287); a literal counts as base 1 without extra bits
+    const uint32_t lt = is_match ? T.len_tab[(sym - 257u) & 31u] : 1u;
     const uint32_t w2 = __funnelshift_r(lo, hi, pos);
     uint32_t d = lds_u16(dist0 + 2 * (w2 & ((1u << DIST_BITS) - 1u)));
-    if (is_match && (d & 31u) == 0) {  // rare: distance code longer than the lookup width
+    if (is_match && ((d & 31u) == 0 || lt == 0)) {  // rare: distance code longer than the lookup width, or a bad symbol
       uint32_t ds, dl;
+      if (lt == 0) {
+        flag = SPAN_BAD_SYMBOL;
+        break;
+      }
       if (!canon_decode(w2, DIST_BITS, S.dist_canon, S.dist_sorted, ds, dl)) {
         flag = SPAN_BAD_DISTANCE;
         break;
@@ -234,22 +246,28 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
       pos -= 32;
     }
     remain -= (int32_t)(nb + db);
+    const uint32_t eb = lt >> 16;
+    const uint32_t length = (lt & 0xffffu) + ((w >> (nb - eb)) & ~(0xffffffffu << eb));
     if (STORE) {
-      const uint32_t lt = T.len_tab[(sym - 257u) & 31u];  // 0 marks the invalid symbols 286, 287
-      const uint32_t dt = T.dist_tab[(d >> 8) & 31u];     // 0 marks the invalid symbols 30, 31
-      if (is_match && (lt == 0 || dt == 0)) {
-        flag = lt == 0 ? SPAN_BAD_SYMBOL : SPAN_BAD_DISTANCE;
-        break;
+      if (is_match) {
+        const uint32_t dt = T.dist_tab[(d >> 8) & 31u];  // 0 marks the invalid symbols 30, 31
+        const uint32_t deb = dt >> 16;
+        const uint32_t dist = (dt & 0xffffu) + ((w2 >> (db - deb)) & ~(0xffffffffu << deb));
+        if (dt == 0 || dist > opos + bytes) {
+          flag = SPAN_BAD_DISTANCE;
+          break;
+        }
+        sts_u32(ml, (opos + bytes) | ((length - 3u) << 16));
+        sts_u32(ml + 4, dist);
+        ml += 8;
+      } else {
+        out[opos + bytes] = (uint8_t)sym;
       }
-      const uint32_t eb = lt >> 16, deb = dt >> 16;
-      const uint32_t length = (lt & 0xffffu) + ((w >> (nb - eb)) & ~(0xffffffffu << eb));
-      const uint32_t dist = (dt & 0xffffu) + ((w2 >> (db - deb)) & ~(0xffffffffu << deb));
-      sts_u32(tok, is_match ? (0x80000000u | ((length - 3u) << 16) | (dist - 1u)) : sym);
-      tok += 4;
     }
-    n++;
+    bytes += length;
+    nm += is_match ? 1u : 0u;
   } while (remain > 0);
-  return make_uint2((uint32_t)((int32_t)limit - remain), n | (flag << 16));
+  return make_uint2((uint32_t)((int32_t)limit - remain) | (flag << 24), nm | (bytes << 12));
 }
 
 #ifdef BND_EMUL_STATS
@@ -263,8 +281,8 @@ extern unsigned long long g_dbg[16];
 template <class Smem>
 __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables &T, const uint8_t *blk, uint32_t blk_size, uint8_t *out,
                                   uint32_t isize_expected, const CrcTables *crcT, int verify_crc) {
-  constexpr int NT = Smem::MAX_TOKENS, SPAN = Smem::SPAN, STAGE_WORDS = Smem::STAGE_WORDS;
-  static_assert(SPAN >= 64 && SPAN + 64 <= NT, "a span's tokens must fit the token array");
+  constexpr int NM = Smem::MAX_MATCHES, SPAN = Smem::SPAN, STAGE_WORDS = Smem::STAGE_WORDS, RUNIN = BND_SPEC_RUNIN;
+  static_assert(SPAN >= 64 && (SPAN + 64) / 2 <= NM, "a span's matches (>= 2 bits each) must fit the match list");
   const int lane = tile.lane;
   if (blk_size < 26) return INF_BAD_HEADER;
   const uint32_t xlen = blk[10] | ((uint32_t)blk[11] << 8);
@@ -279,7 +297,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
   const uint32_t *base = (const uint32_t *)((uintptr_t)payload & ~(uintptr_t)3);
   uint32_t p0 = (uint32_t)((uintptr_t)payload & 3) * 8;
   const uint32_t end_bit = p0 + (uint32_t)(pend - payload) * 8;
-  const saddr_t tok0 = smem_addr(S.tokens), stage0 = smem_addr(S.stage);
+  const saddr_t ml0 = smem_addr(S.matches), stage0 = smem_addr(S.stage);
   const uint32_t word_limit = ((end_bit + 31u) >> 5) + 2u;  // words holding payload bits, + 2 inside the block's 8-byte trailer
   // asynchronous copy of one round of input, starting at the word holding bit p: global -> shared, zeros past the payload
   auto stage_issue = [&](uint32_t p) {
@@ -367,21 +385,30 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
       tile.sync();
       const uint32_t sbit0 = p0 & ~31u;  // bit address of the first staged word
       // ---- pass 1: every lane decodes its span from the span's first bit ----
-      uint32_t start = p0 + (uint32_t)lane * SPAN;
+      // (speculative lanes start RUNIN bits early: more codes to fall into step with the true sequence before the span's end)
+      uint32_t start = p0 + (uint32_t)lane * SPAN - (lane ? (uint32_t)RUNIN : 0u);
       const uint32_t limit = tmin(p0 + (uint32_t)(lane + 1) * SPAN, end_bit);
-      uint32_t exitb = start, nf = SPAN_PAST_END << 16;
-      if (start < end_bit) {
-        const uint2 r = span_decode<false>(start - sbit0, limit - sbit0, S, T, 0);
-        exitb = r.x + sbit0;
-        nf = r.y;
-      }
+      uint32_t exitb = start, flag = SPAN_PAST_END, cnt = 0;  // cnt: matches | bytes << 12
+      auto scan = [&]() {
+        if (start < end_bit) {
+          const uint2 r = span_decode<false>(start - sbit0, limit - sbit0, S, T, nullptr, 0u, 0);
+          exitb = (r.x & 0xffffffu) + sbit0;
+          flag = r.x >> 24;
+          cnt = r.y;
+        } else {
+          exitb = start;
+          flag = SPAN_PAST_END;
+          cnt = 0;
+        }
+      };
+      scan();
       BND_STAT(0, lane == 0);
       // ---- fix-up: restart from the predecessor's exit until every live lane starts where its predecessor stopped ----
       int first_term;
       for (;;) {
         uint32_t want = tile.shfl_up(exitb, 1);
         if (lane == 0) want = p0;
-        const uint32_t term = tile.ballot((nf >> 16) != SPAN_OK);
+        const uint32_t term = tile.ballot(flag != SPAN_OK);
         first_term = term ? __ffs((int)term) - 1 : 32;
         const bool need = lane <= first_term && want != start;
         if (tile.ballot(need) == 0) break;
@@ -389,35 +416,35 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
         BND_STAT(2, need);
         if (need) {
           start = want;
-          if (start < end_bit) {
-            const uint2 r = span_decode<false>(start - sbit0, limit - sbit0, S, T, 0);
-            exitb = r.x + sbit0;
-            nf = r.y;
-          } else {
-            exitb = start;
-            nf = SPAN_PAST_END << 16;
-          }
+          scan();
         }
       }
-      // ---- place the tokens: lanes 0..first_term hold true tokens; take as many whole lanes as the array holds ----
+      // ---- place: lanes 0..first_term hold true tokens; take as many whole lanes as the match list holds ----
       const int nvalid = first_term < 32 ? first_term + 1 : 32;
-      const uint32_t n = lane < nvalid ? (nf & 0xffffu) : 0u;
-      uint32_t incl = n;
+      const uint32_t nm = lane < nvalid ? (cnt & 0xfffu) : 0u, nbytes = lane < nvalid ? (cnt >> 12) : 0u;
+      uint32_t minc = nm, binc = nbytes;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = tile.shfl_up(incl, d);
-        if (lane >= d) incl += v;
+        const uint32_t v = tile.shfl_up(minc, d), u = tile.shfl_up(binc, d);
+        if (lane >= d) {
+          minc += v;
+          binc += u;
+        }
       }
-      const bool taken = lane < nvalid && incl <= (uint32_t)NT;
-      const int m = __popc(tile.ballot(taken));  // >= 1: one span never holds more than NT tokens
+      const bool taken = lane < nvalid && minc <= (uint32_t)NM;
+      const int m = __popc(tile.ballot(taken));  // >= 1: one span never holds more than NM matches
       BND_STAT(3, lane == 0 ? nvalid - m : 0);
-      // ---- store pass ----
+      const uint32_t total = tile.shfl(binc, m - 1), nmatch = tile.shfl(minc, m - 1);
+      if (outpos + total > isize) {
+        status = INF_OUTPUT_OVERRUN;
+        break;
+      }
+      // ---- store pass: literals to out[], matches to the list ----
       bool bad = false;
-      uint32_t flag = nf >> 16;
       if (taken && start < end_bit) {
-        const uint2 r = span_decode<true>(start - sbit0, limit - sbit0, S, T, tok0 + 4 * (incl - n));
-        bad = r.x + sbit0 != exitb || (r.y & 0xffffu) != n;  // only an invalid length/distance symbol ends the store pass early
-        if (bad) flag = r.y >> 16;
+        const uint2 r = span_decode<true>(start - sbit0, limit - sbit0, S, T, out, outpos + binc - nbytes, ml0 + 8 * (minc - nm));
+        bad = (r.x & 0xffffffu) + sbit0 != exitb || r.y != cnt;  // only an invalid distance ends the store pass early
+        if (bad) flag = r.x >> 24;
       }
       const uint32_t badmask = tile.ballot(taken && (bad || flag >= SPAN_BAD_SYMBOL));
       if (badmask) {
@@ -425,63 +452,67 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
         status = f == SPAN_BAD_SYMBOL ? INF_BAD_SYMBOL : f == SPAN_BAD_DISTANCE ? INF_BAD_DISTANCE : INF_INPUT_OVERRUN;
         break;
       }
-      const uint32_t ntok = tile.shfl(incl, m - 1);
       p0 = tile.shfl(exitb, m - 1);
       eob = tile.shfl(flag, m - 1) == SPAN_EOB;
       if (eob && p0 > end_bit) {
         status = INF_INPUT_OVERRUN;
         break;
       }
-      BND_STAT(4, lane == 0 ? ntok : 0);
-      tile.sync();  // tokens visible to the whole warp; nobody reads the staged words any more
+      BND_STAT(4, lane == 0 ? nmatch : 0);
+      tile.sync();  // literals and the match list are visible to the whole warp; nobody reads the staged words any more
       staged = !eob && p0 < end_bit;
-      if (staged) stage_issue(p0);  // the next round's input arrives while this round's tokens are finished
-      // ---- finish: lane t places token tbase + t ----
-      for (uint32_t tbase = 0; tbase < ntok; tbase += 32) {
-        const uint32_t ti = tbase + (uint32_t)lane;
-        const bool mine = ti < ntok;
-        const uint32_t tk = mine ? S.tokens[ti] : 0u;
-        const bool is_match = (tk >> 31) != 0;
-        const uint32_t length = ((tk >> 16) & 0xffu) + 3u, dist = (tk & 0x7fffu) + 1u;
-        const uint32_t olen = is_match ? length : (mine ? 1u : 0u);
-        uint32_t pin = olen;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t v = tile.shfl_up(pin, d);
-          if (lane >= d) pin += v;
-        }
-        const uint32_t total = tile.shfl(pin, 31);
-        const uint32_t mypos = outpos + pin - olen;
-        if (tile.ballot(is_match && dist > mypos)) {
-          status = INF_BAD_DISTANCE;
-          break;
-        }
-        if (outpos + total > isize) {
-          status = INF_OUTPUT_OVERRUN;
-          break;
-        }
-        if (mine && !is_match) out[mypos] = (uint8_t)tk;
-        const uint32_t mmask = tile.ballot(is_match);
-#ifdef BND_EMUL_STATS
-        if (is_match) {
-          BND_STAT(5, 1);
-          BND_STAT(6, length);
-          int b = 8;
-          while (b < 15 && (1u << b) < dist) b++;
-          BND_STAT(b, 1);  // 8: dist <= 256, 9: <= 512, ... 15: <= 32768
-        }
-#endif
-        if (mmask) {
-          // matches that only read bytes produced before the batch's first match do not depend on each other.  Short ones
-          // (<= 16 bytes) are copied one per lane, up to three longer ones (<= 64 bytes) by the whole warp, and all of
-          // these loads are issued before the first store so that their L2 round trips overlap.  The rest follow in
-          // stream order.
-          const uint32_t first = tile.shfl(mypos, __ffs((int)mmask) - 1);
-          const bool indep = is_match && mypos - dist + length <= first;
-          const bool par = indep && length <= 16;
-          uint32_t wide = tile.ballot(indep && !par && length <= 64);
-          uint32_t later = tile.ballot(is_match && !par);
-          tile.sync();  // this batch's literals are visible
+      if (staged) stage_issue(p0);  // the next round's input arrives while this round's matches are resolved
+      // ---- resolve the matches, 32 at a time: lane t owns match mb + t ----
+      for (uint32_t mb = 0; mb < nmatch; mb += 32) {
+        const bool mine = mb + (uint32_t)lane < nmatch;
+        const uint2 me = mine ? S.matches[mb + lane] : make_uint2(0u, 1u);
+        const uint32_t mypos = me.x & 0xffffu, length = (me.x >> 16) + 3u, dist = me.y;
+        const uint32_t src_end = mypos - dist + length;
+        uint32_t pend = tile.ballot(mine);
+        BND_STAT(6, lane == 0);
+        // Everything before the first unfinished match is final (literals were stored by the store pass), so every
+        // match whose source ends there can be copied now, all of them at once; the first unfinished one itself always
+        // can (its source precedes it, or it repeats its own first bytes).  Usually one or two waves empty the batch.
+#pragma unroll 1
+        while (pend) {
+          const int fl = __ffs((int)pend) - 1;
+          const uint32_t frontier = tile.shfl(mypos, fl);
+          const bool ready = ((pend >> lane) & 1u) != 0 && src_end <= frontier;
+          const uint32_t rmask = tile.ballot(ready);
+          BND_STAT(5, lane == 0);
+          if (rmask == 0) {
+            BND_STAT(7, lane == 0);
+            // the first unfinished match overlaps its own output: period `dist` < length, copied by the whole warp
+            const uint32_t len = tile.shfl(length, fl), dd = tile.shfl(dist, fl);
+            const uint8_t *src = out + frontier - dd;
+            uint8_t *dst = out + frontier;
+            if (dd >= 32u) {
+              // a pass of 32 bytes only reads bytes of earlier passes
+              for (uint32_t b = 0; b < len; b += 32) {
+                const uint32_t i = b + lane;
+                if (i < len) dst[i] = src[i];
+                tile.sync();
+              }
+            } else {
+              // short period: output byte i equals src[i % dist]
+              uint32_t r = (uint32_t)lane % dd;
+              const uint32_t step = 32u % dd;
+              for (uint32_t i = lane; i < len; i += 32) {
+                dst[i] = src[r];
+                r += step;
+                if (r >= dd) r -= dd;
+              }
+            }
+            pend &= ~(1u << fl);
+            tile.sync();
+            continue;
+          }
+          // short ready matches (<= 16 bytes): one per lane; longer ones: the whole warp, up to three at a time
+          // (<= 64 bytes each) with all loads issued before the first store; the rare longer ones one by one
+          const bool par = ready && length <= 16;
+          uint32_t wide = rmask & ~tile.ballot(par);
+          const uint32_t wide0 = wide;
+          (void)wide0;
           uint8_t buf[16];
           if (par) {
             const uint8_t *src = out + mypos - dist;
@@ -498,13 +529,14 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
             wa[k] = wb[k] = 0;
             if (wide) {  // uniform
               const int sl = __ffs((int)wide) - 1;
-              wide &= wide - 1;
-              later &= ~(1u << sl);
-              wlen[k] = tile.shfl(length, sl);
-              wpos[k] = tile.shfl(mypos, sl);
-              const uint8_t *src = out + wpos[k] - tile.shfl(dist, sl);
-              if ((uint32_t)lane < wlen[k]) wa[k] = src[lane];
-              if ((uint32_t)lane + 32u < wlen[k]) wb[k] = src[lane + 32];
+              if (tile.shfl(length, sl) <= 64u) {
+                wide &= wide - 1;
+                wlen[k] = tile.shfl(length, sl);
+                wpos[k] = tile.shfl(mypos, sl);
+                const uint8_t *src = out + wpos[k] - tile.shfl(dist, sl);
+                if ((uint32_t)lane < wlen[k]) wa[k] = src[lane];
+                if ((uint32_t)lane + 32u < wlen[k]) wb[k] = src[lane + 32];
+              }
             }
           }
           if (par) {
@@ -519,40 +551,23 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
             if ((uint32_t)lane < wlen[k]) dst[lane] = wa[k];
             if ((uint32_t)lane + 32u < wlen[k]) dst[lane + 32] = wb[k];
           }
-          tile.sync();
 #pragma unroll 1
-          while (later) {
-            const int sl = __ffs((int)later) - 1;
-            later &= later - 1;
-            const uint32_t len = tile.shfl(length, sl), dd = tile.shfl(dist, sl), mp = tile.shfl(mypos, sl);
-            const uint8_t *src = out + mp - dd;
+          BND_STAT(9, lane == 0 ? __builtin_popcount(rmask) : 0);
+          BND_STAT(10, lane == 0 ? __builtin_popcount(wide0) : 0);
+          while (wide) {  // ready, disjoint from their source, not yet copied: more than three or longer than 64 bytes
+            const int sl = __ffs((int)wide) - 1;
+            wide &= wide - 1;
+            BND_STAT(8, lane == 0);
+            const uint32_t len = tile.shfl(length, sl), mp = tile.shfl(mypos, sl);
+            const uint8_t *src = out + mp - tile.shfl(dist, sl);
             uint8_t *dst = out + mp;
-            if (dd >= len) {
-              for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
-            } else if (dd >= 32u) {
-              // overlapping with a period of at least one pass: a pass only reads bytes of earlier passes
-              for (uint32_t b = 0; b < len; b += 32) {
-                const uint32_t i = b + lane;
-                if (i < len) dst[i] = src[i];
-                tile.sync();
-              }
-            } else {
-              // short period: every output byte i equals src[i % dist]
-              uint32_t r = (uint32_t)lane % dd;
-              const uint32_t step = 32u % dd;
-              for (uint32_t i = lane; i < len; i += 32) {
-                dst[i] = src[r];
-                r += step;
-                if (r >= dd) r -= dd;
-              }
-            }
-            tile.sync();
+            for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
           }
-        } else {
+          pend &= ~rmask;
           tile.sync();
         }
-        outpos += total;
       }
+      outpos += total;
     }
   }
   if (status == INF_OK && outpos != isize) status = INF_SIZE_MISMATCH;

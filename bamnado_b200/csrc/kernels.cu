@@ -43,8 +43,8 @@ struct InflateVariant {
 // lane-group width / CTA size / resident CTAs per SM (and LUT widths below); selected with BND_INFLATE_VARIANT
 const InflateVariant kVariants[] = {{32, 256, 5}, {32, 128, 9}, {32, 128, 12}, {32, 256, 6}, {32, 256, 4}, {32, 128, 8},
                                     // 6..: speculative 32-lane walk (inflate_spec.cuh)
-                                    {32, 256, 3}, {32, 128, 5}, {32, 256, 2}, {32, 192, 4}};
-constexpr int kDefaultVariant = 6;  // speculative walk, 256 threads, 3 CTAs / SM (profiles/r1_sweeps.md)
+                                    {32, 256, 3}, {32, 128, 5}, {32, 256, 2}, {32, 192, 4}, {32, 224, 4}, {32, 256, 4}, {32, 320, 3}};
+constexpr int kDefaultVariant = 12;  // speculative walk, 320 threads x 3 CTAs / SM = 30 warps, 9-bit root table (profiles/r1_sweeps.md)
 int variant_index() {
   static int v = -1;
   if (v < 0) {
@@ -118,11 +118,14 @@ cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
     case 3: return launch_inflate_t<32, 256, 6, 9, 7>(a, sm_count, v.ctas_per_sm, s);
     case 4: return launch_inflate_t<32, 256, 4, 10, 8>(a, sm_count, v.ctas_per_sm, s);  // 32 warps / SM, <= 64 registers
     case 5: return launch_inflate_t<32, 128, 8, 10, 8>(a, sm_count, v.ctas_per_sm, s);
-    case 7: return launch_inflate_spec_t<128, 5, 10, 8, 256, 1024>(a, sm_count, v.ctas_per_sm, s);
-    case 8: return launch_inflate_spec_t<256, 2, 11, 8, 256, 1024>(a, sm_count, v.ctas_per_sm, s);
-    case 9: return launch_inflate_spec_t<192, 4, 10, 8, 192, 768>(a, sm_count, v.ctas_per_sm, s);
+    case 7: return launch_inflate_spec_t<128, 5, 10, 8, 256, 512>(a, sm_count, v.ctas_per_sm, s);
+    case 8: return launch_inflate_spec_t<256, 2, 11, 8, 256, 512>(a, sm_count, v.ctas_per_sm, s);
+    case 9: return launch_inflate_spec_t<192, 4, 10, 8, 192, 384>(a, sm_count, v.ctas_per_sm, s);
+    case 10: return launch_inflate_spec_t<224, 4, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // 28 warps / SM
+    case 11: return launch_inflate_spec_t<256, 4, 9, 8, 256, 256>(a, sm_count, v.ctas_per_sm, s);  // 32 warps / SM, 64 registers
+    case 6: return launch_inflate_spec_t<256, 3, 10, 8, 256, 512>(a, sm_count, v.ctas_per_sm, s);
     case 0: return launch_inflate_t<32, 256, 5, 10, 8>(a, sm_count, v.ctas_per_sm, s);  // single-lane walk (round-1 v10)
-    default: return launch_inflate_spec_t<256, 3, 10, 8, 256, 1024>(a, sm_count, v.ctas_per_sm, s);
+    default: return launch_inflate_spec_t<320, 3, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM, 64 registers
   }
 }
 

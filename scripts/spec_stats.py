@@ -39,10 +39,7 @@ f = nat.L.bnd_dbg_counter
 f.restype = ctypes.c_ulonglong
 c = [f(i) for i in range(16)]
 print(f"blocks {len(st)}  inflated {len(out)} B  compressed {len(data)} B")
-print(f"rounds {c[0]}  tokens {c[4]}  tokens/round {c[4] / max(c[0], 1):.1f}  bits/token {8 * len(data) / max(c[4], 1):.2f}")
+print(f"rounds {c[0]}  matches/round {c[4] / max(c[0], 1):.1f}")
 print(f"fix-up iterations/round {c[1] / max(c[0], 1):.2f}  lanes re-decoded/round {c[2] / max(c[0], 1):.2f}  dropped lanes/round {c[3] / max(c[0], 1):.2f}")
-print(f"matches {c[5]}  mean length {c[6] / max(c[5], 1):.1f}  share of tokens {c[5] / max(c[4], 1):.3f}")
-cum = 0
-for b in range(8, 16):
-    cum += c[b]
-    print(f"  distance <= {1 << b:5d}: {cum / max(c[5], 1):.3f}")
+print(f"matches {c[4]}  batches of 32: {c[6]}  waves/batch {c[5] / max(c[6], 1):.2f}  self-overlapping firsts/batch {c[7] / max(c[6], 1):.2f}")
+print(f"ready matches/wave {c[9] / max(c[5] - c[7], 1):.1f}  of them longer than 16 B: {c[10] / max(c[9], 1):.3f}  left to the one-by-one loop/batch {c[8] / max(c[6], 1):.2f}")
