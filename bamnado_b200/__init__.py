@@ -66,3 +66,61 @@ def get_signal_for_chromosome(bam_path: str, chromosome_name: str, bin_size: int
     pile = dict(bam_path=bam_path, bin_size=bin_size, norm="raw", scale_factor=scale_factor, use_fragment=use_fragment,
                 collapse=True, ignore_scaffold=ignore_scaffold_chromosomes)
     return _native.lib().signal_for_chromosome(pile, filt, chromosome_name)
+
+
+class BinCounts:
+    """Sample x bin read-count matrix (`BinCounts`, bamnado/src/bin_counts.rs:36-48).
+
+    `counts` has shape (n_bins, n_samples), dtype uint64; `bins` yields (chrom, start, end) with 1-based inclusive
+    coordinates in row order; `library_sizes` are the post-filter library sizes per sample.
+    """
+
+    def __init__(self, sample_names, bin_size, raw):
+        self.sample_names = list(sample_names)
+        self.bin_size = int(bin_size)
+        self.counts = raw["counts"]
+        self.library_sizes = raw["library_sizes"]
+        self.chroms = raw["chroms"]
+        self.chrom_len = raw["chrom_len"]
+        self.chrom_first_row = raw["chrom_first_row"]
+
+    @property
+    def n_bins(self) -> int:
+        return int(self.counts.shape[0])
+
+    def bin_arrays(self):
+        """(chrom index per row, start, end) as numpy arrays."""
+        rows = np.diff(self.chrom_first_row).astype(np.int64)
+        chrom_idx = np.repeat(np.arange(len(self.chroms)), rows)
+        i = np.arange(self.n_bins, dtype=np.uint64) - np.repeat(self.chrom_first_row[:-1], rows)
+        start = 1 + i * np.uint64(self.bin_size)
+        end = np.minimum(start + np.uint64(self.bin_size - 1), np.repeat(self.chrom_len, rows))
+        return chrom_idx, start, end
+
+    @property
+    def bins(self):
+        chrom_idx, start, end = self.bin_arrays()
+        for c, s, e in zip(chrom_idx, start, end):
+            yield self.chroms[int(c)], int(s), int(e)
+
+
+def count_bins(bam_paths, sample_names, bin_size: int, filters=None, use_fragment: bool = False,
+               ignore_scaffold_chromosomes: bool = False) -> BinCounts:
+    """Bin-count reads (or fragments) of several BAMs on one shared grid (`count_bins`, bamnado/src/bin_counts.rs:100-289).
+
+    Same argument checks as the reference: at least one BAM, as many sample names and filters as BAMs, identical
+    chromosome name -> length maps (RuntimeError otherwise).
+    """
+    bam_paths = [str(p) for p in bam_paths]
+    if not bam_paths:
+        raise RuntimeError("At least one BAM file is required for bin counting")
+    if len(bam_paths) != len(sample_names):
+        raise RuntimeError(f"Number of BAM paths ({len(bam_paths)}) does not match number of sample names ({len(sample_names)})")
+    if filters is None:
+        filters = [None] * len(bam_paths)
+    if len(bam_paths) != len(filters):
+        raise RuntimeError(f"Number of BAM paths ({len(bam_paths)}) does not match number of filters ({len(filters)})")
+    piles = [dict(bam_path=p, bin_size=bin_size, norm="raw", use_fragment=use_fragment, collapse=False,
+                  ignore_scaffold=ignore_scaffold_chromosomes) for p in bam_paths]
+    filts = [dict(_DEFAULT_FILTER) if f is None else (f._cfg() if isinstance(f, ReadFilter) else dict(f)) for f in filters]
+    return BinCounts(sample_names, bin_size, _native.lib().bin_counts(piles, filts))

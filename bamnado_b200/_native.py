@@ -29,7 +29,7 @@ EXPORTS = [
     "bnd_pileup_destroy", "bnd_pileup_to_bedgraph", "bnd_pileup_to_bigwig", "bnd_pileup_chromosome", "bnd_pileup_runs",
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
-    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_multi_prepare",
+    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
     "bnd_multi_change_flags", "bnd_multi_compact", "bnd_pileup_refs", "bnd_collapse_bedgraph",
     "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
 ]
@@ -223,6 +223,32 @@ class Native:
         ps = (PileupCfg * n)(*[make_pileup_cfg(**p) for p in pileups])
         fs = (FilterCfg * n)(*[make_filter_cfg(**f) for f in filters])
         self.check(self.L.bnd_multi_to_tsv(ps, fs, n, _b(out_path)))
+
+    def bin_counts(self, pileups: list, filters: list):
+        """bin_counts::count_bins: dict(counts (n_bins, n_samples) u64, chroms, chrom_len, chrom_first_row, library_sizes)."""
+        n = len(pileups)
+        if n != len(filters):
+            raise ValueError(f"Number of BAM paths ({n}) does not match number of filters ({len(filters)})")
+        ps = (PileupCfg * max(n, 1))(*[make_pileup_cfg(**p) for p in pileups])
+        fs = (FilterCfg * max(n, 1))(*[make_filter_cfg(**f) for f in filters])
+        counts, names = C.POINTER(C.c_uint64)(), C.c_char_p()
+        clen, crow = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
+        n_bins, n_chroms = C.c_uint64(), C.c_uint64()
+        lib = (C.c_uint64 * max(n, 1))()
+        names_p = C.c_void_p()
+        self.check(self.L.bnd_bin_counts(ps, fs, n, C.byref(counts), C.byref(n_bins), C.byref(names_p), C.byref(clen), C.byref(crow),
+                                         C.byref(n_chroms), lib))
+        nb, nc = n_bins.value, n_chroms.value
+        out = dict(
+            counts=np.ctypeslib.as_array(counts, shape=(nb * n,)).reshape(nb, n).copy() if nb else np.zeros((0, n), np.uint64),
+            chroms=C.string_at(names_p).decode().split("\n") if nc else [],
+            chrom_len=np.ctypeslib.as_array(clen, shape=(nc,)).copy() if nc else np.zeros(0, np.uint64),
+            chrom_first_row=np.ctypeslib.as_array(crow, shape=(nc + 1,)).copy(),
+            library_sizes=[int(lib[i]) for i in range(n)],
+        )
+        for ptr in (counts, names_p, clen, crow):
+            self.L.bnd_free(C.cast(ptr, C.c_void_p))
+        return out
 
     def collapse_bedgraph(self, in_path, out_path):
         self.check(self.L.bnd_collapse_bedgraph(_b(in_path), _b(out_path)))

@@ -165,7 +165,7 @@ int Geometry::ref_of_chunk(uint64_t c) const {
   return (int)lo;
 }
 
-Geometry make_geometry(const BamHeader &h, const Bai &bai, uint64_t bin) {
+Geometry make_geometry(const BamHeader &h, const Bai &bai, uint64_t bin, bool drop_scaffold_refs) {
   if (bin == 0) fail("bin size must be greater than 0", ERR_INVALID);
   Geometry g;
   const size_t n_ref = h.names.size();
@@ -200,7 +200,7 @@ Geometry make_geometry(const BamHeader &h, const Bai &bai, uint64_t bin) {
   g.ref_first_chunk.assign(n_ref + 1, 0);
   for (size_t r = 0; r < n_ref; r++) {
     uint64_t bins = 0, chunks = 0;
-    if (g.in_stats[r] && h.lens[r] > 0) {
+    if (g.in_stats[r] && h.lens[r] > 0 && !(drop_scaffold_refs && is_scaffold(h.names[r]))) {
       const uint64_t len = h.lens[r];
       chunks = (len + g.L - 1) / g.L;
       const uint64_t cs_last = (chunks - 1) * g.L + 1;  // last chunk [cs_last, len]: bins tile [cs_last, len)

@@ -72,7 +72,9 @@ struct Geometry {
   uint64_t first_bin_of_chunk(uint64_t c) const;
   int ref_of_chunk(uint64_t c) const;
 };
-Geometry make_geometry(const BamHeader &h, const Bai &bai, uint64_t bin_size);
+// drop_scaffold_refs: scaffold contigs get no chunks at all, so their reads are neither counted nor visited
+// (bin_counts.rs:190-200 filters the chunk list; BamPileup only drops their rows at output time)
+Geometry make_geometry(const BamHeader &h, const Bai &bai, uint64_t bin_size, bool drop_scaffold_refs = false);
 
 // is_scaffold (bam_utils.rs:38-43): ^chrUn | _alt$ | _random$
 bool is_scaffold(const std::string &name);

@@ -160,6 +160,32 @@ int bnd_multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, 
   return guarded([&] { bnd::multi_to_tsv(cfgs, filters, n_bams, out_path); });
 }
 
+int bnd_bin_counts(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int32_t n_samples, uint64_t **counts, uint64_t *n_bins,
+                   char **chrom_names, uint64_t **chrom_len, uint64_t **chrom_first_row, uint64_t *n_chroms, uint64_t *library_sizes) {
+  return guarded([&] {
+    bnd::Pileup::BinCounts bc;
+    bnd::Pileup::count_bins(cfgs, filters, n_samples, bc);
+    std::string names;
+    for (size_t i = 0; i < bc.chroms.size(); i++) {
+      if (i) names.push_back('\n');
+      names += bc.chroms[i];
+    }
+    auto dup = [](const void *src, size_t bytes) {
+      void *m = malloc(bytes ? bytes : 1);
+      if (!m) bnd::fail("out of host memory");
+      if (bytes) memcpy(m, src, bytes);
+      return m;
+    };
+    *counts = (uint64_t *)dup(bc.counts.data(), bc.counts.size() * 8);
+    *n_bins = bc.n_bins;
+    *chrom_names = (char *)dup(names.c_str(), names.size() + 1);
+    *chrom_len = (uint64_t *)dup(bc.chrom_len.data(), bc.chrom_len.size() * 8);
+    *chrom_first_row = (uint64_t *)dup(bc.chrom_first_row.data(), bc.chrom_first_row.size() * 8);
+    *n_chroms = bc.chroms.size();
+    for (size_t i = 0; i < bc.library_sizes.size(); i++) library_sizes[i] = bc.library_sizes[i];
+  });
+}
+
 int bnd_multi_prepare(bnd_pileup *p, uint64_t *n_bins) {
   return guarded([&] { *n_bins = P(p)->multi_prepare(); });
 }

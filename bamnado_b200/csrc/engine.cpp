@@ -419,7 +419,7 @@ void device_inflate(const uint8_t *bgzf, uint64_t n_bytes, std::vector<uint8_t> 
 }
 
 // ---- construction ---------------------------------------------------------------------------------------------------
-Pileup::Pileup(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter) : im_(new Impl()) {
+Pileup::Pileup(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter, bool drop_scaffold_chunks) : im_(new Impl()) {
   if (!cfg || !cfg->bam_path) fail("missing BAM path", ERR_INVALID);
   cfg_ = *cfg;
   bam_path_ = cfg->bam_path;
@@ -435,7 +435,7 @@ Pileup::Pileup(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter) : im_(ne
   dflt.max_length = 0xffffffffu;
   dflt.barcode_csv_column = -1;
   filt_ = make_filter_host(filter ? filter : &dflt, hdr_);
-  geo_ = make_geometry(hdr_, bai_, cfg_.bin_size);
+  geo_ = make_geometry(hdr_, bai_, cfg_.bin_size, drop_scaffold_chunks);
   if (env_u64("BND_DEBUG_TIMING", 0))
     fprintf(stderr, "[bnd] create: device context %.2f ms, open (index, header, cut points) %.2f ms, filter + geometry %.2f ms\n", t_c1 - t_c0, t_c2 - t_c1,
             now_ms() - t_c2);
@@ -1277,6 +1277,109 @@ void Pileup::multi_collapse(std::vector<Pileup *> &bams, std::vector<RunRow> &ro
   release();
 }
 
+// bin_counts::count_bins (bamnado/src/bin_counts.rs:100-289).  Every sample runs the ordinary pile-up without collapsing
+// (`bin_intervals(.., false)`, :240) and without shift/truncate (`IntervalMaker::new(.., None, None)`, :219-227); its dense
+// counts are scattered on the device into column `s` of one matrix whose rows follow the shared grid: chromosomes sorted
+// by name (:150-154), bins [1 + i * bin, min((i + 1) * bin, len)] (:158-170).  The samples are processed one after the other
+// like the reference's outer loop (:178); the matrix stays in HBM until the last one is done.
+void Pileup::count_bins(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int n_samples, BinCounts &out) {
+  if (n_samples < 1 || !cfgs) fail("At least one BAM file is required for bin counting", ERR_INVALID);
+  const uint64_t bin = cfgs[0].bin_size;
+  const bool drop_scaffold = cfgs[0].ignore_scaffold != 0;
+  const bool use_fragment = cfgs[0].use_fragment != 0;
+  out = BinCounts();
+  out.bin_size = bin;
+  out.library_sizes.assign((size_t)n_samples, 0);
+  std::map<std::string, uint64_t> grid_sizes;  // chromsizes_ref_name() of the first sample
+  std::map<std::string, uint64_t> row0_of;
+  DevBuf d_matrix, d_row0;
+  DeviceCtx *ctx0 = nullptr;
+  auto release = [&] {
+    d_matrix.release();
+    d_row0.release();
+  };
+  try {
+    for (int s = 0; s < n_samples; s++) {
+      bnd_pileup_cfg c = cfgs[s];
+      if (c.bin_size != bin) fail("all samples must use the same bin size", ERR_INVALID);
+      c.collapse = 0;
+      c.norm_method = 0;  // raw counts
+      c.scale_factor = 1.0f;
+      c.use_fragment = use_fragment;
+      c.ignore_scaffold = 0;  // handled by the chunk list, not at output time
+      c.has_shift = c.has_truncate = 0;
+      c.shard_rank = 0;
+      c.shard_world = 1;
+      c.device = cfgs[0].device;
+      Pileup p(&c, filters ? &filters[s] : nullptr, drop_scaffold);
+      std::map<std::string, uint64_t> sizes;
+      for (size_t r = 0; r < p.hdr_.names.size(); r++)
+        if (p.geo_.in_stats[r]) sizes[p.hdr_.names[r]] = p.hdr_.lens[r];
+      if (s == 0) {
+        grid_sizes = sizes;
+        ctx0 = p.im_->ctx;
+        uint64_t rows = 0;
+        for (auto &kv : grid_sizes) {  // std::map iterates in byte-string order = the sorted chromosome names
+          if (drop_scaffold && is_scaffold(kv.first)) continue;
+          out.chroms.push_back(kv.first);
+          out.chrom_len.push_back(kv.second);
+          out.chrom_first_row.push_back(rows);
+          row0_of[kv.first] = rows;
+          rows += (kv.second + bin - 1) / bin;  // `while start <= length` (:161)
+        }
+        out.chrom_first_row.push_back(rows);
+        out.n_bins = rows;
+        if (rows == 0) fail("No bins produced; check --bin-size and --ignore-scaffolds");
+        std::lock_guard<std::mutex> lock(ctx0->mu);
+        CU(cudaSetDevice(ctx0->device));
+        d_matrix.ensure((size_t)rows * (size_t)n_samples * 8 + 16);
+        CU(cudaMemset(d_matrix.p, 0, (size_t)rows * (size_t)n_samples * 8));
+      } else if (sizes != grid_sizes) {
+        fail("Chromosome name/length mismatch between BAM files: " + p.bam_path_ + " does not match " + std::string(cfgs[0].bam_path) +
+             ". bam-normalize requires all input BAM files to share an identical set of reference sequences so that a common bin grid can be used.");
+      }
+      p.multi_prepare();  // pile-up + dense raw counts on the device
+      uint64_t st[ST_N_COUNTERS];
+      p.stats(st);
+      uint64_t failed = 0;
+      for (int k = 1; k < ST_N_COUNTERS; k++) failed += st[k];
+      out.library_sizes[(size_t)s] = st[ST_N_TOTAL] - failed;  // n_reads_after_filtering (read_filter.rs:229-243)
+      std::vector<uint64_t> row0(p.hdr_.names.size(), ~0ull);
+      for (size_t r = 0; r < row0.size(); r++) {
+        auto it = row0_of.find(p.hdr_.names[r]);
+        if (it != row0_of.end() && p.geo_.in_stats[r]) row0[r] = it->second;
+      }
+      Impl &im = *p.im_;
+      DeviceCtx &ctx = *im.ctx;
+      std::lock_guard<std::mutex> lock(ctx.mu);
+      CU(cudaSetDevice(ctx.device));
+      cudaStream_t strm = ctx.sets[0].stream;
+      d_row0.ensure(row0.size() * 8 + 16);
+      CU(cudaMemcpyAsync(d_row0.p, row0.data(), row0.size() * 8, cudaMemcpyHostToDevice, strm));
+      BinMatrixArgs a{};
+      a.counts = im.d_counts.as<uint32_t>();
+      a.g = im.gdev;
+      a.grid_row0 = d_row0.as<uint64_t>();
+      a.matrix = d_matrix.as<unsigned long long>();
+      a.bins_per_chunk_grid = p.geo_.L / bin;
+      a.n_samples = (uint32_t)n_samples;
+      a.sample = (uint32_t)s;
+      CU(launch_bin_matrix(a, ctx.sm_count, strm));
+      CU(cudaStreamSynchronize(strm));
+    }
+    out.counts.resize((size_t)out.n_bins * (size_t)n_samples);
+    {
+      std::lock_guard<std::mutex> lock(ctx0->mu);
+      CU(cudaSetDevice(ctx0->device));
+      CU(cudaMemcpy(out.counts.data(), d_matrix.p, out.counts.size() * 8, cudaMemcpyDeviceToHost));
+    }
+  } catch (...) {
+    release();
+    throw;
+  }
+  release();
+}
+
 uint64_t Pileup::multi_prepare() {
   if (cfg_.collapse) fail("All BAM pileups must have collapse set to false", ERR_INVALID);
   run_pass(shard_, false);
@@ -1788,7 +1891,10 @@ void Pileup::to_bedgraph(const std::string &path) {
     close(fd);
     throw;
   }
-  if (map) munmap(map, out_bytes);
+  const double t2a = now_ms();
+  // The file's pages are complete; tearing down 2 GB of page-table entries (26 ms) only concerns this process's address
+  // space, so it is left to a detached thread and the file is truncated to size and closed right away.
+  if (map) std::thread([map, out_bytes] { munmap(map, out_bytes); }).detach();
   const double t2 = now_ms();
   if (ftruncate(fd, (off_t)out_bytes) != 0) {
     close(fd);
@@ -1797,8 +1903,8 @@ void Pileup::to_bedgraph(const std::string &path) {
   if (close(fd) != 0) fail("write error on " + path);
   tm_.text_ms = now_ms() - t0;
   if (env_u64("BND_DEBUG_TIMING", 0))
-    fprintf(stderr, "[bnd] to_bedgraph: pile-up %.2f ms (prealloc %llu MB), format %.2f ms, drain %.2f ms, truncate+close %.2f ms, %llu bytes\n", t0 - t00,
-            (unsigned long long)(prealloc >> 20), t1 - t0, t2 - t1, now_ms() - t2, (unsigned long long)job.nbytes);
+    fprintf(stderr, "[bnd] to_bedgraph: pile-up %.2f ms (prealloc %llu MB), format %.2f ms, drain %.2f ms (munmap %.2f ms), truncate+close %.2f ms, %llu bytes\n", t0 - t00,
+            (unsigned long long)(prealloc >> 20), t1 - t0, t2 - t1, t2 - t2a, now_ms() - t2, (unsigned long long)job.nbytes);
 }
 
 }  // namespace bnd

@@ -28,7 +28,8 @@ struct Shape {
 
 class Pileup {
  public:
-  Pileup(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter);
+  // drop_scaffold_chunks: scaffold contigs are left out of the chunk list itself (bin_counts.rs:190-200)
+  Pileup(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter, bool drop_scaffold_chunks = false);
   ~Pileup();
   Pileup(const Pileup &) = delete;
 
@@ -61,6 +62,16 @@ class Pileup {
   // one BAM per rank: raw dense counts stay on the device, the ranks OR their per-bin change flags together
   // (NCCL all-reduce MAX over device memory owned by the caller), then every rank compacts its own column
   uint64_t multi_prepare();
+  // bin_counts::count_bins (bin_counts.rs:100-289): samples x bins matrix of raw counts on the grid shared by all BAMs
+  struct BinCounts {
+    uint64_t bin_size = 0, n_bins = 0;
+    std::vector<std::string> chroms;        // grid chromosomes, sorted by name
+    std::vector<uint64_t> chrom_len;        // their lengths
+    std::vector<uint64_t> chrom_first_row;  // [chroms + 1] first matrix row of each chromosome
+    std::vector<uint64_t> counts;           // [n_bins][n_samples]
+    std::vector<uint64_t> library_sizes;    // reads kept by each sample's filter (per read and chunk, like the pile-up)
+  };
+  static void count_bins(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int n_samples, BinCounts &out);
   void multi_change_flags(uint8_t *dev_flags);
   void multi_compact(const uint8_t *dev_flags, std::vector<RunRow> &rows, std::vector<uint32_t> &vals);
 

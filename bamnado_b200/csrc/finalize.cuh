@@ -331,4 +331,27 @@ __global__ void __launch_bounds__(TEXT_THREADS) text_write_kernel(TextArgs a) {
   }
 }
 
+// One thread per bin of the pile-up's own layout (per reference: chunk-major, `nbf` bins per full chunk).  The bin that
+// starts at base `start` lands in grid row (start - 1) / bin of its chromosome (bin_counts.rs:258-260); bins the chunks do
+// not produce (the single-base bin after a chunk's last base) keep the matrix's zero.
+__global__ void bin_matrix_kernel(BinMatrixArgs a) {
+  const uint64_t n = a.g.bin_hi - a.g.bin_lo;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t gb = a.g.bin_lo + t;
+    int lo = 0, hi = a.g.n_ref;  // last reference whose first bin is <= gb
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (a.g.ref_first_bin[mid] <= gb)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    const uint64_t row0 = a.grid_row0[lo];
+    if (row0 == ~0ull || a.g.nbf == 0) continue;
+    const uint64_t j = gb - a.g.ref_first_bin[lo];
+    const uint64_t row = row0 + (j / a.g.nbf) * a.bins_per_chunk_grid + (j % a.g.nbf);
+    a.matrix[row * a.n_samples + a.sample] = a.counts[t];
+  }
+}
+
 }  // namespace bnd

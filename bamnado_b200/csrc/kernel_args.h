@@ -249,4 +249,15 @@ struct MultiArgs {
   uint8_t *flags_out;    // multi_flags_kernel output
 };
 
+// bin_counts::count_bins (bin_counts.rs:254-262): one sample's dense per-bin counts scattered into its column of the
+// shared (n_bins x n_samples) matrix; rows follow the grid of chromosomes sorted by name
+struct BinMatrixArgs {
+  const uint32_t *counts;         // dense counts of bins [g.bin_lo, g.bin_hi)
+  GeomDev g;
+  const uint64_t *grid_row0;      // [n_ref] first matrix row of each reference, ~0 = not on the grid
+  unsigned long long *matrix;     // [n_rows][n_samples]
+  uint64_t bins_per_chunk_grid;   // L / bin: grid bins spanned by one genomic chunk
+  uint32_t n_samples, sample;
+};
+
 }  // namespace bnd

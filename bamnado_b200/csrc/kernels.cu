@@ -43,7 +43,7 @@ struct InflateVariant {
 // lane-group width / CTA size / resident CTAs per SM (and LUT widths below); selected with BND_INFLATE_VARIANT
 const InflateVariant kVariants[] = {{32, 256, 5}, {32, 128, 9}, {32, 128, 12}, {32, 256, 6}, {32, 256, 4}, {32, 128, 8},
                                     // 6..: speculative 32-lane walk (inflate_spec.cuh)
-                                    {32, 256, 3}, {32, 128, 5}, {32, 256, 2}, {32, 192, 4}, {32, 224, 4}, {32, 256, 4}, {32, 320, 3}};
+                                    {32, 256, 3}, {32, 128, 5}, {32, 256, 2}, {32, 192, 4}, {32, 224, 4}, {32, 256, 4}, {32, 320, 3}, {32, 192, 5}, {32, 160, 6}};
 constexpr int kDefaultVariant = 12;  // speculative walk, 320 threads x 3 CTAs / SM = 30 warps, 9-bit root table (profiles/r1_sweeps.md)
 int variant_index() {
   static int v = -1;
@@ -124,6 +124,8 @@ cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
     case 10: return launch_inflate_spec_t<224, 4, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // 28 warps / SM
     case 11: return launch_inflate_spec_t<256, 4, 9, 8, 256, 256>(a, sm_count, v.ctas_per_sm, s);  // 32 warps / SM, 64 registers
     case 6: return launch_inflate_spec_t<256, 3, 10, 8, 256, 512>(a, sm_count, v.ctas_per_sm, s);
+    case 13: return launch_inflate_spec_t<192, 5, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // smaller CTAs leave the SM sooner in a launch's tail
+    case 14: return launch_inflate_spec_t<160, 6, 9, 8, 256, 320>(a, sm_count, v.ctas_per_sm, s);
     case 0: return launch_inflate_t<32, 256, 5, 10, 8>(a, sm_count, v.ctas_per_sm, s);  // single-lane walk (round-1 v10)
     default: return launch_inflate_spec_t<320, 3, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM, 64 registers
   }
@@ -216,6 +218,12 @@ cudaError_t launch_bdg_emit(const BdgArgs &a, int sm_count, cudaStream_t s) {
 cudaError_t launch_u64_scan(uint64_t *v, uint32_t n, unsigned long long *total_out, cudaStream_t s) {
   auto k = u64_scan_kernel<1024>;
   BND_LAUNCH(k, dim3(1), dim3(1024), 0, s, v, n, total_out);
+  return launched();
+}
+cudaError_t launch_bin_matrix(const BinMatrixArgs &a, int sm_count, cudaStream_t s) {
+  const uint64_t n = a.g.bin_hi - a.g.bin_lo;
+  if (n == 0) return cudaSuccess;
+  BND_LAUNCH(bin_matrix_kernel, dim3(grid_for(n, COL_THREADS, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
   return launched();
 }
 cudaError_t launch_multi_flags(const MultiArgs &a, int sm_count, cudaStream_t s) {

@@ -34,6 +34,7 @@ cudaError_t launch_bdg_count(const BdgArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_bdg_emit(const BdgArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_u64_scan(uint64_t *v, uint32_t n, unsigned long long *total_out, cudaStream_t s);
 cudaError_t launch_multi_flags(const MultiArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bin_matrix(const BinMatrixArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_count(const MultiArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_emit(const MultiArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_rows(const RunArgs &a, int sm_count, cudaStream_t s);

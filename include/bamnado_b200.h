@@ -135,6 +135,22 @@ int bnd_signal_for_chromosome(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *f
 /* ---- MultiBamPileup::to_tsv (coverage_analysis.rs:766-865) ------------------------------------------------ */
 int bnd_multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int32_t n_bams, const char *out_path);
 
+/* ---- bin_counts::count_bins (bamnado/src/bin_counts.rs:100-289; front half of `bam-normalize`, src/cli.rs:1455, and of
+ * compute_scale_factors, bamnado-python/src/lib.rs:505) -------------------------------------------------------------------
+ * Raw read (or fragment) counts of n_samples BAMs on one shared grid of bins.  bin_size, use_fragment and ignore_scaffold
+ * are taken from cfgs[0] (the reference passes one value for all samples); normalisation, collapse, shift and truncate
+ * fields are ignored (the reference counts raw, uncollapsed, unshifted).  Every BAM must have the same contig names and
+ * lengths (else BND_ERR_RUNTIME with the reference's message).  Outputs (library-allocated, release with bnd_free):
+ *   counts            [n_bins][n_samples] row-major, BinCounts::counts
+ *   chrom_names       grid chromosomes in row order (sorted by name), '\n'-separated, NUL-terminated
+ *   chrom_len         [n_chroms] contig lengths
+ *   chrom_first_row   [n_chroms + 1] first matrix row of each chromosome; bin i of a chromosome covers the 1-based inclusive
+ *                     interval [1 + i * bin_size, min((i + 1) * bin_size, len)] (BinRegion, bin_counts.rs:27-34)
+ *   library_sizes     caller-provided array of n_samples: BinCounts::library_sizes (reads kept by each sample's filter) */
+int bnd_bin_counts(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int32_t n_samples, uint64_t **counts,
+                   uint64_t *n_bins, char **chrom_names, uint64_t **chrom_len, uint64_t **chrom_first_row, uint64_t *n_chroms,
+                   uint64_t *library_sizes);
+
 /* ---- MultiBamPileup with one BAM per GPU: the pileups run independently, the ranks OR their per-bin change
  * flags together with one all-reduce(MAX) over NVLink on memory the caller owns (e.g. a torch CUDA tensor), and every rank
  * compacts its own column at the shared run heads.  `dev_flags` are DEVICE pointers to n_bins bytes. ------------------------ */

@@ -259,3 +259,63 @@ def count_records(bam_path):
     a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
     _check(lib().orc_count_records(_b(bam_path), C.byref(a), C.byref(b), C.byref(c)))
     return {"n_records": a.value, "inflated_bytes": b.value, "n_blocks": c.value}
+
+
+def bam_header_refs(bam_path):
+    """(names, lengths) of the @SQ dictionary in the binary BAM header (SAM spec 4.2), read through Python's gzip."""
+    import gzip
+    import struct
+
+    with gzip.open(bam_path, "rb") as f:
+        if f.read(4) != b"BAM\1":
+            raise OracleError(1, "not a BAM file")
+        (l_text,) = struct.unpack("<i", f.read(4))
+        f.read(l_text)
+        (n_ref,) = struct.unpack("<i", f.read(4))
+        names, lens = [], []
+        for _ in range(n_ref):
+            (l_name,) = struct.unpack("<i", f.read(4))
+            names.append(f.read(l_name)[:-1].decode())
+            lens.append(struct.unpack("<i", f.read(4))[0])
+    return names, lens
+
+
+def count_bins(bam_paths, bin_size, filters, use_fragment=False, ignore_scaffold=False):
+    """Restatement of bin_counts::count_bins (bamnado/src/bin_counts.rs:100-289) on top of the oracle's pile-up.
+
+    Grid (:146-170): chromosomes of the first BAM's stats sorted by name (scaffolds dropped on request), bins
+    [start, min(start + bin - 1, len)] while start <= len.  Per sample (:178-262): the chunk list without scaffold
+    chunks, `bin_intervals(.., collapse=false)` per chunk, every interval's count written to row
+    offset[chrom] + (start - 1) // bin.  library size = n_reads_after_filtering of that sample's filter (:264).
+    Returns (counts[n_bins, n_samples] u64, [(chrom, len, first_row)], library_sizes).
+    """
+    import re
+
+    scaffold = re.compile(r"^chrUn|_alt$|_random$")  # bam_utils.rs:38-43
+    sizes0 = dict(zip(*bam_header_refs(bam_paths[0])))
+    names = sorted(n for n in sizes0 if not (ignore_scaffold and scaffold.search(n)))
+    grid, rows = [], 0
+    for n in names:
+        grid.append((n, sizes0[n], rows))
+        rows += -(-sizes0[n] // bin_size)
+    if rows == 0:
+        raise OracleError(1, "No bins produced; check --bin-size and --ignore-scaffolds")
+    offset = {n: r for n, _, r in grid}
+    counts = np.zeros((rows, len(bam_paths)), dtype=np.uint64)
+    libs = []
+    for s, (bam, filt) in enumerate(zip(bam_paths, filters)):
+        ref_names, ref_lens = bam_header_refs(bam)
+        if dict(zip(ref_names, ref_lens)) != sizes0:
+            raise OracleError(1, "Chromosome name/length mismatch between BAM files")
+        keep = [n for n in ref_names if not (ignore_scaffold and scaffold.search(n))]
+        lib = 0
+        # the reference's chunk list minus the scaffold chunks == the pile-up restricted to the kept chromosomes; the
+        # filter counters only see reads of visited chunks, so they are summed over those chromosomes
+        for chrom in keep:
+            runs, sd = pileup_chromosome(dict(bam_path=bam, bin_size=bin_size, norm="raw", use_fragment=use_fragment, collapse=False), filt, chrom)
+            lib += sd["n_total"] - sum(v for k, v in sd.items() if k != "n_total")
+            if len(runs):
+                idx = offset[chrom] + (runs["start"].astype(np.int64) - 1) // bin_size
+                counts[idx, s] = runs["val"]
+        libs.append(int(lib))
+    return counts, grid, libs
