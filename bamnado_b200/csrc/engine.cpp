@@ -31,6 +31,17 @@ namespace {
     if (e_ != cudaSuccess) fail(std::string("CUDA error: ") + cudaGetErrorString(e_) + " in " #call);     \
   } while (0)
 
+// Host cores this process should plan for: the machine's cores divided by the processes sharing the node (one per GPU
+// under torchrun, which exports LOCAL_WORLD_SIZE); BND_HOST_SHARE overrides the divisor.
+static unsigned host_cores_share() {
+  const unsigned hw = std::max(4u, std::thread::hardware_concurrency());
+  uint64_t share = 1;
+  if (const char *e = getenv("BND_HOST_SHARE")) share = strtoull(e, nullptr, 10);
+  else if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = strtoull(e, nullptr, 10);
+  if (share < 1) share = 1;
+  return std::max(2u, (unsigned)(hw / share));
+}
+
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -197,7 +208,7 @@ DeviceCtx &ctx_for(int device) {
   c->seg_bytes = env_u64("BND_SEGMENT_BYTES", 96ull << 20);
   c->carry_cap = env_u64("BND_CARRY_BYTES", 8ull << 20);
   c->carry_cap = (c->carry_cap + REC_TILE - 1) / REC_TILE * REC_TILE;
-  c->n_readers = (int)env_u64("BND_READERS", 8);
+  c->n_readers = (int)env_u64("BND_READERS", std::min(8u, std::max(2u, host_cores_share() / 2)));
   c->n_sets = (int)std::min<uint64_t>(MAX_SETS, std::max<uint64_t>(2, env_u64("BND_SETS", 6)));
   int n_slots = (int)env_u64("BND_STAGES", 4);
   if (n_slots < 2) n_slots = 2;
@@ -1872,8 +1883,8 @@ void Pileup::to_bedgraph(const std::string &path) {
     }
     // the writers spend most of their time in page faults, so more of them than cores pays: 8 -> 24 threads on the
     // 16-core B200 hosts takes the drain of 2.1 GB from 155 to 125 ms (profiles/r1_sweeps.md)
-    const unsigned hw = std::max(4u, std::thread::hardware_concurrency());
-    const int writers = (int)env_u64("BND_WRITERS", std::min(32u, hw + hw / 2));
+    const unsigned hw = host_cores_share();
+    const int writers = (int)env_u64("BND_WRITERS", std::min(32u, std::max(4u, hw + hw / 2)));
     if (map)
       drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, writers,
                  [map](const uint8_t *src, uint64_t len, uint64_t off) { memcpy(map + off, src, len); });
