@@ -225,6 +225,69 @@ __device__ uint32_t tile_crc32(const Tile<G> &tile, const uint8_t *out, uint32_t
   return ~c;
 }
 
+// The same CRC-32 computed while the block is being produced: `advance` folds every complete group of 32 words that has
+// become final since the last call (still in L1/L2: the block-end pass of tile_crc32 re-read the whole output from DRAM,
+// profiles/r1_inflate_v15_spec_shipped.txt), `finish` adds the last words and bytes.  Lane l keeps the register for words
+// l, l + 32, ...; the registers are only combined in `finish`.
+struct CrcStream {
+  uint32_t c = 0xffffffffu;  // serial register: leading bytes up to 4-byte alignment
+  uint32_t acc = 0;          // this lane's interleaved register
+  uint32_t words = 0;        // aligned words folded so far (multiple of 32)
+  uint32_t lead = 0;
+  bool started = false;
+  __device__ __forceinline__ void advance(int lane, const uint8_t *out, uint32_t upto, const CrcTables *T) {
+    if (!started) {
+      lead = (uint32_t)((4 - ((uintptr_t)out & 3)) & 3);
+      if (upto < lead) return;
+      for (uint32_t i = 0; i < lead; i++) c = T->t[(c ^ out[i]) & 0xff] ^ (c >> 8);
+      started = true;
+    }
+    const uint32_t *w = (const uint32_t *)(out + lead);
+    const uint32_t avail = (upto - lead) >> 2;
+    while (words + 128 <= avail) {  // four loads in flight ahead of the table chain
+      uint32_t v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = w[words + 32 * k + lane];
+      if (words == 0 && lane == 0) v[0] ^= c;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        acc = T->z[0][acc & 0xff] ^ T->z[1][(acc >> 8) & 0xff] ^ T->z[2][(acc >> 16) & 0xff] ^ T->z[3][acc >> 24] ^ v[k];
+      words += 128;
+    }
+    while (words + 32 <= avail) {
+      uint32_t v = w[words + lane];
+      if (words == 0 && lane == 0) v ^= c;
+      acc = T->z[0][acc & 0xff] ^ T->z[1][(acc >> 8) & 0xff] ^ T->z[2][(acc >> 16) & 0xff] ^ T->z[3][acc >> 24] ^ v;
+      words += 32;
+    }
+  }
+  // all n bytes of the block are final; every lane returns the CRC
+  __device__ __forceinline__ uint32_t finish(const Tile<32> &tile, const uint8_t *out, uint32_t n, const CrcTables *T) {
+    const int lane = tile.lane;
+    if (!started && n > 0) {
+      lead = (uint32_t)((4 - ((uintptr_t)out & 3)) & 3);
+      if (lead > n) lead = n;
+      for (uint32_t i = 0; i < lead; i++) c = T->t[(c ^ out[i]) & 0xff] ^ (c >> 8);
+      started = true;
+    }
+    if (n >= lead) advance(lane, out, n, T);
+    uint32_t r = c;
+    if (words) {
+      // lane l still has to advance by (32 - l) words of zeros
+      for (int k = 0; k < 32 - lane; k++) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc = T->t[acc & 0xff] ^ (acc >> 8);
+      }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) acc ^= tile.shfl_xor(acc, d);
+      r = acc;
+    }
+    const uint32_t done = lead + words * 4;
+    for (uint32_t i = done; i < n; i++) r = T->t[(r ^ out[i]) & 0xff] ^ (r >> 8);  // < 128 bytes, serial
+    return ~r;
+  }
+};
+
 // Dynamic block header (RFC 1951 3.2.7), read by ONE lane: HLIT/HDIST/HCLEN, the code-length code, then the literal/
 // length and distance code lengths into lens[0..288) and lens[288..320).  Returns an INF_* status.
 __device__ inline int read_dynamic_lengths(BitReader &br, uint16_t *cl_lut, uint8_t *lens) {

@@ -312,6 +312,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
   uint32_t outpos = 0;
   int status = INF_OK;
   bool final_block = false;
+  CrcStream crc;
 
   while (!final_block && status == INF_OK) {
     // ---- block header (lane 0), broadcast ----
@@ -361,6 +362,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
       outpos += stored_len;
       p0 += stored_len * 8;
       tile.sync();
+      if (verify_crc) crc.advance(lane, out, outpos, crcT);
       continue;
     }
     if (btype == 1) {
@@ -568,12 +570,13 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
         }
       }
       outpos += total;
+      if (verify_crc) crc.advance(lane, out, outpos, crcT);  // the round's bytes are final and still cached
     }
   }
   if (status == INF_OK && outpos != isize) status = INF_SIZE_MISMATCH;
   tile.sync();
   if (status == INF_OK && verify_crc && isize > 0) {
-    const uint32_t c = tile_crc32<32>(tile, out, isize, crcT);
+    const uint32_t c = crc.finish(tile, out, isize, crcT);
     if (c != crc_expected) status = INF_CRC_MISMATCH;
   }
   return status;
