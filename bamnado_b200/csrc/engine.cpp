@@ -208,7 +208,8 @@ DeviceCtx &ctx_for(int device) {
   c->seg_bytes = env_u64("BND_SEGMENT_BYTES", 96ull << 20);
   c->carry_cap = env_u64("BND_CARRY_BYTES", 8ull << 20);
   c->carry_cap = (c->carry_cap + REC_TILE - 1) / REC_TILE * REC_TILE;
-  c->n_readers = (int)env_u64("BND_READERS", std::min(8u, std::max(2u, host_cores_share() / 2)));
+  // 12 readers keep up with the B200 at 35 GB/s of BAM on the 16-core hosts (8: the pile-up waits 110-130 ms per 11.5 GB)
+  c->n_readers = (int)env_u64("BND_READERS", std::min(12u, std::max(2u, host_cores_share() * 3 / 4)));
   c->n_sets = (int)std::min<uint64_t>(MAX_SETS, std::max<uint64_t>(2, env_u64("BND_SETS", 6)));
   int n_slots = (int)env_u64("BND_STAGES", 4);
   if (n_slots < 2) n_slots = 2;

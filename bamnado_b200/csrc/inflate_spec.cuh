@@ -20,10 +20,6 @@
 
 namespace bnd {
 
-#ifndef BND_SPEC_RUNIN
-#define BND_SPEC_RUNIN 0
-#endif
-
 // Per-warp shared memory.  The code-length scratch (codes/lens) is only live while a block's tables are being built
 // and shares the token array.
 template <int LB, int DB, int NT, int SPAN_BITS>
@@ -281,7 +277,7 @@ extern unsigned long long g_dbg[16];
 template <class Smem>
 __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables &T, const uint8_t *blk, uint32_t blk_size, uint8_t *out,
                                   uint32_t isize_expected, const CrcTables *crcT, int verify_crc) {
-  constexpr int NM = Smem::MAX_MATCHES, SPAN = Smem::SPAN, STAGE_WORDS = Smem::STAGE_WORDS, RUNIN = BND_SPEC_RUNIN;
+  constexpr int NM = Smem::MAX_MATCHES, SPAN = Smem::SPAN, STAGE_WORDS = Smem::STAGE_WORDS;
   static_assert(SPAN >= 64 && (SPAN + 64) / 2 <= NM, "a span's matches (>= 2 bits each) must fit the match list");
   const int lane = tile.lane;
   if (blk_size < 26) return INF_BAD_HEADER;
@@ -387,8 +383,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
       tile.sync();
       const uint32_t sbit0 = p0 & ~31u;  // bit address of the first staged word
       // ---- pass 1: every lane decodes its span from the span's first bit ----
-      // (speculative lanes start RUNIN bits early: more codes to fall into step with the true sequence before the span's end)
-      uint32_t start = p0 + (uint32_t)lane * SPAN - (lane ? (uint32_t)RUNIN : 0u);
+      uint32_t start = p0 + (uint32_t)lane * SPAN;
       const uint32_t limit = tmin(p0 + (uint32_t)(lane + 1) * SPAN, end_bit);
       uint32_t exitb = start, flag = SPAN_PAST_END, cnt = 0;  // cnt: matches | bytes << 12
       auto scan = [&]() {
