@@ -504,12 +504,13 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
             tile.sync();
             continue;
           }
-          // short ready matches (<= 16 bytes): one per lane; longer ones: the whole warp, up to three at a time
-          // (<= 64 bytes each) with all loads issued before the first store; the rare longer ones one by one
-          const bool par = ready && length <= 16;
+          // Many ready matches: the short ones (<= 16 bytes) one per lane, the others by the whole warp, up to three at
+          // a time (<= 64 bytes each); all loads are issued before the first store.  Up to three ready matches (the usual
+          // case after a batch's first wave): all of them by the whole warp, which costs a fraction of the per-lane path.
+          const bool few = __popc(rmask) <= 3;
+          const bool par = !few && ready && length <= 16;
           uint32_t wide = rmask & ~tile.ballot(par);
           const uint32_t wide0 = wide;
-          (void)wide0;
           uint8_t buf[16];
           if (par) {
             const uint8_t *src = out + mypos - dist;
@@ -542,15 +543,17 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
             for (int i = 0; i < 16; i++)
               if ((uint32_t)i < length) dst[i] = buf[i];
           }
+          if (wide0) {  // uniform
 #pragma unroll
-          for (int k = 0; k < 3; k++) {
-            uint8_t *dst = out + wpos[k];
-            if ((uint32_t)lane < wlen[k]) dst[lane] = wa[k];
-            if ((uint32_t)lane + 32u < wlen[k]) dst[lane + 32] = wb[k];
+            for (int k = 0; k < 3; k++) {
+              uint8_t *dst = out + wpos[k];
+              if ((uint32_t)lane < wlen[k]) dst[lane] = wa[k];
+              if ((uint32_t)lane + 32u < wlen[k]) dst[lane + 32] = wb[k];
+            }
           }
-#pragma unroll 1
           BND_STAT(9, lane == 0 ? __builtin_popcount(rmask) : 0);
           BND_STAT(10, lane == 0 ? __builtin_popcount(wide0) : 0);
+#pragma unroll 1
           while (wide) {  // ready, disjoint from their source, not yet copied: more than three or longer than 64 bytes
             const int sl = __ffs((int)wide) - 1;
             wide &= wide - 1;
