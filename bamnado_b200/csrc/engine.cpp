@@ -777,6 +777,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
   const bool verify_crc = env_u64("BND_VERIFY_CRC", 1) != 0;
   const int use_window = (int)env_u64("BND_USE_WINDOW", 1);
   const bool serialize = env_u64("BND_SERIALIZE", 0) != 0;  // one segment at a time: clean per-kernel event timings
+  const bool dbg_k1_only = env_u64("BND_DEBUG_K1_ONLY", 0) != 0;  // timing experiments only: K2-K4 are skipped, results are meaningless
   for (auto &s : ctx.sets) s.carry_pending = false;
 
   size_t i = 0;
@@ -884,7 +885,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
       ra.rec_off = S.rec_off.as<uint64_t>();
       ra.st = S.st;
       ra.carry_cap = ctx.carry_cap;
-      CU(launch_record_index(ra, st));
+      if (!dbg_k1_only) CU(launch_record_index(ra, st));
       CU(cudaEventRecord(S.ev_idx, st));
       CU(cudaEventRecord(E.e[3], st));
       PileArgs pa{};
@@ -898,7 +899,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
       pa.p = im.pdev;
       pa.g = im.gdev;
       pa.use_window = use_window;
-      CU(launch_pileup(pa, ctx.sm_count, st));
+      if (!dbg_k1_only) CU(launch_pileup(pa, ctx.sm_count, st));
       CU(cudaEventRecord(E.e[4], st));
       shape_.comp_bytes += clen;
       shape_.inflated_bytes += ulen;
