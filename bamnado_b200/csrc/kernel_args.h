@@ -38,8 +38,8 @@ struct InflateArgs {
   int verify_crc;
 };
 
-constexpr uint32_t REC_TILE = 8192;    // bytes of inflated stream per tile
-constexpr uint32_t REC_SLOTS = 232;    // >= ceil(REC_TILE / 36): a record is at least 4 + 32 bytes
+constexpr uint32_t REC_TILE = 16384;   // bytes of inflated stream per tile
+constexpr uint32_t REC_SLOTS = 456;    // >= ceil(REC_TILE / 36): a record is at least 4 + 32 bytes
 constexpr uint64_t REC_NONE = ~0ull;   // "no / invalid offset"
 constexpr uint32_t REC_MAX_SIZE = 1u << 28;
 
