@@ -288,6 +288,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
   const uint32_t crc_expected = pend[0] | ((uint32_t)pend[1] << 8) | ((uint32_t)pend[2] << 16) | ((uint32_t)pend[3] << 24);
   const uint32_t isize = pend[4] | ((uint32_t)pend[5] << 8) | ((uint32_t)pend[6] << 16) | ((uint32_t)pend[7] << 24);
   if (isize != isize_expected) return INF_SIZE_MISMATCH;
+  if (isize > 65536u) return INF_BAD_HEADER;  // BGZF blocks hold at most 64 KiB (SAM spec 4.1); match positions are 16-bit here
 
   // the payload as a bit-addressed array of aligned words
   const uint32_t *base = (const uint32_t *)((uintptr_t)payload & ~(uintptr_t)3);

@@ -110,6 +110,13 @@ def test_spec_inflate_corruption_is_detected_not_decoded(backend):
                 assert s != 0 or chunk == payload
 
 
+def test_spec_inflate_rejects_oversized_block(backend):
+    # a gzip member that claims (and holds) more than the 64 KiB a BGZF block may inflate to (SAM spec 4.1) is refused by
+    # the block scan before anything is launched (the kernel's 16-bit match positions rely on it)
+    with pytest.raises(RuntimeError, match="ISIZE exceeds 64 KiB"):
+        backend.bgzf_inflate(bgzf_block(b"hello world " * 100) + bgzf_block(b"A" * 70000))
+
+
 @pytest.mark.gpu
 def test_spec_inflate_zoo_on_gpu_many_copies(native_gpu):
     # the same zoo, every block repeated so that all resident warps decode different streams side by side
