@@ -18,6 +18,9 @@
 #pragma once
 #include "inflate.cuh"
 
+#ifndef BND_K1_MAXREG
+#define BND_K1_MAXREG 56
+#endif
 namespace bnd {
 
 // Per-warp shared memory.  The code-length scratch (codes/lens) is only live while a block's tables are being built
@@ -582,7 +585,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
 }
 
 template <int THREADS, int MIN_CTAS, int LB, int DB, int SPAN, int NT>
-__global__ void __launch_bounds__(THREADS, MIN_CTAS) bgzf_inflate_spec_kernel(InflateArgs a) {
+__global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs a) {
   using Smem = SpecSmemT<LB, DB, NT, SPAN>;
   BND_DYN_SMEM(smem_raw);
   constexpr int WARPS = THREADS / 32;

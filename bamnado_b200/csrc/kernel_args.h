@@ -134,7 +134,7 @@ struct GeomDev {
   uint64_t bin_lo, bin_hi;          // global bin range of those chunks; the diff array has bin_hi - bin_lo + 1 slots
 };
 
-constexpr int PILE_THREADS = 256;
+constexpr int PILE_THREADS = 128;
 constexpr int PILE_RPT = 4;                      // records per thread per tile
 constexpr uint32_t PILE_WIN = 2048;              // bins in the CTA-private window
 constexpr uint32_t PILE_WIN_MARGIN = PILE_WIN / 8;

@@ -135,13 +135,13 @@ cudaError_t launch_record_index(const RecArgs &a, cudaStream_t s) {
   if (a.n_tiles == 0) return cudaSuccess;
   constexpr int T = 256;
   auto k1 = rec_guess_walk_kernel<T>;
-  auto k2 = rec_fix_scan_kernel<1024>;
+  auto k2 = rec_fix_scan_kernel<256>;
   auto k3 = rec_compact_kernel<T>;
   unsigned grid = (unsigned)(((uint64_t)a.n_tiles * 32 + T - 1) / T);
   BND_LAUNCH(k1, dim3(grid), dim3(T), 0, s, a);
   cudaError_t e = launched();
   if (e != cudaSuccess) return e;
-  BND_LAUNCH(k2, dim3(1), dim3(1024), 0, s, a);
+  BND_LAUNCH(k2, dim3(1), dim3(256), 0, s, a);
   e = launched();
   if (e != cudaSuccess) return e;
   BND_LAUNCH(k3, dim3(grid), dim3(T), 0, s, a);
@@ -155,7 +155,7 @@ cudaError_t launch_carry_copy(const uint8_t *src_buf, uint8_t *dst_buf, const Se
 }
 
 cudaError_t launch_pileup(const PileArgs &a, int sm_count, cudaStream_t s) {
-  BND_LAUNCH(pileup_kernel, dim3((unsigned)(sm_count * 8)), dim3(PILE_THREADS), 0, s, a);
+  BND_LAUNCH(pileup_kernel, dim3((unsigned)(sm_count * 16)), dim3(PILE_THREADS), 0, s, a);
   return launched();
 }
 

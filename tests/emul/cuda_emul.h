@@ -23,6 +23,7 @@
 #define __constant__ static const
 #define __shared__ static thread_local
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __restrict__
 #define __align__(n) __attribute__((aligned(n)))
 
