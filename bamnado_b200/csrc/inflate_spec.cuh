@@ -8,7 +8,8 @@
 //            it left the span (`exit`: the first code boundary at or beyond the span's end);
 //   fix-up   lane i restarts from the exit of lane i-1 whenever that differs from where it started; repeated until
 //            nothing changes.  Lane 0 is right by construction and every iteration makes at least one more lane right,
-//            so the loop ends after <= 32 iterations (typically 2: synchronisation happens well inside one span);
+//            so the loop ends after <= 32 iterations (2.6 on average on BAM data: 90 % of the lanes synchronise inside
+//            their own span);
 //   store    every lane now knows how many bytes and matches the lanes before it produce (a warp scan), so a last pass
 //            writes the literals straight to their place in the output and appends the matches (position, length,
 //            distance) to one list in shared memory.
@@ -18,13 +19,15 @@
 #pragma once
 #include "inflate.cuh"
 
+// Register cap of the kernel: 960 threads x 56 registers leave room on every SM for one block of the small kernels of the
+// previous segment (K2, K3/K4), which otherwise wait for the whole launch to drain (profiles/r1_sweeps.md).
 #ifndef BND_K1_MAXREG
 #define BND_K1_MAXREG 56
 #endif
 namespace bnd {
 
 // Per-warp shared memory.  The code-length scratch (codes/lens) is only live while a block's tables are being built
-// and shares the token array.
+// and shares the match list.
 template <int LB, int DB, int NT, int SPAN_BITS>
 struct alignas(16) SpecSmemT {
   static constexpr int LIT_BITS = LB, DIST_BITS = DB, MAX_MATCHES = NT, SPAN = SPAN_BITS;
