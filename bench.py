@@ -151,7 +151,7 @@ def run_reference(args, bam: Path, meta: dict):
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "compressed_GBps": v * meta["file_bytes"] / meta["records"] / 1e9,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, meta):
@@ -160,6 +160,29 @@ def config_dict(args, meta):
                         f"--min-mapq 30 --proper-pairs, bedGraph",
             "pairs": args.pairs, "bin_size": BIN, "parallelism": f"chunk-sharded x{args.gpus}" if args.gpus > 1 else "single GPU",
             "l2": "inputs (compressed + inflated stream) are far larger than the 126 MB L2; no explicit flush"}
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly one JSON line, but native libraries write there too (NCCL prints its version banner on
+    the first collective): file descriptor 1 is pointed at stderr for the whole run and the result line goes to a saved
+    duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -171,6 +194,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("BND_BENCH_PAIRS", "100000000")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -191,9 +215,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its debug output (the version banner at WARN/VERSION, everything at INFO) to stdout by default; rank 0's
-        # stdout must hold exactly one JSON line, so whatever level the caller asked for goes to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -345,7 +366,7 @@ def main():
             "gpu_launches": launches, "rows": rows, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stages_ms_resident_last_step": tm_res,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
