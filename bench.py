@@ -363,7 +363,7 @@ def main():
             "compressed_GBps": meta["file_bytes"] * args.steps / res_s / 1e9,
             "e2e": {"value": e2e, "unit": "reads/s", "ms_per_step": 1e3 * e2e_s / args.steps, "compressed_GBps": meta["file_bytes"] * args.steps / e2e_s / 1e9,
                     "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": out_bytes, "stages_ms_last_step": tm_e2e},
-            "gpu_launches": launches, "rows": rows, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "rows": rows, "host_cores": os.cpu_count(), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stages_ms_resident_last_step": tm_res,
         }
         emit(line)
