@@ -130,3 +130,39 @@ def test_spec_inflate_zoo_on_gpu_many_copies(native_gpu):
     out, status = native_gpu.bgzf_inflate(b"".join(blocks))
     assert int(np.count_nonzero(status)) == 0
     assert out == b"".join(expected)
+
+
+@pytest.mark.parametrize("variant", ["0", "6", "11"])
+def test_other_kernel_shapes_stay_correct(variant, tmp_path):
+    # BND_INFLATE_VARIANT is read once per process: the single-lane kernel (0), the 10-bit-root shape (6) and the
+    # 256-entry match list (11: lanes are dropped whenever a round holds more matches) run the zoo in a child process
+    # against the CPU emulator build
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    code = (
+        "import ctypes, sys, zlib\n"
+        f"sys.path.insert(0, {str(root)!r}); sys.path.insert(0, {str(root / 'tests')!r})\n"
+        "from bamnado_b200._native import Native\n"
+        "from bamnado_b200.build import build_emul\n"
+        "from test_inflate_stress import payload_zoo, bgzf_block\n"
+        "nat = Native(ctypes.CDLL(str(build_emul())))\n"
+        "zoo = payload_zoo(3)\n"
+        "blocks, exp = [], []\n"
+        "for name, p in zoo.items():\n"
+        "    for lvl, strat in ((6, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_HUFFMAN_ONLY), (1, zlib.Z_FIXED)):\n"
+        "        q = p[:40000] if strat == zlib.Z_HUFFMAN_ONLY and name == 'random' else p\n"
+        "        try:\n"
+        "            blocks.append(bgzf_block(q, lvl, strat)); exp.append(q)\n"
+        "        except AssertionError:\n"
+        "            pass\n"
+        "out, st = nat.bgzf_inflate(b''.join(blocks))\n"
+        "assert not st.any(), st\n"
+        "assert out == b''.join(exp)\n"
+        "print('ok', len(blocks))\n"
+    )
+    env = dict(**__import__("os").environ, BND_INFLATE_VARIANT=variant)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
