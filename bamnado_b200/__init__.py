@@ -9,7 +9,7 @@ import numpy as np
 
 from . import _native
 
-__all__ = ["ReadFilter", "get_signal_for_chromosome", "__version__"]
+__all__ = ["ReadFilter", "get_signal_for_chromosome", "__version__", "count_bins", "BinCounts"]
 
 
 def __version__() -> str:

@@ -73,7 +73,9 @@ def test_compute_fails_loudly_without_a_gpu(product_lib):
 def test_python_surface_mirrors_reference():
     import bamnado_b200 as b
 
-    assert b.__all__ == ["ReadFilter", "get_signal_for_chromosome", "__version__"]
+    # the reference module's names for this path, plus the count_bins front half of compute_scale_factors (lib.rs:505)
+    assert b.__all__ == ["ReadFilter", "get_signal_for_chromosome", "__version__", "count_bins", "BinCounts"]
+    assert callable(b.count_bins)
     f = b.ReadFilter()
     assert (f.min_mapq, f.proper_pair, f.min_length, f.max_length, f.strand) == (0, False, 0, 1000, "both")
     with pytest.raises(ValueError):
