@@ -166,3 +166,49 @@ def test_other_kernel_shapes_stay_correct(variant, tmp_path):
     env = dict(**__import__("os").environ, BND_INFLATE_VARIANT=variant)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def _random_payload(rng, max_len=60000):
+    """A payload stitched from pieces of very different statistics, so that code lengths, match lengths and distances
+    change inside one block (and inside one round of the speculative walk)."""
+    out = bytearray()
+    n = int(rng.integers(1, max_len))
+    while len(out) < n:
+        kind = int(rng.integers(0, 6))
+        k = int(rng.integers(1, 4000))
+        if kind == 0:
+            out += bytes(rng.integers(0, 256, k, dtype=np.uint8))                        # incompressible
+        elif kind == 1:
+            out += bytes([int(rng.integers(0, 256))]) * k                                  # one long run
+        elif kind == 2:
+            alpha = rng.integers(0, 256, int(rng.integers(2, 20)), dtype=np.uint8)
+            out += bytes(alpha[rng.integers(0, len(alpha), k)])                            # small alphabet
+        elif kind == 3 and len(out) > 8:
+            d = int(rng.integers(1, min(len(out), 32768) + 1))                             # copy from far back
+            src = len(out) - d
+            out += bytes(out[src:src + min(k, d)])
+        elif kind == 4:
+            unit = bytes(rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8))
+            out += (unit * (k // len(unit) + 1))[:k]                                       # periodic
+        else:
+            out += bytes(np.minimum(rng.geometric(0.08, k), 255).astype(np.uint8))         # skewed
+    return bytes(out[:n])
+
+
+def test_spec_inflate_random_structures(backend):
+    rng = np.random.default_rng(20260219)
+    blocks, expected = [], []
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_RLE, zlib.Z_HUFFMAN_ONLY, zlib.Z_FIXED]
+    while len(blocks) < 120:
+        p = _random_payload(rng)
+        level = int(rng.integers(1, 10))
+        strat = strategies[int(rng.integers(0, len(strategies)))]
+        flush = int(rng.choice([0, 0, 0, 513, 5000]))
+        try:
+            blocks.append(bgzf_block(p, level, strat, mem_level=int(rng.integers(1, 10)), flush_every=flush))
+        except AssertionError:
+            continue  # did not fit one BGZF block
+        expected.append(p)
+    out, status = backend.bgzf_inflate(b"".join(blocks))
+    assert not np.count_nonzero(status), [int(i) for i in np.nonzero(status)[0]]
+    assert out == b"".join(expected)
