@@ -1815,7 +1815,31 @@ void Pileup::bedgraph_text(std::string &out) {
   tm_.text_ms = now_ms() - t0;
 }
 
+// Unmaps finished output mappings off the caller's critical path.  The threads are joined when the next job starts and
+// when the library is unloaded, so no thread of ours outlives the code it runs.
+namespace {
+struct Unmapper {
+  std::mutex mu;
+  std::vector<std::thread> threads;
+  void reap() {
+    std::vector<std::thread> t;
+    {
+      std::lock_guard<std::mutex> g(mu);
+      t.swap(threads);
+    }
+    for (auto &x : t)
+      if (x.joinable()) x.join();
+  }
+  void submit(char *map, uint64_t len) {
+    std::lock_guard<std::mutex> g(mu);
+    threads.emplace_back([map, len] { munmap(map, len); });
+  }
+  ~Unmapper() { reap(); }
+} g_unmapper;
+}  // namespace
+
 void Pileup::to_bedgraph(const std::string &path) {
+  g_unmapper.reap();
   DeviceCtx &ctx = *im_->ctx;
   const double t00 = now_ms();
   int fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
@@ -1906,8 +1930,8 @@ void Pileup::to_bedgraph(const std::string &path) {
   }
   const double t2a = now_ms();
   // The file's pages are complete; tearing down 2 GB of page-table entries (26 ms) only concerns this process's address
-  // space, so it is left to a detached thread and the file is truncated to size and closed right away.
-  if (map) std::thread([map, out_bytes] { munmap(map, out_bytes); }).detach();
+  // space, so it is left to a background thread and the file is truncated to size and closed right away.
+  if (map) g_unmapper.submit(map, out_bytes);
   const double t2 = now_ms();
   if (ftruncate(fd, (off_t)out_bytes) != 0) {
     close(fd);
