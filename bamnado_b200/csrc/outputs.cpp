@@ -49,7 +49,7 @@ struct Section {  // one BigWig data section (<= ITEMS_PER_SLOT bedGraph items o
   uint32_t chrom, start, end;
   uint64_t offset, size;
 };
-constexpr uint32_t ITEMS_PER_SLOT = 1024, BLOCK = 256;
+constexpr uint32_t ITEMS_PER_SLOT = 1024, BLOCK = 256, MAX_ZOOM = 10;
 
 // B+ tree over (name -> id, size), keys sorted bytewise
 void write_chrom_tree(Buf &b, std::vector<std::tuple<std::string, uint32_t, uint32_t>> items) {
@@ -210,7 +210,7 @@ std::string lower(std::string s) {
 
 // ---- to_bigwig (coverage_analysis.rs:642-759) -------------------------------------------------------------------------------
 // Rows: optional scaffold drop, BAM header order, start-1 / end-1, score = (count as f64 * factor) as f32.
-// The file is a version-4 bigWig with bedGraph sections, no zoom levels and uncompressed sections (uncompressBufSize 0).
+// The file is a version-4 bigWig with bedGraph sections, zoom levels and uncompressed sections (uncompressBufSize 0).
 void pileup_to_bigwig(Pileup &p, const std::string &path) {
   std::vector<RunRow> rows;
   p.runs(rows);
@@ -226,12 +226,18 @@ void pileup_to_bigwig(Pileup &p, const std::string &path) {
     if (keep[r]) chroms.emplace_back(h.names[r], (uint32_t)r, (uint32_t)h.lens[r]);
   }
   Buf b;
-  b.pad_to(64 + 40);  // header + total summary, filled at the end
+  b.pad_to(64 + MAX_ZOOM * 24 + 40);  // header, zoom headers, total summary: filled at the end
   const uint64_t chrom_tree_off = b.d.size();
   write_chrom_tree(b, chroms);
   const uint64_t data_off = b.d.size();
   b.u64(0);  // section count, patched below
   std::vector<Section> secs;
+  struct Item {
+    uint32_t chrom, start, end;
+    float v;
+  };
+  std::vector<Item> items;  // what the zoom levels summarise
+  items.reserve(rows.size());
   uint64_t covered = 0;
   double mn = 0, mx = 0, sum = 0, sumsq = 0;
   bool any = false;
@@ -257,6 +263,7 @@ void pileup_to_bigwig(Pileup &p, const std::string &path) {
           const uint32_t st = (uint32_t)(rows[k].start - 1), en = (uint32_t)(rows[k].stop - 1);
           const float v = (float)((double)rows[k].val * factor);
           b.u32(st), b.u32(en), b.f32(v);
+          items.push_back(Item{(uint32_t)ref, st, en, v});
           const double w = (double)(en - st), dv = (double)v;
           covered += en - st;
           sum += dv * w;
@@ -274,19 +281,86 @@ void pileup_to_bigwig(Pileup &p, const std::string &path) {
   b.put_u64_at(data_off, secs.size());
   const uint64_t index_off = b.d.size();
   write_rtree(b, secs, index_off);
+  // Zoom levels (what bigtools / UCSC writers add for viewers): per level, every chromosome is cut into windows of
+  // `reduction` bases and each window that holds data gets one summary record (covered bases, min, max, sum, sum of
+  // squares); the first reduction is ~10x the mean item width, each further level 4x coarser, until a level is small.
+  struct ZoomHdr {
+    uint32_t reduction;
+    uint64_t data_off, index_off;
+  };
+  std::vector<ZoomHdr> zooms;
+  if (!items.empty()) {
+    uint64_t reduction = std::max<uint64_t>(10, covered / items.size() * 10);
+    for (uint32_t z = 0; z < MAX_ZOOM && reduction <= 0x7fffffffull; z++, reduction *= 4) {
+      struct Rec {
+        uint32_t chrom, start, end, valid;
+        float mn, mx, sum, sumsq;
+      };
+      std::vector<Rec> recs;
+      for (const Item &it : items) {
+        for (uint64_t w = it.start / reduction; w * reduction < it.end; w++) {  // windows the item overlaps
+          const uint32_t a = (uint32_t)std::max<uint64_t>(it.start, w * reduction), e = (uint32_t)std::min<uint64_t>(it.end, (w + 1) * reduction);
+          const float n = (float)(e - a);
+          if (!recs.empty() && recs.back().chrom == it.chrom && recs.back().start / reduction == w) {
+            Rec &r = recs.back();
+            r.end = e;
+            r.valid += e - a;
+            r.mn = std::min(r.mn, it.v);
+            r.mx = std::max(r.mx, it.v);
+            r.sum += it.v * n;
+            r.sumsq += it.v * it.v * n;
+          } else {
+            recs.push_back(Rec{it.chrom, a, e, e - a, it.v, it.v, it.v * n, it.v * it.v * n});
+          }
+        }
+      }
+      if (z > 0 && recs.size() < 64) break;  // coarse enough: a viewer reads the previous level in one go
+      ZoomHdr zh;
+      zh.reduction = (uint32_t)reduction;
+      zh.data_off = b.d.size();
+      b.u32((uint32_t)std::min<uint64_t>(recs.size(), 0xffffffffull));
+      std::vector<Section> zsecs;
+      for (size_t r0 = 0; r0 < recs.size();) {
+        size_t r1 = r0;
+        while (r1 < recs.size() && r1 - r0 < ITEMS_PER_SLOT && recs[r1].chrom == recs[r0].chrom) r1++;
+        Section sec;
+        sec.chrom = recs[r0].chrom;
+        sec.start = recs[r0].start;
+        sec.end = recs[r1 - 1].end;
+        sec.offset = b.d.size();
+        for (size_t k = r0; k < r1; k++) {
+          const Rec &r = recs[k];
+          b.u32(r.chrom), b.u32(r.start), b.u32(r.end), b.u32(r.valid);
+          b.f32(r.mn), b.f32(r.mx), b.f32(r.sum), b.f32(r.sumsq);
+        }
+        sec.size = b.d.size() - sec.offset;
+        zsecs.push_back(sec);
+        r0 = r1;
+      }
+      zh.index_off = b.d.size();
+      write_rtree(b, zsecs, zh.index_off);
+      zooms.push_back(zh);
+      if (recs.size() < 64) break;
+    }
+  }
   // header
   Buf hd;
   hd.u32(0x888FFC26);
   hd.u16(4);
-  hd.u16(0);  // zoom levels
+  hd.u16((uint16_t)zooms.size());
   hd.u64(chrom_tree_off);
   hd.u64(data_off);
   hd.u64(index_off);
   hd.u16(0), hd.u16(0);
   hd.u64(0);
-  hd.u64(64);  // total summary offset
+  hd.u64(64 + MAX_ZOOM * 24);  // total summary offset: after the (reserved) zoom headers
   hd.u32(0);   // uncompressBufSize: sections are stored raw
   hd.u64(0);
+  for (uint32_t z = 0; z < MAX_ZOOM; z++) {
+    const bool on = z < zooms.size();
+    hd.u32(on ? zooms[z].reduction : 0), hd.u32(0);
+    hd.u64(on ? zooms[z].data_off : 0), hd.u64(on ? zooms[z].index_off : 0);
+  }
   hd.u64(covered), hd.f64(mn), hd.f64(mx), hd.f64(sum), hd.f64(sumsq);
   memcpy(b.d.data(), hd.d.data(), hd.d.size());
   b.u32(0x888FFC26);  // trailing magic, as UCSC writers append

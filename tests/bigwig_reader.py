@@ -74,4 +74,22 @@ def read_bigwig(path):
     if summ_off:
         cov, mn, mx, sm, sq = struct.unpack_from("<Qdddd", d, summ_off)
         summary = dict(bases_covered=cov, min_val=mn, max_val=mx, sum_data=sm, sum_squares=sq)
-    return dict(chroms=chroms, intervals=intervals, summary=summary, zoom_levels=zooms, version=version)
+    zoom = []
+    for z in range(zooms):
+        reduction, _, zdata, zindex = struct.unpack_from("<IIQQ", d, 64 + 24 * z)
+        (count,) = struct.unpack_from("<I", d, zdata)
+        zmagic, _, zitems = struct.unpack_from("<IIQ", d, zindex)
+        assert zmagic == 0x2468ACE0
+        leaves.clear()
+        if zitems:
+            walk_r(zindex + 48)
+        recs = []
+        for doff, dsize in sorted(leaves):
+            sec = d[doff:doff + dsize]
+            if ubuf:
+                sec = zlib.decompress(sec)
+            for k in range(len(sec) // 32):
+                recs.append(struct.unpack_from("<IIIIffff", sec, 32 * k))  # chrom, start, end, valid, min, max, sum, sumsq
+        # UCSC writers put the record count in front of a level's blocks, libBigWig (deepTools) does not: reported, not checked
+        zoom.append(dict(reduction=reduction, records=recs, leading_count=count))
+    return dict(chroms=chroms, intervals=intervals, summary=summary, zoom_levels=zooms, version=version, zoom=zoom)

@@ -26,6 +26,45 @@ def test_bigwig_matches_reference_known_answers(backend, oracle, tmp_path):
         assert len(bw["chroms"]) == 456 and bw["chroms"]["chr9"] == (58, 138394717)
 
 
+def test_bigwig_zoom_levels_summarise_the_data(backend, tmp_path, make_bam):
+    # zoom records are recomputed from the file's own intervals: windows of `reduction` bases per chromosome, covered
+    # bases, min, max, sum and sum of squares (f32 accumulation like the writer's)
+    bam = make_bam("pe", "--pairs", 20000, "--odd")
+    out = tmp_path / "z.bw"
+    with backend.pileup(dict(bam_path=bam, bin_size=50, norm="cpm"), CLI_FILTER) as h:
+        h.to_bigwig(out)
+    bw = read_bigwig(out)
+    assert 1 <= bw["zoom_levels"] <= 10
+    prev = 0
+    for z in bw["zoom"]:
+        red = z["reduction"]
+        assert red > prev
+        prev = red
+        exp = {}
+        for cid, s, e, v in bw["intervals"]:
+            v = np.float32(v)
+            for w in range(s // red, (e - 1) // red + 1):
+                a, b = max(s, w * red), min(e, (w + 1) * red)
+                n = np.float32(b - a)
+                r = exp.get((cid, w))
+                if r is None:
+                    exp[(cid, w)] = [a, b, b - a, v, v, v * n, v * v * n]
+                else:
+                    r[1] = b
+                    r[2] += b - a
+                    r[3], r[4] = min(r[3], v), max(r[4], v)
+                    r[5] = np.float32(r[5] + v * n)
+                    r[6] = np.float32(r[6] + v * v * n)
+        got = z["records"]
+        assert len(got) == len(exp) == z["leading_count"]
+        for (cid, s, e, valid, mn, mx, sm, sq), ((ecid, w), r) in zip(got, sorted(exp.items())):
+            assert (cid, s, e, valid) == (ecid, r[0], r[1], r[2])
+            assert (np.float32(mn), np.float32(mx)) == (r[3], r[4])
+            assert abs(sm - float(r[5])) <= 1e-5 * max(1.0, abs(float(r[5]))) and abs(sq - float(r[6])) <= 1e-5 * max(1.0, abs(float(r[6])))
+    counts = [len(z["records"]) for z in bw["zoom"]]
+    assert counts == sorted(counts, reverse=True) and counts[0] < len(bw["intervals"])  # every level is coarser than the last
+
+
 def test_bigwig_ignore_scaffold_and_large(backend, oracle, tmp_path, make_bam):
     bam = make_bam("pe", "--pairs", 20000, "--odd")
     out = tmp_path / "x.bigwig"
