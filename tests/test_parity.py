@@ -163,7 +163,7 @@ def test_signal_for_chromosome(backend, oracle, make_bam):
         backend.signal_for_chromosome(pile, {}, "nope")
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_contig_sharded_union_equals_whole(backend, oracle, make_bam, world, small_segments):
     # §8(e): shards own disjoint chunk ranges; rows concatenate, counters add up (13 x u64 sum before CPM/RPKM)
     bam = make_bam("pe", "--pairs", 20000, "--odd")
