@@ -43,7 +43,7 @@ struct InflateVariant {
 // lane-group width / CTA size / resident CTAs per SM (and LUT widths below); selected with BND_INFLATE_VARIANT
 const InflateVariant kVariants[] = {{32, 256, 5}, {32, 128, 9}, {32, 128, 12}, {32, 256, 6}, {32, 256, 4}, {32, 128, 8},
                                     // 6..: speculative 32-lane walk (inflate_spec.cuh)
-                                    {32, 256, 3}, {32, 128, 5}, {32, 256, 2}, {32, 192, 4}, {32, 224, 4}, {32, 256, 4}, {32, 320, 3}, {32, 192, 5}, {32, 160, 6}};
+                                    {32, 256, 3}, {32, 128, 5}, {32, 256, 2}, {32, 192, 4}, {32, 224, 4}, {32, 256, 4}, {32, 320, 3}, {32, 192, 5}, {32, 160, 6}, {32, 320, 3}, {32, 320, 3}};
 constexpr int kDefaultVariant = 12;  // speculative walk, 320 threads x 3 CTAs / SM = 30 warps, 9-bit root table (profiles/r1_sweeps.md)
 int variant_index() {
   static int v = -1;
@@ -126,6 +126,8 @@ cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
     case 6: return launch_inflate_spec_t<256, 3, 10, 8, 256, 512>(a, sm_count, v.ctas_per_sm, s);
     case 13: return launch_inflate_spec_t<192, 5, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // smaller CTAs leave the SM sooner in a launch's tail
     case 14: return launch_inflate_spec_t<160, 6, 9, 8, 256, 320>(a, sm_count, v.ctas_per_sm, s);
+    case 15: return launch_inflate_spec_t<320, 3, 9, 8, 320, 384>(a, sm_count, v.ctas_per_sm, s);  // longer spans: fewer rounds and fix-ups
+    case 16: return launch_inflate_spec_t<320, 3, 9, 8, 288, 384>(a, sm_count, v.ctas_per_sm, s);
     case 0: return launch_inflate_t<32, 256, 5, 10, 8>(a, sm_count, v.ctas_per_sm, s);  // single-lane walk (round-1 v10)
     default: return launch_inflate_spec_t<320, 3, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM, 64 registers
   }
