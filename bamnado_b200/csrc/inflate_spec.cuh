@@ -180,6 +180,15 @@ __device__ bool build_dist_tables(const Tile<32> &tile, Smem &S) {
   return true;
 }
 
+#ifdef BND_EMUL_STATS
+}  // namespace bnd
+#include <vector>
+namespace bnd {
+// statistics build only (scripts/spec_stats.py): where a decode pass saw token boundaries, to measure how many bits a lane
+// restarted at its true position needs before it is back on the path of its speculative pass
+static thread_local std::vector<uint32_t> *g_dbg_path = nullptr;
+#endif
+
 // Decode tokens from bit `start` until the position reaches `limit` (> start), an end-of-block code or an undecodable
 // code.  Bits are addressed from the first bit of the staged words.  Returns {bit position after the last token |
 // flag << 24, matches | output bytes << 12}.  STORE: the span is known to be a true one and `opos` is the output position
@@ -198,6 +207,9 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
   uint32_t nm = 0, bytes = 0, flag = SPAN_OK;
 #pragma unroll 1
   do {
+#ifdef BND_EMUL_STATS
+    if (g_dbg_path) g_dbg_path->push_back((uint32_t)((int32_t)limit - remain));  // bit position of this token's first bit
+#endif
     const uint32_t w = __funnelshift_r(lo, hi, pos);
     uint32_t e = lds_u16(lit0 + 2 * (w & ((1u << LIT_BITS) - 1u)));
     if ((e & 31u) == 0)  // second level (or the reserved zero entry)
@@ -405,7 +417,15 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
           cnt = 0;
         }
       };
+#ifdef BND_EMUL_STATS
+      std::vector<uint32_t> dbg_p1, dbg_p2;
+      g_dbg_path = &dbg_p1;
+#endif
       scan();
+#ifdef BND_EMUL_STATS
+      g_dbg_path = nullptr;
+      int dbg_iter = 0;
+#endif
       BND_STAT(0, lane == 0);
       // ---- fix-up: restart from the predecessor's exit until every live lane starts where its predecessor stopped ----
       int first_term;
@@ -420,8 +440,42 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
         BND_STAT(2, need);
         if (need) {
           start = want;
+#ifdef BND_EMUL_STATS
+          if (dbg_iter == 0) {
+            dbg_p2.clear();
+            g_dbg_path = &dbg_p2;
+          }
+#endif
           scan();
+#ifdef BND_EMUL_STATS
+          g_dbg_path = nullptr;
+#endif
         }
+#ifdef BND_EMUL_STATS
+        if (dbg_iter == 0) {
+          // bits from the true start to the first token boundary shared with the speculative pass (whole span if none)
+          uint32_t sync = 0, span_len = 0;
+          if (need && start < end_bit) {
+            span_len = limit - start;
+            sync = span_len;
+            size_t i = 0;
+            for (uint32_t p : dbg_p2) {
+              while (i < dbg_p1.size() && dbg_p1[i] < p) i++;
+              if (i < dbg_p1.size() && dbg_p1[i] == p) {
+                sync = p - (start - sbit0);
+                break;
+              }
+            }
+          }
+          uint32_t mx = sync;
+          for (int d = 16; d >= 1; d >>= 1) mx = tmax(mx, tile.shfl_xor(mx, d));
+          BND_STAT(11, sync);
+          BND_STAT(12, span_len);
+          BND_STAT(13, lane == 0 ? mx : 0);
+          BND_STAT(14, need && sync == span_len && span_len > 0);
+        }
+        dbg_iter++;
+#endif
       }
       // ---- place: lanes 0..first_term hold true tokens; take as many whole lanes as the match list holds ----
       const int nvalid = first_term < 32 ? first_term + 1 : 32;

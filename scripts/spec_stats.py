@@ -43,3 +43,7 @@ print(f"rounds {c[0]}  matches/round {c[4] / max(c[0], 1):.1f}")
 print(f"fix-up iterations/round {c[1] / max(c[0], 1):.2f}  lanes re-decoded/round {c[2] / max(c[0], 1):.2f}  dropped lanes/round {c[3] / max(c[0], 1):.2f}")
 print(f"matches {c[4]}  batches of 32: {c[6]}  waves/batch {c[5] / max(c[6], 1):.2f}  self-overlapping firsts/batch {c[7] / max(c[6], 1):.2f}")
 print(f"ready matches/wave {c[9] / max(c[5] - c[7], 1):.1f}  of them longer than 16 B: {c[10] / max(c[9], 1):.3f}  left to the one-by-one loop/batch {c[8] / max(c[6], 1):.2f}")
+if c[12]:
+    print(f"first fix-up pass: a lane is back on its speculative path after {c[11] / max(c[12], 1) * 100:.1f} % of its span on average "
+          f"({c[11] / max(c[0], 1) / 31:.0f} bits); the slowest lane of a round needs {c[13] / max(c[0], 1):.0f} bits; "
+          f"{c[14] / max(c[0], 1):.2f} lanes per round never meet it inside the span")
