@@ -187,6 +187,7 @@ namespace bnd {
 // statistics build only (scripts/spec_stats.py): where a decode pass saw token boundaries, to measure how many bits a lane
 // restarted at its true position needs before it is back on the path of its speculative pass
 static thread_local std::vector<uint32_t> *g_dbg_path = nullptr;
+extern unsigned long long g_dbg_depth;
 #endif
 
 // Decode tokens from bit `start` until the position reaches `limit` (> start), an end-of-block code or an undecodable
@@ -521,6 +522,39 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
       staged = !eob && p0 < end_bit;
       if (staged) stage_issue(p0);  // the next round's input arrives while this round's matches are resolved
       // ---- resolve the matches, 32 at a time: lane t owns match mb + t ----
+#ifdef BND_EMUL_STATS
+      if (lane == 0) {  // waves a whole-round resolution would need (same frontier rule, no batches of 32)
+        std::vector<uint8_t> done(nmatch, 0);
+        uint32_t first = 0, waves = 0;
+        while (first < nmatch) {
+          const uint32_t frontier = S.matches[first].x & 0xffffu;
+          bool any = false;
+          for (uint32_t k = first; k < nmatch; k++) {
+            if (done[k]) continue;
+            const uint2 e = S.matches[k];
+            const uint32_t p = e.x & 0xffffu, len = (e.x >> 16) + 3u;
+            if (p - e.y + len <= frontier) done[k] = 1, any = true;
+          }
+          if (!any) done[first] = 1;
+          waves++;
+          while (first < nmatch && done[first]) first++;
+        }
+        BND_STAT(15, waves);
+        // exact dependency depth: a match waits only for the matches whose output its source overlaps
+        std::vector<uint32_t> depth(nmatch, 1);
+        uint32_t deepest = 0;
+        for (uint32_t k = 0; k < nmatch; k++) {
+          const uint2 e = S.matches[k];
+          const uint32_t p = e.x & 0xffffu, len = (e.x >> 16) + 3u, s0 = p - e.y, s1 = s0 + len;
+          for (uint32_t j = 0; j < k; j++) {
+            const uint32_t pj = S.matches[j].x & 0xffffu, lj = (S.matches[j].x >> 16) + 3u;
+            if (pj < s1 && pj + lj > s0) depth[k] = tmax(depth[k], depth[j] + 1);
+          }
+          deepest = tmax(deepest, depth[k]);
+        }
+        __atomic_fetch_add(&g_dbg_depth, (unsigned long long)deepest, __ATOMIC_RELAXED);
+      }
+#endif
       for (uint32_t mb = 0; mb < nmatch; mb += 32) {
         const bool mine = mb + (uint32_t)lane < nmatch;
         const uint2 me = mine ? S.matches[mb + lane] : make_uint2(0u, 1u);
