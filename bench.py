@@ -154,6 +154,26 @@ def run_reference(args, bam: Path, meta: dict):
     emit(line)
 
 
+def measure_h2d_gbps(torch, n_bytes=1 << 30, reps=3):
+    """Pinned host -> device copy bandwidth on this box (SURVEY 8d: the roofline that binds the end-to-end path;
+    MEASURED_PEAKS.json has no H2D entry).  Best of `reps` copies of `n_bytes`, CUDA events on the current stream."""
+    try:
+        host = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+        dev = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+        best = 0.0
+        for _ in range(reps + 1):  # first copy warms up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dev.copy_(host, non_blocking=True)
+            e1.record()
+            e1.synchronize()
+            best = max(best, n_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        del host, dev
+        return best
+    except Exception:
+        return None
+
+
 def config_dict(args, meta):
     return {"workload": f"configs[1]: synthetic {args.pairs}-pair paired-end hg38 BAM (seed {SEED}, zlib-6, {meta['records']} records, "
                         f"{meta['file_bytes']} B compressed, {meta['inflated_bytes']} B inflated), bam-coverage --bin-size 50 --normalize rpkm "
@@ -356,13 +376,17 @@ def main():
         records = meta["records"]
         value = records * args.steps / res_s
         e2e = records * args.steps / e2e_s
+        h2d_peak = measure_h2d_gbps(torch)
         line = {
             "metric": "bam-coverage reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * res_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": config_dict(args, meta),
             "compressed_GBps": meta["file_bytes"] * args.steps / res_s / 1e9,
             "e2e": {"value": e2e, "unit": "reads/s", "ms_per_step": 1e3 * e2e_s / args.steps, "compressed_GBps": meta["file_bytes"] * args.steps / e2e_s / 1e9,
-                    "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": out_bytes, "stages_ms_last_step": tm_e2e},
+                    "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": out_bytes, "stages_ms_last_step": tm_e2e,
+                    # the end-to-end path against the measured pinned H2D bandwidth of this box
+                    "h2d_peak_GBps": h2d_peak,
+                    "frac_of_h2d_roofline": (meta["file_bytes"] * args.steps / e2e_s / 1e9 / h2d_peak / world) if h2d_peak else None},
             "gpu_launches": launches, "rows": rows, "host_cores": os.cpu_count(), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stages_ms_resident_last_step": tm_res,
         }
