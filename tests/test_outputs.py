@@ -141,6 +141,34 @@ def test_collapse_bedgraph_matches_oracle(backend, oracle, tmp_path, make_bam):
         assert len(a.read_text().splitlines()) < len(sel)
 
 
+def test_collapse_bedgraph_random_rows_match_oracle(backend, oracle, tmp_path):
+    # synthetic rows built to sit on every decision of collapse_adjacent_bins (bedgraph_utils.rs:5-45): touching and
+    # gapped bins, scores equal, within and just beyond 1e-6 of the previous ROW (drift chains), repeated starts,
+    # several chromosomes in shuffled order, integer- and float-looking scores
+    rng = np.random.default_rng(99)
+    for trial in range(6):
+        lines = []
+        for chrom in rng.permutation(["chr1", "chr10", "chr2", "chrX", "scaffold_9"])[: int(rng.integers(1, 6))]:
+            pos, score = int(rng.integers(0, 1000)), float(rng.integers(0, 5))
+            for _ in range(int(rng.integers(1, 400))):
+                width = int(rng.choice([1, 10, 50, 137]))
+                gap = int(rng.choice([0, 0, 0, 1, 25]))
+                step = float(rng.choice([0.0, 0.0, 4e-7, 9e-7, 1.1e-6, 1.0, -1.0, 0.5]))
+                score = max(0.0, score + step)
+                pos += gap
+                lines.append(f"{chrom}\t{pos}\t{pos + width}\t{score!r}" if rng.random() < 0.8 else f"{chrom}\t{pos}\t{pos + width}\t{int(score)}")
+                if rng.random() < 0.03:
+                    lines.append(lines[-1])  # an exact duplicate row
+                pos += width
+        order = rng.permutation(len(lines))
+        src = tmp_path / f"r{trial}.bdg"
+        src.write_text("\n".join(lines[i] for i in order) + "\n")
+        a, b = tmp_path / "ra.bdg", tmp_path / "rb.bdg"
+        backend.collapse_bedgraph(src, a)
+        oracle.collapse_bedgraph(src, b)
+        assert a.read_bytes() == b.read_bytes(), f"trial {trial}"
+
+
 def test_cli_exit_codes_and_outputs(backend, oracle, tmp_path, capfd):
     # test/test_interface.py:103-105: --help / --version -> 0, parse errors -> 2; runtime errors -> 1 (src/cli.rs:750-756)
     assert backend.cli_main(["bamnado", "--help"]) == 0
