@@ -104,6 +104,25 @@ def test_multi_bam_tsv(backend, oracle, tmp_path, make_bam):
                              [CLI_FILTER] * 2, tmp_path / "x.tsv")
 
 
+def test_multi_bam_random_filters_and_bins(backend, oracle, tmp_path, make_bam):
+    # per-BAM filters differ (coverage_analysis.rs:783-848 runs every BAM's own pile-up before the equal-row collapse),
+    # small contigs so that bin 1 and odd bin sizes stay affordable on the CPU side
+    contigs = "chr1:60000,chr2:25001,chrUn_x:9000,chrM:1657"
+    bams = [make_bam(f"mr{i}", "--pairs", 1500, "--seed", 31 + i, "--contigs", contigs, "--odd") for i in range(3)]
+    rng = np.random.default_rng(7)
+    for trial in range(5):
+        n = int(rng.integers(1, 4))
+        bin_size = int(rng.choice([1, 13, 50, 1000]))
+        use_fragment = bool(rng.random() < 0.4)
+        piles = [dict(bam_path=bams[i], bin_size=bin_size, collapse=False, use_fragment=use_fragment) for i in range(n)]
+        filts = [dict(CLI_FILTER, min_mapq=int(rng.choice([0, 20, 40])), proper_pair=bool(rng.random() < 0.5),
+                      exclude_duplicates=bool(rng.random() < 0.5)) for _ in range(n)]
+        a, b = tmp_path / f"mg{trial}.tsv", tmp_path / f"mc{trial}.tsv"
+        backend.multi_to_tsv(piles, filts, a)
+        oracle.multi_to_tsv(piles, filts, b)
+        assert _rows(a) == _rows(b), f"trial {trial}: bin {bin_size}, {n} BAMs, fragment {use_fragment}, {filts}"
+
+
 def test_collapse_bedgraph_reference_vectors(backend, tmp_path):
     # bedgraph_utils.rs:82-129
     def run(rows):
