@@ -187,7 +187,8 @@ namespace bnd {
 // statistics build only (scripts/spec_stats.py): where a decode pass saw token boundaries, to measure how many bits a lane
 // restarted at its true position needs before it is back on the path of its speculative pass
 static thread_local std::vector<uint32_t> *g_dbg_path = nullptr;
-extern unsigned long long g_dbg_depth;
+static thread_local uint32_t g_dbg_iters = 0;  // loop iterations of the last span_decode call on this host thread
+extern unsigned long long g_dbg_depth, g_dbg_iter_sum, g_dbg_iter_max;
 #endif
 
 // Decode tokens from bit `start` until the position reaches `limit` (> start), an end-of-block code or an undecodable
@@ -206,10 +207,14 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
   wa += 12;
   int32_t remain = (int32_t)(limit - start);
   uint32_t nm = 0, bytes = 0, flag = SPAN_OK;
+#ifdef BND_EMUL_STATS
+  uint32_t n_iter_dbg = 1;
+#endif
 #pragma unroll 1
   do {
 #ifdef BND_EMUL_STATS
     if (g_dbg_path) g_dbg_path->push_back((uint32_t)((int32_t)limit - remain));  // bit position of this token's first bit
+    g_dbg_iters = n_iter_dbg++;
 #endif
     const uint32_t w = __funnelshift_r(lo, hi, pos);
     uint32_t e = lds_u16(lit0 + 2 * (w & ((1u << LIT_BITS) - 1u)));
@@ -426,6 +431,13 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
 #ifdef BND_EMUL_STATS
       g_dbg_path = nullptr;
       int dbg_iter = 0;
+      {
+        const uint32_t it = start < end_bit ? g_dbg_iters : 0u;  // pass 1: iterations of this lane
+        uint32_t mx = it;
+        for (int d = 16; d >= 1; d >>= 1) mx = tmax(mx, tile.shfl_xor(mx, d));
+        __atomic_fetch_add(&g_dbg_iter_sum, (unsigned long long)it, __ATOMIC_RELAXED);
+        if (lane == 0) __atomic_fetch_add(&g_dbg_iter_max, (unsigned long long)mx, __ATOMIC_RELAXED);
+      }
 #endif
       BND_STAT(0, lane == 0);
       // ---- fix-up: restart from the predecessor's exit until every live lane starts where its predecessor stopped ----

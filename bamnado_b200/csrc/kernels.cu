@@ -88,8 +88,8 @@ cudaError_t launch_inflate_spec_t(const InflateArgs &a, int sm_count, int ctas_p
 
 #ifdef BND_EMUL_STATS
 unsigned long long g_dbg[16];
-unsigned long long g_dbg_depth;
-extern "C" unsigned long long bnd_dbg_counter(int i) { return i == 16 ? g_dbg_depth : g_dbg[i & 15]; }
+unsigned long long g_dbg_depth, g_dbg_iter_sum, g_dbg_iter_max;
+extern "C" unsigned long long bnd_dbg_counter(int i) { return i == 16 ? g_dbg_depth : i == 17 ? g_dbg_iter_sum : i == 18 ? g_dbg_iter_max : g_dbg[i & 15]; }
 #endif
 
 int inflate_ctas_per_sm() { return kVariants[variant_index()].ctas_per_sm; }

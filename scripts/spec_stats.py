@@ -37,7 +37,7 @@ while buf:
 assert out == ref, "inflate mismatch"
 f = nat.L.bnd_dbg_counter
 f.restype = ctypes.c_ulonglong
-c = [f(i) for i in range(17)]
+c = [f(i) for i in range(19)]
 print(f"blocks {len(st)}  inflated {len(out)} B  compressed {len(data)} B")
 print(f"rounds {c[0]}  matches/round {c[4] / max(c[0], 1):.1f}")
 print(f"fix-up iterations/round {c[1] / max(c[0], 1):.2f}  lanes re-decoded/round {c[2] / max(c[0], 1):.2f}  dropped lanes/round {c[3] / max(c[0], 1):.2f}")
@@ -49,3 +49,5 @@ if c[12]:
           f"{c[14] / max(c[0], 1):.2f} lanes per round never meet it inside the span")
 print(f"waves per round: {c[5] / max(c[0], 1):.1f} in batches of 32, {c[15] / max(c[0], 1):.1f} if a whole round were resolved at once")
 print(f"exact dependency depth of a round's matches (a match waits only for matches whose output its source overlaps): {c[16] / max(c[0], 1):.1f}")
+print(f"pass 1: {c[17] / max(c[0], 1) / 32:.1f} tokens per lane on average, {c[18] / max(c[0], 1):.1f} on the slowest lane of a round "
+      f"(a pass lasts as long as its slowest lane: {c[18] / max(c[17] / 32, 1):.2f}x the mean)")
