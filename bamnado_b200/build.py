@@ -54,7 +54,6 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         jobs.append((cmd, o))
     for src in HOST_SOURCES:
         o = obj_dir / (src + ".o")
-        cmd = [nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-pthread", "-x", "cu", *NVCC_ARCH, "-c", str(CSRC / src), "-o", str(o)]
         # host files hold no device code; plain g++ with the CUDA include path is enough and much faster
         cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-pthread", "-I", "/usr/local/cuda/include", "-c", str(CSRC / src), "-o", str(o)]
         jobs.append((cmd, o))
@@ -83,8 +82,6 @@ def build_emul(force: bool = False) -> Path:
         return EMUL_LIB
     EMUL_LIB.parent.mkdir(parents=True, exist_ok=True)
     common = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-pthread", "-DBND_EMUL", "-I", str(EMUL_DIR), "-I", str(CSRC), "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function"]
-    if os.environ.get("BND_EMUL_STATS"):
-        common.append("-DBND_EMUL_STATS")  # walk statistics of the inflate kernels (scripts/spec_stats.py)
     objs, procs = [], []
     for src in DEVICE_SOURCES + HOST_SOURCES:
         o = EMUL_LIB.parent / (src + ".o")

@@ -167,6 +167,23 @@ struct StageSlot {
   }
 };
 
+struct PinnedBounce {  // pinned bounce buffers for device -> host text, one pair per device context
+  static constexpr int N = 2;
+  uint8_t *buf[N] = {nullptr, nullptr};
+  size_t cap = 0;
+  cudaEvent_t ev[N] = {nullptr, nullptr};
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    for (int i = 0; i < N; i++) {
+      if (buf[i]) CU(cudaFreeHost(buf[i]));
+      buf[i] = nullptr;
+      CU(cudaHostAlloc((void **)&buf[i], n, cudaHostAllocDefault));
+      if (!ev[i]) CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    cap = n;
+  }
+};
+
 }  // namespace
 
 struct DeviceCtx {
@@ -178,6 +195,7 @@ struct DeviceCtx {
   std::vector<StageSlot> slots;
   uint64_t seg_bytes = 0, carry_cap = 0;
   int n_readers = 4;
+  PinnedBounce bounce;  // created on this context's device, used under `mu`
   std::mutex mu;  // one pass at a time per device context
 };
 
@@ -961,7 +979,8 @@ void Pileup::run_pass(const Range &range, bool resident) {
     fprintf(stderr, "[bnd] pass: %zu segments, wall %.2f ms, waited on readers %.2f ms, on staging reuse %.2f ms, final sync %.2f ms\n", segs.size(),
             tm_.wall_ms, dbg_wait_read, dbg_wait_h2d, dbg_sync);
   shape_.launches = launch_count() - launches0;
-  accumulated_ = true;
+  // the accumulators now hold `range`; only a pass over the shard's own range feeds the whole-object outputs
+  accumulated_ = range.chunk_lo == shard_.chunk_lo && range.chunk_hi == shard_.chunk_hi && range.byte_begin == shard_.byte_begin;
 }
 
 void Pileup::accumulate() { run_pass(shard_, false); }
@@ -1026,6 +1045,8 @@ void Pileup::stats(uint64_t out[ST_N_COUNTERS]) const {
 
 double Pileup::norm_factor() const {
   // NormalizationMethod::scale_factor (signal_normalization.rs:50-74) over n_reads_after_filtering (read_filter.rs:229-243)
+  if (cfg_.shard_world > 1 && cfg_.norm_method != 0 && !total_stats_set_)
+    fail("sharded pile-up: CPM/RPKM needs the job-wide filter counters (bnd_pileup_set_total_stats) before normalising", ERR_INVALID);
   uint64_t failed = 0;
   for (int k = 1; k < ST_N_COUNTERS; k++) failed += stats_[k];
   return bnd_scale_factor(cfg_.norm_method, cfg_.scale_factor, cfg_.bin_size, stats_[0] - failed);
@@ -1141,6 +1162,9 @@ void Pileup::chromosome(const std::string &chrom, std::vector<RunRow> &out) {
   run_pass(range, false);
   finalize_range(false);
   fetch_rows(out);
+  // the bin array, counters and rows now describe this contig only: a later whole-object call starts over
+  // (pileup_chromosome does not change what to_bedgraph writes, coverage_analysis.rs:337-430)
+  accumulated_ = finalized_ = false;
 }
 
 void Pileup::signal(const std::string &chrom, std::vector<float> &out) {
@@ -1162,6 +1186,7 @@ void Pileup::signal(const std::string &chrom, std::vector<float> &out) {
   }
   im.pdev = saved;
   finalize_range(true);
+  accumulated_ = finalized_ = false;  // single-contig state, see chromosome()
   DeviceCtx &ctx = *im.ctx;
   std::lock_guard<std::mutex> lock(ctx.mu);
   const uint64_t n = hdr_.lens[r];
@@ -1569,23 +1594,6 @@ struct TextPiece {
   uint64_t out_off;             // where it goes in the output
 };
 
-struct PinnedBounce {  // process-wide pinned bounce buffers for device -> host text
-  static constexpr int N = 2;
-  uint8_t *buf[N] = {nullptr, nullptr};
-  size_t cap = 0;
-  cudaEvent_t ev[N] = {nullptr, nullptr};
-  void ensure(size_t n) {
-    if (n <= cap) return;
-    for (int i = 0; i < N; i++) {
-      if (buf[i]) CU(cudaFreeHost(buf[i]));
-      buf[i] = nullptr;
-      CU(cudaHostAlloc((void **)&buf[i], n, cudaHostAllocDefault));
-      if (!ev[i]) CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-    }
-    cap = n;
-  }
-};
-PinnedBounce g_bounce;
 
 // copies [a, b) of the device text, as seen through `pieces`, to its destinations via `sink(src, len, out_off)`
 template <class Sink>
@@ -1715,7 +1723,7 @@ template <class Sink>
 static void drain_text(DeviceCtx &ctx, const uint8_t *d_text, uint64_t nbytes, const std::vector<TextPiece> &pieces, int n_threads, Sink sink) {
   if (nbytes == 0) return;
   const uint64_t CH = std::min<uint64_t>(env_u64("BND_TEXT_CHUNK_BYTES", 64ull << 20), nbytes);
-  g_bounce.ensure(CH);
+  ctx.bounce.ensure(CH);
   cudaStream_t st = ctx.sets[0].stream;
   const uint64_t n_chunks = (nbytes + CH - 1) / CH;
   // worker pool consuming (chunk, sub-range) tasks
@@ -1748,7 +1756,7 @@ static void drain_text(DeviceCtx &ctx, const uint8_t *d_text, uint64_t nbytes, c
       {
         std::lock_guard<std::mutex> g(mu);
         for (int i = 0; i < PinnedBounce::N; i++)
-          if (t.src >= g_bounce.buf[i] && t.src < g_bounce.buf[i] + g_bounce.cap) outstanding[i]--;
+          if (t.src >= ctx.bounce.buf[i] && t.src < ctx.bounce.buf[i] + ctx.bounce.cap) outstanding[i]--;
       }
       cv_done.notify_all();
     }
@@ -1772,18 +1780,18 @@ static void drain_text(DeviceCtx &ctx, const uint8_t *d_text, uint64_t nbytes, c
           cv_done.wait(g, [&] { return outstanding[b] == 0; });
         }
         const uint64_t a0 = k * CH, a1 = std::min(nbytes, a0 + CH);
-        CU(cudaMemcpyAsync(g_bounce.buf[b], d_text + a0, a1 - a0, cudaMemcpyDeviceToHost, st));
-        CU(cudaEventRecord(g_bounce.ev[b], st));
+        CU(cudaMemcpyAsync(ctx.bounce.buf[b], d_text + a0, a1 - a0, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ctx.bounce.ev[b], st));
       }
       if (k > 0) {  // hand the previous chunk to the workers while this one is in flight
         const uint64_t j = k - 1;
         const int b = (int)(j % PinnedBounce::N);
-        CU(cudaEventSynchronize(g_bounce.ev[b]));
+        CU(cudaEventSynchronize(ctx.bounce.ev[b]));
         const uint64_t a0 = j * CH, a1 = std::min(nbytes, a0 + CH);
         const uint64_t SUB = 4ull << 20;
         std::lock_guard<std::mutex> g(mu);
         for (uint64_t x = a0; x < a1; x += SUB) {
-          q.push_back(Task{g_bounce.buf[b] + (x - a0), x, std::min(a1, x + SUB)});
+          q.push_back(Task{ctx.bounce.buf[b] + (x - a0), x, std::min(a1, x + SUB)});
           outstanding[b]++;
         }
         cv.notify_all();
@@ -1903,7 +1911,9 @@ void Pileup::to_bedgraph(const std::string &path) {
     for (const TextPiece &pc : job.pieces) out_bytes = std::max(out_bytes, pc.out_off + (pc.dev_end - pc.dev_begin));
     // regular files: the writer threads memcpy into a shared mapping (parallel page-cache fills; pwrite would
     // serialise on the inode lock); anything unmappable falls back to positional writes
-    if (out_bytes && (prealloc >= out_bytes || ftruncate(fd, (off_t)out_bytes) == 0)) {
+    // every byte the writers will touch must be backed before it is mapped: a store into a hole of a sparse file
+    // raises SIGBUS when the file system is full, which would take the host process down instead of returning an error
+    if (out_bytes && (prealloc >= out_bytes || posix_fallocate(fd, (off_t)prealloc, (off_t)(out_bytes - prealloc)) == 0)) {
       void *m = mmap(nullptr, out_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
       if (m != MAP_FAILED) map = (char *)m;
     }

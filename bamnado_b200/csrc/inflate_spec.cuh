@@ -180,16 +180,6 @@ __device__ bool build_dist_tables(const Tile<32> &tile, Smem &S) {
   return true;
 }
 
-#ifdef BND_EMUL_STATS
-}  // namespace bnd
-#include <vector>
-namespace bnd {
-// statistics build only (scripts/spec_stats.py): where a decode pass saw token boundaries, to measure how many bits a lane
-// restarted at its true position needs before it is back on the path of its speculative pass
-static thread_local std::vector<uint32_t> *g_dbg_path = nullptr;
-static thread_local uint32_t g_dbg_iters = 0;  // loop iterations of the last span_decode call on this host thread
-extern unsigned long long g_dbg_depth, g_dbg_iter_sum, g_dbg_iter_max;
-#endif
 
 // Decode tokens from bit `start` until the position reaches `limit` (> start), an end-of-block code or an undecodable
 // code.  Bits are addressed from the first bit of the staged words.  Returns {bit position after the last token |
@@ -207,15 +197,8 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
   wa += 12;
   int32_t remain = (int32_t)(limit - start);
   uint32_t nm = 0, bytes = 0, flag = SPAN_OK;
-#ifdef BND_EMUL_STATS
-  uint32_t n_iter_dbg = 1;
-#endif
 #pragma unroll 1
   do {
-#ifdef BND_EMUL_STATS
-    if (g_dbg_path) g_dbg_path->push_back((uint32_t)((int32_t)limit - remain));  // bit position of this token's first bit
-    g_dbg_iters = n_iter_dbg++;
-#endif
     const uint32_t w = __funnelshift_r(lo, hi, pos);
     uint32_t e = lds_u16(lit0 + 2 * (w & ((1u << LIT_BITS) - 1u)));
     if ((e & 31u) == 0)  // second level (or the reserved zero entry)
@@ -290,12 +273,6 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
   return make_uint2((uint32_t)((int32_t)limit - remain) | (flag << 24), nm | (bytes << 12));
 }
 
-#ifdef BND_EMUL_STATS
-extern unsigned long long g_dbg[16];
-#define BND_STAT(i, v) __atomic_fetch_add(&g_dbg[i], (unsigned long long)(v), __ATOMIC_RELAXED)
-#else
-#define BND_STAT(i, v) ((void)0)
-#endif
 
 // Inflate one BGZF block with one warp.  Returns a status code (same on every lane).
 template <class Smem>
@@ -423,23 +400,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
           cnt = 0;
         }
       };
-#ifdef BND_EMUL_STATS
-      std::vector<uint32_t> dbg_p1, dbg_p2;
-      g_dbg_path = &dbg_p1;
-#endif
       scan();
-#ifdef BND_EMUL_STATS
-      g_dbg_path = nullptr;
-      int dbg_iter = 0;
-      {
-        const uint32_t it = start < end_bit ? g_dbg_iters : 0u;  // pass 1: iterations of this lane
-        uint32_t mx = it;
-        for (int d = 16; d >= 1; d >>= 1) mx = tmax(mx, tile.shfl_xor(mx, d));
-        __atomic_fetch_add(&g_dbg_iter_sum, (unsigned long long)it, __ATOMIC_RELAXED);
-        if (lane == 0) __atomic_fetch_add(&g_dbg_iter_max, (unsigned long long)mx, __ATOMIC_RELAXED);
-      }
-#endif
-      BND_STAT(0, lane == 0);
       // ---- fix-up: restart from the predecessor's exit until every live lane starts where its predecessor stopped ----
       int first_term;
       for (;;) {
@@ -449,46 +410,10 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
         first_term = term ? __ffs((int)term) - 1 : 32;
         const bool need = lane <= first_term && want != start;
         if (tile.ballot(need) == 0) break;
-        BND_STAT(1, lane == 0);
-        BND_STAT(2, need);
         if (need) {
           start = want;
-#ifdef BND_EMUL_STATS
-          if (dbg_iter == 0) {
-            dbg_p2.clear();
-            g_dbg_path = &dbg_p2;
-          }
-#endif
           scan();
-#ifdef BND_EMUL_STATS
-          g_dbg_path = nullptr;
-#endif
         }
-#ifdef BND_EMUL_STATS
-        if (dbg_iter == 0) {
-          // bits from the true start to the first token boundary shared with the speculative pass (whole span if none)
-          uint32_t sync = 0, span_len = 0;
-          if (need && start < end_bit) {
-            span_len = limit - start;
-            sync = span_len;
-            size_t i = 0;
-            for (uint32_t p : dbg_p2) {
-              while (i < dbg_p1.size() && dbg_p1[i] < p) i++;
-              if (i < dbg_p1.size() && dbg_p1[i] == p) {
-                sync = p - (start - sbit0);
-                break;
-              }
-            }
-          }
-          uint32_t mx = sync;
-          for (int d = 16; d >= 1; d >>= 1) mx = tmax(mx, tile.shfl_xor(mx, d));
-          BND_STAT(11, sync);
-          BND_STAT(12, span_len);
-          BND_STAT(13, lane == 0 ? mx : 0);
-          BND_STAT(14, need && sync == span_len && span_len > 0);
-        }
-        dbg_iter++;
-#endif
       }
       // ---- place: lanes 0..first_term hold true tokens; take as many whole lanes as the match list holds ----
       const int nvalid = first_term < 32 ? first_term + 1 : 32;
@@ -504,7 +429,6 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
       }
       const bool taken = lane < nvalid && minc <= (uint32_t)NM;
       const int m = __popc(tile.ballot(taken));  // >= 1: one span never holds more than NM matches
-      BND_STAT(3, lane == 0 ? nvalid - m : 0);
       const uint32_t total = tile.shfl(binc, m - 1), nmatch = tile.shfl(minc, m - 1);
       if (outpos + total > isize) {
         status = INF_OUTPUT_OVERRUN;
@@ -529,51 +453,16 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
         status = INF_INPUT_OVERRUN;
         break;
       }
-      BND_STAT(4, lane == 0 ? nmatch : 0);
       tile.sync();  // literals and the match list are visible to the whole warp; nobody reads the staged words any more
       staged = !eob && p0 < end_bit;
       if (staged) stage_issue(p0);  // the next round's input arrives while this round's matches are resolved
       // ---- resolve the matches, 32 at a time: lane t owns match mb + t ----
-#ifdef BND_EMUL_STATS
-      if (lane == 0) {  // waves a whole-round resolution would need (same frontier rule, no batches of 32)
-        std::vector<uint8_t> done(nmatch, 0);
-        uint32_t first = 0, waves = 0;
-        while (first < nmatch) {
-          const uint32_t frontier = S.matches[first].x & 0xffffu;
-          bool any = false;
-          for (uint32_t k = first; k < nmatch; k++) {
-            if (done[k]) continue;
-            const uint2 e = S.matches[k];
-            const uint32_t p = e.x & 0xffffu, len = (e.x >> 16) + 3u;
-            if (p - e.y + len <= frontier) done[k] = 1, any = true;
-          }
-          if (!any) done[first] = 1;
-          waves++;
-          while (first < nmatch && done[first]) first++;
-        }
-        BND_STAT(15, waves);
-        // exact dependency depth: a match waits only for the matches whose output its source overlaps
-        std::vector<uint32_t> depth(nmatch, 1);
-        uint32_t deepest = 0;
-        for (uint32_t k = 0; k < nmatch; k++) {
-          const uint2 e = S.matches[k];
-          const uint32_t p = e.x & 0xffffu, len = (e.x >> 16) + 3u, s0 = p - e.y, s1 = s0 + len;
-          for (uint32_t j = 0; j < k; j++) {
-            const uint32_t pj = S.matches[j].x & 0xffffu, lj = (S.matches[j].x >> 16) + 3u;
-            if (pj < s1 && pj + lj > s0) depth[k] = tmax(depth[k], depth[j] + 1);
-          }
-          deepest = tmax(deepest, depth[k]);
-        }
-        __atomic_fetch_add(&g_dbg_depth, (unsigned long long)deepest, __ATOMIC_RELAXED);
-      }
-#endif
       for (uint32_t mb = 0; mb < nmatch; mb += 32) {
         const bool mine = mb + (uint32_t)lane < nmatch;
         const uint2 me = mine ? S.matches[mb + lane] : make_uint2(0u, 1u);
         const uint32_t mypos = me.x & 0xffffu, length = (me.x >> 16) + 3u, dist = me.y;
         const uint32_t src_end = mypos - dist + length;
         uint32_t pend = tile.ballot(mine);
-        BND_STAT(6, lane == 0);
         // Everything before the first unfinished match is final (literals were stored by the store pass), so every
         // match whose source ends there can be copied now, all of them at once; the first unfinished one itself always
         // can (its source precedes it, or it repeats its own first bytes).  Usually one or two waves empty the batch.
@@ -583,9 +472,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
           const uint32_t frontier = tile.shfl(mypos, fl);
           const bool ready = ((pend >> lane) & 1u) != 0 && src_end <= frontier;
           const uint32_t rmask = tile.ballot(ready);
-          BND_STAT(5, lane == 0);
           if (rmask == 0) {
-            BND_STAT(7, lane == 0);
             // the first unfinished match overlaps its own output: period `dist` < length, copied by the whole warp
             const uint32_t len = tile.shfl(length, fl), dd = tile.shfl(dist, fl);
             const uint8_t *src = out + frontier - dd;
@@ -658,13 +545,10 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
               if ((uint32_t)lane + 32u < wlen[k]) dst[lane + 32] = wb[k];
             }
           }
-          BND_STAT(9, lane == 0 ? __builtin_popcount(rmask) : 0);
-          BND_STAT(10, lane == 0 ? __builtin_popcount(wide0) : 0);
 #pragma unroll 1
           while (wide) {  // ready, disjoint from their source, not yet copied: more than three or longer than 64 bytes
             const int sl = __ffs((int)wide) - 1;
             wide &= wide - 1;
-            BND_STAT(8, lane == 0);
             const uint32_t len = tile.shfl(length, sl), mp = tile.shfl(mypos, sl);
             const uint8_t *src = out + mp - tile.shfl(dist, sl);
             uint8_t *dst = out + mp;

@@ -13,7 +13,6 @@
 
 #include "collapse.cuh"
 #include "finalize.cuh"
-#include "inflate.cuh"
 #include "inflate_spec.cuh"
 #include "pileup.cuh"
 #include "records.cuh"
@@ -37,37 +36,20 @@ inline unsigned grid_for(uint64_t items, uint64_t per_cta, uint64_t cap) {
 unsigned long long launch_count() { return g_launches.load(); }
 
 namespace {
-struct InflateVariant {
-  int g, threads, ctas_per_sm;
+// K1 shapes: CTA size / resident CTAs per SM / root table bits / span bits / match-list length.  One shape ships; the
+// others exist for the tests (a short match list forces rounds that cannot take all 32 lanes) and for A/B timing.
+struct InflateShape {
+  int threads, ctas_per_sm;
 };
-// lane-group width / CTA size / resident CTAs per SM (and LUT widths below); selected with BND_INFLATE_VARIANT
-const InflateVariant kVariants[] = {{32, 256, 5}, {32, 128, 9}, {32, 128, 12}, {32, 256, 6}, {32, 256, 4}, {32, 128, 8},
-                                    // 6..: speculative 32-lane walk (inflate_spec.cuh)
-                                    {32, 256, 3}, {32, 128, 5}, {32, 256, 2}, {32, 192, 4}, {32, 224, 4}, {32, 256, 4}, {32, 320, 3}, {32, 192, 5}, {32, 160, 6}, {32, 320, 3}, {32, 320, 3}};
-constexpr int kDefaultVariant = 12;  // speculative walk, 320 threads x 3 CTAs / SM = 30 warps, 9-bit root table (profiles/r1_sweeps.md)
-int variant_index() {
+const InflateShape kShapes[] = {{320, 3}, {320, 3}, {256, 4}};
+int shape_index() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("BND_INFLATE_VARIANT");
-    v = e ? atoi(e) : kDefaultVariant;
-    if (v < 0 || v >= (int)(sizeof(kVariants) / sizeof(kVariants[0]))) v = kDefaultVariant;
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v >= (int)(sizeof(kShapes) / sizeof(kShapes[0]))) v = 0;
   }
   return v;
-}
-template <int G, int T, int MINB, int LB, int DB>
-cudaError_t launch_inflate_t(const InflateArgs &a, int sm_count, int ctas_per_sm, cudaStream_t s) {
-  auto kern = bgzf_inflate_kernel<G, T, MINB, LB, DB>;
-  constexpr int groups = T / G;
-  const size_t smem = inflate_smem_bytes<LB, DB>(groups);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  unsigned grid = grid_for(a.n_blocks, groups, (uint64_t)sm_count * ctas_per_sm);
-  BND_LAUNCH(kern, dim3(grid), dim3(T), smem, s, a);
-  return launched();
 }
 template <int T, int MINB, int LB, int DB, int SPAN, int NT>
 cudaError_t launch_inflate_spec_t(const InflateArgs &a, int sm_count, int ctas_per_sm, cudaStream_t s) {
@@ -86,51 +68,30 @@ cudaError_t launch_inflate_spec_t(const InflateArgs &a, int sm_count, int ctas_p
 }
 }  // namespace
 
-#ifdef BND_EMUL_STATS
-unsigned long long g_dbg[16];
-unsigned long long g_dbg_depth, g_dbg_iter_sum, g_dbg_iter_max;
-extern "C" unsigned long long bnd_dbg_counter(int i) { return i == 16 ? g_dbg_depth : i == 17 ? g_dbg_iter_sum : i == 18 ? g_dbg_iter_max : g_dbg[i & 15]; }
-#endif
-
-int inflate_ctas_per_sm() { return kVariants[variant_index()].ctas_per_sm; }
+int inflate_ctas_per_sm() { return kShapes[shape_index()].ctas_per_sm; }
 
 void make_crc_tables(CrcTables *T) {
-  const int G = kVariants[variant_index()].g;
   for (uint32_t i = 0; i < 256; i++) {
     uint32_t c = i;
     for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
     T->t[i] = c;
   }
-  // z[b][x]: the CRC register value (x << 8b) advanced over 32*G zero bits (= 4*G zero bytes)
+  // z[b][x]: the CRC register value (x << 8b) advanced over 32 words of zero bits (one word per lane of the warp)
   for (int b = 0; b < 4; b++)
     for (uint32_t x = 0; x < 256; x++) {
       uint32_t c = x << (8 * b);
-      for (int k = 0; k < 4 * G; k++) c = T->t[c & 0xff] ^ (c >> 8);
+      for (int k = 0; k < 4 * 32; k++) c = T->t[c & 0xff] ^ (c >> 8);
       T->z[b][x] = c;
     }
 }
 
 cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_blocks == 0) return cudaSuccess;
-  const InflateVariant &v = kVariants[variant_index()];
-  switch (variant_index()) {
-    case 1: return launch_inflate_t<32, 128, 9, 10, 8>(a, sm_count, v.ctas_per_sm, s);
-    case 2: return launch_inflate_t<32, 128, 12, 9, 7>(a, sm_count, v.ctas_per_sm, s);  // 48 warps / SM, <= 40 registers
-    case 3: return launch_inflate_t<32, 256, 6, 9, 7>(a, sm_count, v.ctas_per_sm, s);
-    case 4: return launch_inflate_t<32, 256, 4, 10, 8>(a, sm_count, v.ctas_per_sm, s);  // 32 warps / SM, <= 64 registers
-    case 5: return launch_inflate_t<32, 128, 8, 10, 8>(a, sm_count, v.ctas_per_sm, s);
-    case 7: return launch_inflate_spec_t<128, 5, 10, 8, 256, 512>(a, sm_count, v.ctas_per_sm, s);
-    case 8: return launch_inflate_spec_t<256, 2, 11, 8, 256, 512>(a, sm_count, v.ctas_per_sm, s);
-    case 9: return launch_inflate_spec_t<192, 4, 10, 8, 192, 384>(a, sm_count, v.ctas_per_sm, s);
-    case 10: return launch_inflate_spec_t<224, 4, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // 28 warps / SM
-    case 11: return launch_inflate_spec_t<256, 4, 9, 8, 256, 256>(a, sm_count, v.ctas_per_sm, s);  // 32 warps / SM, 64 registers
-    case 6: return launch_inflate_spec_t<256, 3, 10, 8, 256, 512>(a, sm_count, v.ctas_per_sm, s);
-    case 13: return launch_inflate_spec_t<192, 5, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // smaller CTAs leave the SM sooner in a launch's tail
-    case 14: return launch_inflate_spec_t<160, 6, 9, 8, 256, 320>(a, sm_count, v.ctas_per_sm, s);
-    case 15: return launch_inflate_spec_t<320, 3, 9, 8, 320, 384>(a, sm_count, v.ctas_per_sm, s);  // longer spans: fewer rounds and fix-ups
-    case 16: return launch_inflate_spec_t<320, 3, 9, 8, 288, 384>(a, sm_count, v.ctas_per_sm, s);
-    case 0: return launch_inflate_t<32, 256, 5, 10, 8>(a, sm_count, v.ctas_per_sm, s);  // single-lane walk (round-1 v10)
-    default: return launch_inflate_spec_t<320, 3, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM, 64 registers
+  const InflateShape &v = kShapes[shape_index()];
+  switch (shape_index()) {
+    case 1: return launch_inflate_spec_t<320, 3, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // round-1 shape: 256-bit spans
+    case 2: return launch_inflate_spec_t<256, 4, 9, 8, 256, 256>(a, sm_count, v.ctas_per_sm, s);  // short match list (tests)
+    default: return launch_inflate_spec_t<320, 3, 9, 8, 320, 384>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM, 320-bit spans
   }
 }
 

@@ -219,11 +219,17 @@ void pileup_to_bigwig(Pileup &p, const std::string &path) {
   const bool skip_scaffold = p.config().ignore_scaffold != 0;
   const size_t n_ref = h.names.size();
   std::vector<uint8_t> keep(n_ref, 1);
+  // chromosome ids are dense (0 .. kept - 1, header order): readers such as libBigWig index arrays of `itemCount`
+  // entries by id, so the BAM reference index cannot be used once references are dropped
+  std::vector<uint32_t> dense(n_ref, 0);
   std::vector<std::tuple<std::string, uint32_t, uint32_t>> chroms;
   for (size_t r = 0; r < n_ref; r++) {
     if (skip_scaffold && is_scaffold(h.names[r])) keep[r] = 0;
     if (h.lens[r] > 0xffffffffull) fail("chromosome too long for BigWig");
-    if (keep[r]) chroms.emplace_back(h.names[r], (uint32_t)r, (uint32_t)h.lens[r]);
+    if (keep[r]) {
+      dense[r] = (uint32_t)chroms.size();
+      chroms.emplace_back(h.names[r], dense[r], (uint32_t)h.lens[r]);
+    }
   }
   Buf b;
   b.pad_to(64 + MAX_ZOOM * 24 + 40);  // header, zoom headers, total summary: filled at the end
@@ -250,7 +256,7 @@ void pileup_to_bigwig(Pileup &p, const std::string &path) {
       for (size_t s0 = i; s0 < j; s0 += ITEMS_PER_SLOT) {
         const size_t s1 = std::min(j, s0 + ITEMS_PER_SLOT);
         Section sec;
-        sec.chrom = (uint32_t)ref;
+        sec.chrom = dense[ref];
         sec.offset = b.d.size();
         if (rows[s0].start == 0 || rows[s1 - 1].stop - 1 > 0xffffffffull) fail("interval out of range for BigWig");
         sec.start = (uint32_t)(rows[s0].start - 1);
@@ -263,7 +269,7 @@ void pileup_to_bigwig(Pileup &p, const std::string &path) {
           const uint32_t st = (uint32_t)(rows[k].start - 1), en = (uint32_t)(rows[k].stop - 1);
           const float v = (float)((double)rows[k].val * factor);
           b.u32(st), b.u32(en), b.f32(v);
-          items.push_back(Item{(uint32_t)ref, st, en, v});
+          items.push_back(Item{dense[ref], st, en, v});
           const double w = (double)(en - st), dv = (double)v;
           covered += en - st;
           sum += dv * w;

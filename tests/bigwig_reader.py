@@ -30,6 +30,9 @@ def read_bigwig(path):
     if n_items:
         walk_chrom(chrom_off + 32, key_size)
 
+    # libBigWig (pyBigWig, deepTools) indexes arrays of `n_items` entries by chromosome id: ids must be dense
+    assert sorted(cid for cid, _ in chroms.values()) == list(range(len(chroms))), "chromosome ids are not dense"
+
     leaves = []
 
     def walk_r(off):
@@ -69,6 +72,7 @@ def read_bigwig(path):
                 s = cstart + i * step
                 e = s + span
                 p += 4
+            assert cid < len(chroms), "section refers to a chromosome id outside the tree"
             intervals.append((cid, s, e, v))
     summary = None
     if summ_off:

@@ -172,7 +172,33 @@ def test_record_discovery_survives_fake_record_chains(backend, oracle, tmp_path,
     runs, stats = same(backend, oracle, dict(bam_path=str(bam), bin_size=100), dict())
     assert stats["n_total"] == len(pos)
     # independent check of the pile-up itself: every record covers [pos + 1, pos + 51)
-    cov = np.zeros(400001, np.int64)
-    np.add.at(cov, pos + 1, 1)
-    np.add.at(cov, pos + 51, -1)
+    # (1-based half-open), and a bin [a, b) counts #{start < b} - #{stop <= a} (Lapper::count, bam_utils.rs:59); a run's
+    # value is the count of its first bin
+    starts, stops = np.sort(pos + 1), np.sort(pos + 51)
+    a = runs["start"].astype(np.int64)
+    b = np.minimum(a + 100, runs["stop"].astype(np.int64))
+    expect = np.searchsorted(starts, b, side="left") - np.searchsorted(stops, a, side="right")
+    assert (runs["val"].astype(np.int64) == expect).all()
     assert runs["val"].max() > 0 and int((runs["val"].astype(np.int64) > 0).sum()) > 100
+
+
+def test_chromosome_query_leaves_whole_object_outputs_alone(backend, oracle, tmp_path, make_bam):
+    # pileup_chromosome (coverage_analysis.rs:337-430) does not change what a later to_bedgraph writes: the handle must not
+    # keep the single-contig accumulators as if they were the whole result
+    bam = make_bam("pe", "--pairs", 20000, "--odd")
+    pile, filt = dict(bam_path=bam, bin_size=50, norm="cpm"), CLI_FILTER
+    ref_out = tmp_path / "oracle.bdg"
+    ostats, _ = oracle.pileup_to_bedgraph(pile, filt, ref_out)
+    with backend.pileup(pile, filt) as h:  # contig query first, whole output afterwards
+        c2 = h.chromosome("chr2")
+        assert len(c2) > 0 and (c2["ref_id"] == c2["ref_id"][0]).all()
+        out = tmp_path / "after_query.bdg"
+        h.to_bedgraph(out)
+        assert h.stats() == ostats
+        assert out.read_bytes() == ref_out.read_bytes()
+    with backend.pileup(pile, filt) as h:  # whole result, contig query, whole result again
+        whole = h.bedgraph_text()
+        sig = h.chromosome("chr3")
+        assert len(sig) > 0
+        assert h.bedgraph_text() == whole == ref_out.read_bytes()
+        assert h.stats() == ostats

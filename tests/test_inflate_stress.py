@@ -132,11 +132,10 @@ def test_spec_inflate_zoo_on_gpu_many_copies(native_gpu):
     assert out == b"".join(expected)
 
 
-@pytest.mark.parametrize("variant", ["0", "6", "11", "15"])
+@pytest.mark.parametrize("variant", ["1", "2"])
 def test_other_kernel_shapes_stay_correct(variant, tmp_path):
-    # BND_INFLATE_VARIANT is read once per process: the single-lane kernel (0), the 10-bit-root shape (6) and the
-    # 256-entry match list (11: lanes are dropped whenever a round holds more matches) and 320-bit spans (15) run the zoo in a child process
-    # against the CPU emulator build
+    # BND_INFLATE_VARIANT is read once per process: 256-bit spans (1) and the 256-entry match list (2: lanes are dropped
+    # whenever a round holds more matches) run the zoo in a child process against the CPU emulator build
     import subprocess
     import sys
     from pathlib import Path

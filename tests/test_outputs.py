@@ -71,11 +71,14 @@ def test_bigwig_ignore_scaffold_and_large(backend, oracle, tmp_path, make_bam):
     pile, filt = dict(bam_path=bam, bin_size=50, norm="rpkm", ignore_scaffold=True), CLI_FILTER
     with backend.pileup(pile, filt) as h:
         h.to_bigwig(out)
+        names, _ = h.refs()
     bw = read_bigwig(out)
     assert all(not (n.startswith("chrUn") or n.endswith("_alt") or n.endswith("_random")) for n in bw["chroms"])
     runs, _, factor = oracle.pileup_runs(pile, filt)
-    keep = {cid for _, (cid, _) in bw["chroms"].items()}
-    exp = [(int(r["ref_id"]), int(r["start"]) - 1, int(r["stop"]) - 1, float(np.float32(float(r["val"]) * factor))) for r in runs if int(r["ref_id"]) in keep]
+    # chromosome ids in the file are dense over the kept references (header order), not BAM reference indexes
+    cid_of_ref = {r: bw["chroms"][n][0] for r, n in enumerate(names) if n in bw["chroms"]}
+    assert len(cid_of_ref) < len(names)
+    exp = [(cid_of_ref[int(r["ref_id"])], int(r["start"]) - 1, int(r["stop"]) - 1, float(np.float32(float(r["val"]) * factor))) for r in runs if int(r["ref_id"]) in cid_of_ref]
     assert bw["intervals"] == exp
 
 
