@@ -29,7 +29,7 @@ EXPORTS = [
     "bnd_pileup_destroy", "bnd_pileup_to_bedgraph", "bnd_pileup_to_bigwig", "bnd_pileup_chromosome", "bnd_pileup_runs",
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
-    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
+    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_pileup_format_bedgraph", "bnd_pileup_write_bedgraph_pieces", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
     "bnd_multi_change_flags", "bnd_multi_compact", "bnd_pileup_refs", "bnd_collapse_bedgraph",
     "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
 ]
@@ -149,6 +149,8 @@ class Native:
         L.bnd_pileup_bedgraph_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.bnd_pileup_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.bnd_pileup_shape.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.bnd_pileup_format_bedgraph.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64]
+        L.bnd_pileup_write_bedgraph_pieces.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
         L.bnd_signal_for_chromosome.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg), C.c_char_p,
                                                 C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_uint64)]
         L.bnd_multi_to_tsv.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg), C.c_int32, C.c_char_p]
@@ -380,9 +382,23 @@ class PileupHandle:
         return dict(zip(["inflate_ms", "index_ms", "pileup_ms", "finalize_ms", "h2d_ms", "text_ms", "wall_ms", "read_ms"], [float(v) for v in ms]))
 
     def shape(self) -> dict:
-        s = (C.c_uint64 * 8)()
+        s = (C.c_uint64 * 16)()
         self.n.check(self.n.L.bnd_pileup_shape(self.h, s))
-        return dict(zip(["records", "comp_bytes", "inflated_bytes", "blocks", "bins", "launches", "chunk_len", "n_chunks"], [int(v) for v in s]))
+        return dict(zip(["records", "comp_bytes", "inflated_bytes", "blocks", "bins", "launches", "chunk_len", "n_chunks", "segments"], [int(v) for v in s]))
+
+    # ---- sharded jobs, one bedGraph ----
+    def format_bedgraph(self) -> list:
+        """Formats this shard's rows on the device -> text bytes per reference (header order)."""
+        names, _ = self.refs()
+        sizes = (C.c_uint64 * max(len(names), 1))()
+        self.n.check(self.n.L.bnd_pileup_format_bedgraph(self.h, sizes, len(names)))
+        return [int(sizes[i]) for i in range(len(names))]
+
+    def write_bedgraph_pieces(self, path, tables: list, rank: int):
+        """tables[k] = format_bedgraph() of rank k; fills this rank's pieces of the one output file."""
+        world, n_ref = len(tables), len(tables[0])
+        flat = (C.c_uint64 * max(world * n_ref, 1))(*[v for t in tables for v in t])
+        self.n.check(self.n.L.bnd_pileup_write_bedgraph_pieces(self.h, _b(path), flat, world, rank))
 
 
 _native = None

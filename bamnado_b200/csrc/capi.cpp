@@ -128,12 +128,24 @@ int bnd_pileup_timings(bnd_pileup *p, double ms[8]) {
     ms[4] = t.h2d_ms, ms[5] = t.text_ms, ms[6] = t.wall_ms, ms[7] = t.read_ms;
   });
 }
-int bnd_pileup_shape(bnd_pileup *p, uint64_t shape[8]) {
+int bnd_pileup_shape(bnd_pileup *p, uint64_t shape[16]) {
   return guarded([&] {
     const bnd::Shape &s = P(p)->shape();
+    memset(shape, 0, 16 * sizeof(uint64_t));
     shape[0] = s.records, shape[1] = s.comp_bytes, shape[2] = s.inflated_bytes, shape[3] = s.blocks;
-    shape[4] = s.bins, shape[5] = s.launches, shape[6] = s.chunk_len, shape[7] = s.n_chunks;
+    shape[4] = s.bins, shape[5] = s.launches, shape[6] = s.chunk_len, shape[7] = s.n_chunks, shape[8] = s.segments;
   });
+}
+int bnd_pileup_format_bedgraph(bnd_pileup *p, uint64_t *bytes_per_ref, uint64_t n_refs) {
+  return guarded([&] {
+    std::vector<uint64_t> v;
+    P(p)->format_bedgraph(v);
+    if (v.size() != n_refs) bnd::fail("bytes_per_ref must have one entry per reference of the BAM header", bnd::ERR_INVALID);
+    for (size_t i = 0; i < v.size(); i++) bytes_per_ref[i] = v[i];
+  });
+}
+int bnd_pileup_write_bedgraph_pieces(bnd_pileup *p, const char *out_path, const uint64_t *bytes_all, int32_t world, int32_t rank) {
+  return guarded([&] { P(p)->write_bedgraph_pieces(out_path, bytes_all, world, rank); });
 }
 
 int bnd_signal_for_chromosome(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter, const char *chrom, float **signal,

@@ -360,6 +360,24 @@ struct ReaderPool {
 
 }  // namespace
 
+// bedGraph text of one shard: formatted on the device in header order; `pieces` say where each reference's rows go
+namespace {
+struct TextPiece {
+  uint64_t dev_begin, dev_end;  // byte range inside the device text
+  uint64_t out_off;             // where it goes in the output
+};
+}  // namespace
+
+struct Pileup::TextJob {
+  DevBuf d_names, d_name_off, d_skip, d_scores, d_row_len, d_tile_off, d_text, d_ref_off;
+  uint64_t nbytes = 0;
+  std::vector<std::pair<uint64_t, uint64_t>> span;  // per reference: [begin, end) of its rows inside the device text
+  std::vector<TextPiece> pieces;                    // where those spans go in the output, sorted by dev_begin
+  ~TextJob() {
+    for (DevBuf *b : {&d_names, &d_name_off, &d_skip, &d_scores, &d_row_len, &d_tile_off, &d_text, &d_ref_off}) b->release();
+  }
+};
+
 // ---- Pileup::Impl: device state of one pileup ------------------------------------------------------------------------
 struct Pileup::Impl {
   DeviceCtx *ctx = nullptr;
@@ -378,6 +396,8 @@ struct Pileup::Impl {
   uint64_t n_runs = 0;
   uint32_t max_val = 0;
   uint64_t fin_bins = 0;
+  // device text between format_bedgraph and write_bedgraph_pieces
+  std::unique_ptr<Pileup::TextJob> text_job;
   // resident copy of the shard's compressed bytes
   DevBuf d_resident;
   std::vector<Segment> res_segs;
@@ -979,6 +999,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
     fprintf(stderr, "[bnd] pass: %zu segments, wall %.2f ms, waited on readers %.2f ms, on staging reuse %.2f ms, final sync %.2f ms\n", segs.size(),
             tm_.wall_ms, dbg_wait_read, dbg_wait_h2d, dbg_sync);
   shape_.launches = launch_count() - launches0;
+  shape_.segments = segs.size();
   // the accumulators now hold `range`; only a pass over the shard's own range feeds the whole-object outputs
   accumulated_ = range.chunk_lo == shard_.chunk_lo && range.chunk_hi == shard_.chunk_hi && range.byte_begin == shard_.byte_begin;
 }
@@ -1589,10 +1610,6 @@ void collapse_rows_device(const BdgRows &in, BdgRows &out, int device) {
 // The rows are formatted on the device in header order; write_bedgraph's (chrom byte string, start) order is a
 // permutation of whole per-reference pieces, applied while the bytes leave the pinned bounce buffers.
 namespace {
-struct TextPiece {
-  uint64_t dev_begin, dev_end;  // byte range inside the device text
-  uint64_t out_off;             // where it goes in the output
-};
 
 
 // copies [a, b) of the device text, as seen through `pieces`, to its destinations via `sink(src, len, out_off)`
@@ -1612,14 +1629,6 @@ void scatter_chunk(const std::vector<TextPiece> &pieces, const uint8_t *src, uin
 }
 }  // namespace
 
-struct Pileup::TextJob {
-  DevBuf d_names, d_name_off, d_skip, d_scores, d_row_len, d_tile_off, d_text, d_ref_off;
-  uint64_t nbytes = 0;
-  std::vector<TextPiece> pieces;  // sorted by dev_begin
-  ~TextJob() {
-    for (DevBuf *b : {&d_names, &d_name_off, &d_skip, &d_scores, &d_row_len, &d_tile_off, &d_text, &d_ref_off}) b->release();
-  }
-};
 
 // Formats every row on the device; returns the device text and how its per-reference pieces map to the output order.
 void Pileup::format_text(TextJob &job) {
@@ -1628,6 +1637,7 @@ void Pileup::format_text(TextJob &job) {
   const size_t n_ref = hdr_.names.size();
   job.nbytes = 0;
   job.pieces.clear();
+  job.span.assign(n_ref, {0, 0});
   if (im.n_runs == 0) return;
   // score text per distinct raw count: (count as f64) * factor, printed like a polars Float64 column
   const double factor = norm_factor();
@@ -1698,24 +1708,36 @@ void Pileup::format_text(TextJob &job) {
   std::vector<uint64_t> ref_off(n_ref + 1);
   CU(cudaMemcpyAsync(ref_off.data(), job.d_ref_off.p, (n_ref + 1) * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  // device text is in header order; write_bedgraph sorts by (chrom as a byte string, start)
-  std::vector<std::pair<uint64_t, uint64_t>> span(n_ref, {0, 0});
+  // device text is in header order; where each reference's rows go is decided by place_pieces()
   uint64_t next = job.nbytes;
   for (size_t r = n_ref; r-- > 0;)
     if (ref_off[r] != ~0ull) {
-      span[r] = {ref_off[r], next};
+      job.span[r] = {ref_off[r], next};
       next = ref_off[r];
     }
+}
+
+// write_bedgraph sorts by (chrom as a byte string, start) (coverage_analysis.rs:63): the output is the references in name
+// order, and inside one reference the shards in rank order (a shard is a contiguous range of genomic chunks).
+// bytes_all[k * n_ref + r] = text bytes shard k holds for reference r.  Returns the size of the whole file.
+uint64_t Pileup::place_pieces(TextJob &job, const uint64_t *bytes_all, int world, int rank) const {
+  const size_t n_ref = hdr_.names.size();
   std::vector<int> order(n_ref);
   for (size_t r = 0; r < n_ref; r++) order[r] = (int)r;
   std::sort(order.begin(), order.end(), [&](int x, int y) { return hdr_.names[x] < hdr_.names[y]; });
+  job.pieces.clear();
   uint64_t out_off = 0;
   for (int r : order)
-    if (span[r].second > span[r].first) {
-      job.pieces.push_back(TextPiece{span[r].first, span[r].second, out_off});
-      out_off += span[r].second - span[r].first;
+    for (int k = 0; k < world; k++) {
+      const uint64_t n = bytes_all[(size_t)k * n_ref + (size_t)r];
+      if (k == rank) {
+        if (n != job.span[r].second - job.span[r].first) fail("bedGraph piece table does not match this shard's text", ERR_INVALID);
+        if (n) job.pieces.push_back(TextPiece{job.span[r].first, job.span[r].second, out_off});
+      }
+      out_off += n;
     }
   std::sort(job.pieces.begin(), job.pieces.end(), [](const TextPiece &x, const TextPiece &y) { return x.dev_begin < y.dev_begin; });
+  return out_off;
 }
 
 // Streams the device text through the pinned bounce buffers; `sink(src, len, out_off)` may be called concurrently.
@@ -1816,6 +1838,9 @@ void Pileup::bedgraph_text(std::string &out) {
   std::lock_guard<std::mutex> lock(ctx.mu);
   TextJob job;
   format_text(job);
+  std::vector<uint64_t> mine(hdr_.names.size());
+  for (size_t r = 0; r < mine.size(); r++) mine[r] = job.span[r].second - job.span[r].first;
+  place_pieces(job, mine.data(), 1, 0);
   out.assign(job.nbytes, '\0');
   char *dst = out.empty() ? nullptr : &out[0];
   drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, 4,
@@ -1846,6 +1871,55 @@ struct Unmapper {
 } g_unmapper;
 }  // namespace
 
+// Fills this shard's pieces into the output file `fd` (size `total`; the first `prealloc` bytes already have pages) and
+// closes it.  Regular files: the writer threads memcpy into a shared mapping (parallel page-cache fills; pwrite would
+// serialise on the inode lock); anything unmappable falls back to positional writes.
+void Pileup::write_pieces(TextJob &job, int fd, const std::string &path, uint64_t total, uint64_t prealloc, bool truncate_at_end) {
+  DeviceCtx &ctx = *im_->ctx;
+  char *map = nullptr;
+  try {
+    // every byte the writers will touch must be backed before it is mapped: a store into a hole of a sparse file raises
+    // SIGBUS when the file system is full, which would take the host process down instead of returning an error
+    bool backed = !job.pieces.empty();
+    for (const TextPiece &pc : job.pieces) {
+      const uint64_t a0 = pc.out_off, a1 = pc.out_off + (pc.dev_end - pc.dev_begin);
+      if (a1 > prealloc && posix_fallocate(fd, (off_t)std::max(a0, prealloc), (off_t)(a1 - std::max(a0, prealloc))) != 0) backed = false;
+    }
+    if (backed && total) {
+      void *m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      if (m != MAP_FAILED) map = (char *)m;
+    }
+    // the writers spend most of their time in page faults, so more of them than cores pays: 8 -> 24 threads on the
+    // 16-core B200 hosts takes the drain of 2.1 GB from 155 to 125 ms (profiles/r1_sweeps.md)
+    const unsigned hw = host_cores_share();
+    const int writers = (int)env_u64("BND_WRITERS", std::min(32u, std::max(4u, hw + hw / 2)));
+    if (map)
+      drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, writers,
+                 [map](const uint8_t *src, uint64_t len, uint64_t off) { memcpy(map + off, src, len); });
+    else
+      drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, writers, [fd](const uint8_t *src, uint64_t len, uint64_t off) {
+        uint64_t done = 0;
+        while (done < len) {
+          ssize_t w = pwrite(fd, src + done, len - done, (off_t)(off + done));
+          if (w <= 0) fail("write error on the bedGraph output");
+          done += (uint64_t)w;
+        }
+      });
+  } catch (...) {
+    if (map) munmap(map, total);
+    close(fd);
+    throw;
+  }
+  // The file's pages are complete; tearing down the page-table entries of the mapping (26 ms for 2 GB) only concerns this
+  // process's address space, so it is left to a background thread and the file is closed right away.
+  if (map) g_unmapper.submit(map, total);
+  if (truncate_at_end && ftruncate(fd, (off_t)total) != 0) {
+    close(fd);
+    fail("write error on " + path);
+  }
+  if (close(fd) != 0) fail("write error on " + path);
+}
+
 void Pileup::to_bedgraph(const std::string &path) {
   g_unmapper.reap();
   DeviceCtx &ctx = *im_->ctx;
@@ -1856,7 +1930,6 @@ void Pileup::to_bedgraph(const std::string &path) {
   // (one fallocate of an upper bound of the text size: rows <= min(bins, 2 reads + chunks), <= name + 46 bytes each).
   // Filling pre-allocated page-cache pages runs at memory speed (16 GB/s with 8 threads on the B200 hosts) instead of the
   // 6 GB/s of faulting them in one by one; the surplus is cut off by the final ftruncate.
-  uint64_t prealloc = 0;
   std::atomic<uint64_t> prealloc_done{0};
   std::atomic<bool> prealloc_stop{false};
   std::thread prealloc_thread;
@@ -1898,60 +1971,67 @@ void Pileup::to_bedgraph(const std::string &path) {
   }
   prealloc_stop.store(true);
   if (prealloc_thread.joinable()) prealloc_thread.join();
-  prealloc = prealloc_done.load();
+  const uint64_t prealloc = prealloc_done.load();
   const double t0 = now_ms();
   std::lock_guard<std::mutex> lock(ctx.mu);
   TextJob job;
-  char *map = nullptr;
   uint64_t out_bytes = 0;
   double t1 = t0;
   try {
     format_text(job);
     t1 = now_ms();
-    for (const TextPiece &pc : job.pieces) out_bytes = std::max(out_bytes, pc.out_off + (pc.dev_end - pc.dev_begin));
-    // regular files: the writer threads memcpy into a shared mapping (parallel page-cache fills; pwrite would
-    // serialise on the inode lock); anything unmappable falls back to positional writes
-    // every byte the writers will touch must be backed before it is mapped: a store into a hole of a sparse file
-    // raises SIGBUS when the file system is full, which would take the host process down instead of returning an error
-    if (out_bytes && (prealloc >= out_bytes || posix_fallocate(fd, (off_t)prealloc, (off_t)(out_bytes - prealloc)) == 0)) {
-      void *m = mmap(nullptr, out_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-      if (m != MAP_FAILED) map = (char *)m;
-    }
-    // the writers spend most of their time in page faults, so more of them than cores pays: 8 -> 24 threads on the
-    // 16-core B200 hosts takes the drain of 2.1 GB from 155 to 125 ms (profiles/r1_sweeps.md)
-    const unsigned hw = host_cores_share();
-    const int writers = (int)env_u64("BND_WRITERS", std::min(32u, std::max(4u, hw + hw / 2)));
-    if (map)
-      drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, writers,
-                 [map](const uint8_t *src, uint64_t len, uint64_t off) { memcpy(map + off, src, len); });
-    else
-      drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, writers, [fd](const uint8_t *src, uint64_t len, uint64_t off) {
-        uint64_t done = 0;
-        while (done < len) {
-          ssize_t w = pwrite(fd, src + done, len - done, (off_t)(off + done));
-          if (w <= 0) fail("write error on the bedGraph output");
-          done += (uint64_t)w;
-        }
-      });
+    std::vector<uint64_t> mine(hdr_.names.size());
+    for (size_t r = 0; r < mine.size(); r++) mine[r] = job.span[r].second - job.span[r].first;
+    out_bytes = place_pieces(job, mine.data(), 1, 0);
   } catch (...) {
-    if (map) munmap(map, out_bytes);
     close(fd);
     throw;
   }
-  const double t2a = now_ms();
-  // The file's pages are complete; tearing down 2 GB of page-table entries (26 ms) only concerns this process's address
-  // space, so it is left to a background thread and the file is truncated to size and closed right away.
-  if (map) g_unmapper.submit(map, out_bytes);
-  const double t2 = now_ms();
-  if (ftruncate(fd, (off_t)out_bytes) != 0) {
-    close(fd);
-    fail("write error on " + path);
-  }
-  if (close(fd) != 0) fail("write error on " + path);
+  write_pieces(job, fd, path, out_bytes, prealloc, true);
   tm_.text_ms = now_ms() - t0;
   if (env_u64("BND_DEBUG_TIMING", 0))
-    fprintf(stderr, "[bnd] to_bedgraph: pile-up %.2f ms (prealloc %llu MB), format %.2f ms, drain %.2f ms (munmap %.2f ms), truncate+close %.2f ms, %llu bytes\n", t0 - t00,
-            (unsigned long long)(prealloc >> 20), t1 - t0, t2 - t1, t2 - t2a, now_ms() - t2, (unsigned long long)job.nbytes);
+    fprintf(stderr, "[bnd] to_bedgraph: pile-up %.2f ms (prealloc %llu MB), format %.2f ms, drain + close %.2f ms, %llu bytes\n", t0 - t00,
+            (unsigned long long)(prealloc >> 20), t1 - t0, now_ms() - t1, (unsigned long long)job.nbytes);
+}
+
+// Sharded jobs write ONE bedGraph (write_bedgraph, coverage_analysis.rs:43-75): every rank formats its rows on the device and
+// reports the bytes it holds per reference; the caller gathers those tables from all ranks (n_ref x u64 each, the only
+// exchange besides the 13 filter counters) and every rank then fills its own pieces of the same file.
+void Pileup::format_bedgraph(std::vector<uint64_t> &bytes_per_ref) {
+  ensure_finalized();
+  Impl &im = *im_;
+  std::lock_guard<std::mutex> lock(im.ctx->mu);
+  im.text_job.reset(new TextJob());
+  try {
+    format_text(*im.text_job);
+  } catch (...) {
+    im.text_job.reset();
+    throw;
+  }
+  bytes_per_ref.assign(hdr_.names.size(), 0);
+  for (size_t r = 0; r < bytes_per_ref.size(); r++) bytes_per_ref[r] = im.text_job->span[r].second - im.text_job->span[r].first;
+}
+
+void Pileup::write_bedgraph_pieces(const std::string &path, const uint64_t *bytes_all, int world, int rank) {
+  Impl &im = *im_;
+  if (!im.text_job) fail("write_bedgraph_pieces called before format_bedgraph", ERR_INVALID);
+  if (world < 1 || rank < 0 || rank >= world || !bytes_all) fail("bad shard table", ERR_INVALID);
+  g_unmapper.reap();
+  const double t0 = now_ms();
+  std::lock_guard<std::mutex> lock(im.ctx->mu);
+  std::unique_ptr<TextJob> job = std::move(im.text_job);
+  const uint64_t total = place_pieces(*job, bytes_all, world, rank);
+  // every rank opens (or creates) the same file and sets the same size; pieces never overlap, so no rank has to wait for
+  // another one before it fills its own
+  int fd = ::open(path.c_str(), O_RDWR | O_CREAT, 0644);
+  if (fd < 0) fail("cannot create " + path);
+  struct stat st;
+  if (fstat(fd, &st) != 0 || ((uint64_t)st.st_size != total && ftruncate(fd, (off_t)total) != 0)) {
+    close(fd);
+    fail("cannot size " + path);
+  }
+  write_pieces(*job, fd, path, total, 0, false);
+  tm_.text_ms = now_ms() - t0;
 }
 
 }  // namespace bnd

@@ -23,7 +23,7 @@ struct Timings {
   double inflate_ms = 0, index_ms = 0, pileup_ms = 0, finalize_ms = 0, h2d_ms = 0, text_ms = 0, wall_ms = 0, read_ms = 0;
 };
 struct Shape {
-  uint64_t records = 0, comp_bytes = 0, inflated_bytes = 0, blocks = 0, bins = 0, launches = 0, chunk_len = 0, n_chunks = 0;
+  uint64_t records = 0, comp_bytes = 0, inflated_bytes = 0, blocks = 0, bins = 0, launches = 0, chunk_len = 0, n_chunks = 0, segments = 0;
 };
 
 class Pileup {
@@ -48,6 +48,10 @@ class Pileup {
   void set_total_stats(const uint64_t s[ST_N_COUNTERS]);
   uint64_t finalize();          // scan + collapse; returns the number of rows
   void bedgraph_text(std::string &out);
+  // sharded jobs, one output file: text on the device + bytes per reference, then this shard's pieces at the offsets that
+  // follow from every rank's table (bytes_all[rank][ref])
+  void format_bedgraph(std::vector<uint64_t> &bytes_per_ref);
+  void write_bedgraph_pieces(const std::string &path, const uint64_t *bytes_all, int world, int rank);
   const Timings &timings() const { return tm_; }
   const Shape &shape() const { return shape_; }
 
@@ -88,6 +92,8 @@ class Pileup {
   struct TextJob;
   std::unique_ptr<Impl> im_;
   void format_text(TextJob &job);
+  uint64_t place_pieces(TextJob &job, const uint64_t *bytes_all, int world, int rank) const;
+  void write_pieces(TextJob &job, int fd, const std::string &path, uint64_t total, uint64_t prealloc, bool truncate_at_end);
 
   void open();
   Range range_for_chunks(uint64_t chunk_lo, uint64_t chunk_hi) const;

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BND_ABI_VERSION 1
+#define BND_ABI_VERSION 2
 
 /* error classes */
 enum { BND_OK = 0, BND_ERR_RUNTIME = 1, BND_ERR_NOT_FOUND = 2, BND_ERR_INVALID = 3 };
@@ -124,8 +124,16 @@ int bnd_pileup_bedgraph_text(bnd_pileup *p, char **text, uint64_t *n_bytes);
 /* per-stage device time of the last accumulate call, ms: [inflate, record index, filter+scatter, finalize, h2d] */
 int bnd_pileup_timings(bnd_pileup *p, double ms[8]);
 /* shape of the last run: [records visited, compressed bytes, inflated bytes, BGZF blocks, bins, kernel launches,
-   chunk length, n chunks] */
-int bnd_pileup_shape(bnd_pileup *p, uint64_t shape[8]);
+   chunk length, n chunks, segments (= K1 launches), 7 reserved] */
+int bnd_pileup_shape(bnd_pileup *p, uint64_t shape[16]);
+/* Sharded jobs write ONE bedGraph (write_bedgraph, coverage_analysis.rs:43-75, sorts all rows by (chrom, start)):
+ * 1. every rank formats its rows on the device and gets the text bytes it holds per reference (header order, n_refs entries);
+ * 2. the caller gathers those tables from all ranks (all-gather of n_refs x u64 - the only exchange besides the counters);
+ * 3. every rank fills its own pieces of the same file: references in byte-string order, inside a reference the shards in rank
+ *    order.  bytes_all is [world][n_refs], row `rank` must be what step 1 returned.  No rank waits for another one; the file is
+ *    complete once every rank has returned (the caller's barrier). */
+int bnd_pileup_format_bedgraph(bnd_pileup *p, uint64_t *bytes_per_ref, uint64_t n_refs);
+int bnd_pileup_write_bedgraph_pieces(bnd_pileup *p, const char *out_path, const uint64_t *bytes_all, int32_t world, int32_t rank);
 
 /* ---- Python front door (bamnado-python/src/lib.rs:248-304) ------------------------------------------------ */
 /* get_signal_for_chromosome: dense float32[chrom_size]; unknown contig -> BND_ERR_NOT_FOUND */

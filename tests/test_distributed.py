@@ -33,6 +33,12 @@ WORKER = textwrap.dedent("""
             open({out!r} + ".factor", "w").write(repr(h.norm_factor()))
         text = h.bedgraph_text()
         open({out!r} + f".text{{rank}}", "wb").write(text)
+        # ONE sorted bedGraph written by all ranks: all-gather of the per-reference byte counts, then every rank fills its pieces
+        sizes = torch.tensor(h.format_bedgraph(), dtype=torch.int64)
+        tables = [torch.empty_like(sizes) for _ in range(world)]
+        dist.all_gather(tables, sizes)
+        h.write_bedgraph_pieces({out!r} + ".merged.bdg", [t.tolist() for t in tables], rank)
+        dist.barrier()
     dist.destroy_process_group()
 """)
 
@@ -57,6 +63,8 @@ def test_two_rank_gloo_sharded_coverage(oracle, make_bam, tmp_path, native_emul)
     oracle.pileup_to_bedgraph(pile, filt, ref)
     got = sorted(open(out + ".text0", "rb").read().splitlines() + open(out + ".text1", "rb").read().splitlines())
     assert got == sorted(ref.read_bytes().splitlines())
+    # the file the ranks wrote together is the reference's artefact byte for byte (write_bedgraph sorts by chrom, start)
+    assert open(out + ".merged.bdg", "rb").read() == ref.read_bytes()
 
 
 def test_multi_bam_one_bam_per_rank_gloo(oracle, make_bam, tmp_path, native_emul):
