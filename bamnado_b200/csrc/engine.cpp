@@ -18,6 +18,7 @@
 #include <mutex>
 #include <thread>
 
+#include "bigwig_layout.h"
 #include "cuda_rt.h"
 #include "kernels.h"
 
@@ -1992,6 +1993,323 @@ void Pileup::to_bedgraph(const std::string &path) {
   if (env_u64("BND_DEBUG_TIMING", 0))
     fprintf(stderr, "[bnd] to_bedgraph: pile-up %.2f ms (prealloc %llu MB), format %.2f ms, drain + close %.2f ms, %llu bytes\n", t0 - t00,
             (unsigned long long)(prealloc >> 20), t1 - t0, now_ms() - t1, (unsigned long long)job.nbytes);
+}
+
+// ---- to_bigwig (coverage_analysis.rs:642-759) ------------------------------------------------------------------------------------
+// Rows: optional scaffold drop, BAM header order, start-1 / end-1, score = (count as f64 * factor) as f32.  Everything that
+// touches the rows runs on the device (bigwig.cuh): items, 1 024-item sections, one zlib stream per section, the summary
+// statistics and the zoom levels; the host lays the file out (header, chromosome tree, R-trees) and the section blobs leave
+// through the same pinned bounce buffers and writer threads as bedGraph text.
+namespace {
+struct BwLevel {  // compressed sections of the data level or of one zoom level, back to back on the device
+  DevBuf blob;
+  uint64_t bytes = 0, n_units = 0;
+  uint32_t reduction = 0;
+  std::vector<bwl::Section> secs;  // chrom, start, end, offset (inside the blob), size
+  ~BwLevel() { blob.release(); }
+};
+}  // namespace
+
+void Pileup::to_bigwig(const std::string &path) {
+  ensure_finalized();
+  g_unmapper.reap();
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  const double t0 = now_ms();
+  const double factor = norm_factor();
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  cudaStream_t st = ctx.sets[0].stream;
+  const size_t n_ref = hdr_.names.size();
+  const bool compress = env_u64("BND_BIGWIG_COMPRESS", 1) != 0;
+
+  // chromosome ids are dense (0 .. kept - 1, header order): readers such as libBigWig index arrays of `itemCount`
+  // entries by id, so the BAM reference index cannot be used once references are dropped
+  std::vector<uint8_t> skip(n_ref, 0);
+  std::vector<uint32_t> dense(n_ref, 0);
+  std::vector<std::tuple<std::string, uint32_t, uint32_t>> chroms;
+  std::vector<int> ref_of_dense;
+  for (size_t r = 0; r < n_ref; r++) {
+    skip[r] = cfg_.ignore_scaffold && is_scaffold(hdr_.names[r]);
+    if (hdr_.lens[r] > 0xffffffffull) fail("chromosome too long for BigWig");
+    if (!skip[r]) {
+      dense[r] = (uint32_t)chroms.size();
+      chroms.emplace_back(hdr_.names[r], dense[r], (uint32_t)hdr_.lens[r]);
+      ref_of_dense.push_back((int)r);
+    }
+  }
+  const uint32_t n_chrom = (uint32_t)chroms.size();
+
+  DevBuf d_row_first, d_item_first, d_skip, d_items, d_flag, d_secs, d_staging, d_sizes, d_bounds, d_stats, d_offsets;
+  DevBuf z_item_first, z_win_first, z_recs, z_flags, z_tiles, z_total, z_out, z_chrom_first;
+  auto release = [&] {
+    for (DevBuf *b : {&d_row_first, &d_item_first, &d_skip, &d_items, &d_flag, &d_secs, &d_staging, &d_sizes, &d_bounds, &d_stats, &d_offsets, &z_item_first,
+                      &z_win_first, &z_recs, &z_flags, &z_tiles, &z_total, &z_out, &z_chrom_first})
+      b->release();
+  };
+  BwLevel data;
+  std::vector<std::unique_ptr<BwLevel>> zooms;
+  uint64_t covered = 0;
+  double mn = 0, mx = 0, sum = 0, sumsq = 0;
+  uint32_t max_raw = 0;
+  int fd = -1;
+  char *map = nullptr;
+  uint64_t file_bytes = 0;
+  try {
+    // ---- items of the kept references ----
+    std::vector<uint64_t> row_first(n_ref + 1, 0), item_first(n_ref + 1, 0);
+    d_row_first.ensure((n_ref + 1) * 8);
+    if (im.n_runs) {
+      CU(launch_bw_row_first(im.d_run_bin.as<uint64_t>(), im.n_runs, im.gdev, d_row_first.as<uint64_t>(), st));
+      CU(cudaMemcpyAsync(row_first.data(), d_row_first.p, (n_ref + 1) * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
+    for (size_t r = 0; r < n_ref; r++) item_first[r + 1] = item_first[r] + (skip[r] ? 0 : row_first[r + 1] - row_first[r]);
+    const uint64_t n_items = item_first[n_ref];
+    std::vector<uint64_t> chrom_item_first(n_chrom + 1, 0);  // per dense chromosome
+    for (uint32_t c = 0; c < n_chrom; c++) chrom_item_first[c] = item_first[ref_of_dense[c]];
+    chrom_item_first[n_chrom] = n_items;
+    upload(d_item_first, item_first.data(), item_first.size());
+    upload(d_skip, skip.data(), skip.size());
+    d_items.ensure(std::max<uint64_t>(n_items, 1) * sizeof(BwItem));
+    d_flag.ensure(16);
+    CU(cudaMemsetAsync(d_flag.p, 0, 16, st));
+    if (im.n_runs) {
+      BwItemArgs ia{};
+      ia.run_bin = im.d_run_bin.as<uint64_t>();
+      ia.run_val = im.d_run_val.as<uint32_t>();
+      ia.n_runs = im.n_runs;
+      ia.g = im.gdev;
+      ia.row_first = d_row_first.as<uint64_t>();
+      ia.item_first = d_item_first.as<uint64_t>();
+      ia.ref_skip = d_skip.as<uint8_t>();
+      ia.factor = factor;
+      ia.items = d_items.as<BwItem>();
+      ia.range_error = d_flag.as<unsigned int>();
+      CU(launch_bw_items(ia, ctx.sm_count, st));
+      unsigned int bad = 0;
+      CU(cudaMemcpyAsync(&bad, d_flag.p, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (bad) fail("interval out of range for BigWig");
+    }
+    // ---- one level = section table -> zlib streams -> packed blob ----
+    auto encode = [&](BwLevel &lv, const uint8_t *units, const std::vector<uint64_t> &first_unit_of_chrom, uint32_t unit_bytes, uint32_t header_bytes,
+                      const uint32_t lags[4], bool want_stats) {
+      std::vector<BwSection> table;
+      for (uint32_t c = 0; c < n_chrom; c++)
+        for (uint64_t u = first_unit_of_chrom[c]; u < first_unit_of_chrom[c + 1]; u += BW_ITEMS)
+          table.push_back(BwSection{u, (uint32_t)std::min<uint64_t>(BW_ITEMS, first_unit_of_chrom[c + 1] - u), c});
+      const uint32_t ns = (uint32_t)table.size();
+      lv.n_units = first_unit_of_chrom[n_chrom];
+      lv.secs.clear();
+      lv.bytes = 0;
+      if (ns == 0) return;
+      const uint32_t raw_max = header_bytes + unit_bytes * BW_ITEMS;
+      const uint32_t stride = ((compress ? bw_comp_bound(raw_max) : raw_max) + 15u) & ~15u;
+      upload(d_secs, table.data(), table.size());
+      d_staging.ensure((size_t)ns * stride + 16);
+      d_sizes.ensure((size_t)ns * 4);
+      d_bounds.ensure((size_t)ns * 8);
+      if (want_stats) d_stats.ensure((size_t)ns * 40);
+      BwDeflateArgs da{};
+      da.units = units;
+      da.sections = d_secs.as<BwSection>();
+      da.n_sections = ns;
+      da.unit_bytes = unit_bytes;
+      da.header_bytes = header_bytes;
+      da.stride = stride;
+      for (int k = 0; k < 4; k++) da.dist[k] = lags[k];
+      da.compress = compress;
+      da.staging = d_staging.as<uint8_t>();
+      da.comp_size = d_sizes.as<uint32_t>();
+      da.bounds = d_bounds.as<uint32_t>();
+      da.stats = want_stats ? d_stats.as<double>() : nullptr;
+      CU(launch_bw_deflate(da, ctx.sm_count, st));
+      std::vector<uint32_t> sizes(ns), bounds((size_t)ns * 2);
+      CU(cudaMemcpyAsync(sizes.data(), d_sizes.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(bounds.data(), d_bounds.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
+      std::vector<double> stats;
+      if (want_stats) {
+        stats.resize((size_t)ns * 5);
+        CU(cudaMemcpyAsync(stats.data(), d_stats.p, (size_t)ns * 40, cudaMemcpyDeviceToHost, st));
+      }
+      CU(cudaStreamSynchronize(st));
+      std::vector<uint64_t> offs(ns);
+      lv.secs.resize(ns);
+      for (uint32_t k = 0; k < ns; k++) {
+        offs[k] = lv.bytes;
+        lv.secs[k] = bwl::Section{table[k].chrom, bounds[2 * k], bounds[2 * k + 1], lv.bytes, sizes[k]};
+        lv.bytes += sizes[k];
+        max_raw = std::max(max_raw, header_bytes + table[k].count * unit_bytes);
+      }
+      if (want_stats)
+        for (uint32_t k = 0; k < ns; k++) {  // section order: reproducible totals
+          const double *q = &stats[(size_t)k * 5];
+          if (k == 0) mn = q[1], mx = q[2];
+          covered += (uint64_t)q[0];
+          mn = std::min(mn, q[1]), mx = std::max(mx, q[2]);
+          sum += q[3], sumsq += q[4];
+        }
+      upload(d_offsets, offs.data(), offs.size());
+      lv.blob.ensure(lv.bytes + 16);
+      BwCompactArgs ca{};
+      ca.staging = d_staging.as<uint8_t>();
+      ca.comp_size = d_sizes.as<uint32_t>();
+      ca.offset = d_offsets.as<uint64_t>();
+      ca.n_sections = ns;
+      ca.stride = stride;
+      ca.blob = lv.blob.as<uint8_t>();
+      CU(launch_bw_compact(ca, ctx.sm_count, st));
+      CU(cudaStreamSynchronize(st));  // d_secs / d_staging are reused by the next level
+    };
+    const uint32_t item_lags[4] = {4, 8, 12, 24};  // start = previous end (lag 8), fields of the previous items (12, 24), zero / equal halves (4)
+    encode(data, d_items.as<uint8_t>(), chrom_item_first, BW_ITEM_BYTES, BW_SEC_HEADER, item_lags, true);
+
+    // ---- zoom levels: first reduction ~10x the mean item width, then 4x per level, until a level is small ----
+    if (n_items) {
+      upload(z_item_first, chrom_item_first.data(), chrom_item_first.size());
+      uint64_t reduction = std::max<uint64_t>(10, covered / n_items * 10);
+      for (uint32_t z = 0; z < bwl::MAX_ZOOM && reduction <= 0x7fffffffull; z++, reduction *= 4) {
+        std::vector<uint64_t> win_first(n_chrom + 1, 0);
+        for (uint32_t c = 0; c < n_chrom; c++) win_first[c + 1] = win_first[c] + ((uint64_t)std::get<2>(chroms[c]) + reduction - 1) / reduction;
+        const uint64_t n_win = win_first[n_chrom];
+        const uint64_t n_tiles64 = (n_win + BW_THREADS - 1) / BW_THREADS;
+        if (n_tiles64 > 0xffffffffull) fail("too many zoom windows");
+        upload(z_win_first, win_first.data(), win_first.size());
+        z_recs.ensure(std::max<uint64_t>(n_win, 1) * BW_ZOOM_BYTES);
+        z_flags.ensure(n_win + 16);
+        z_tiles.ensure(n_tiles64 * 8 + 16);
+        z_total.ensure(16);
+        z_chrom_first.ensure((n_chrom + 1) * 8);
+        BwZoomArgs za{};
+        za.items = d_items.as<BwItem>();
+        za.item_first = z_item_first.as<uint64_t>();
+        za.win_first = z_win_first.as<uint64_t>();
+        za.n_chrom = n_chrom;
+        za.reduction = (uint32_t)reduction;
+        za.n_windows = n_win;
+        za.recs = z_recs.as<uint8_t>();
+        za.flags = z_flags.as<uint8_t>();
+        za.tile_count = z_tiles.as<uint64_t>();
+        za.n_tiles = (uint32_t)n_tiles64;
+        za.chrom_first_rec = z_chrom_first.as<uint64_t>();
+        CU(launch_bw_zoom_windows(za, ctx.sm_count, st));
+        CU(launch_u64_scan(za.tile_count, za.n_tiles, z_total.as<unsigned long long>(), st));
+        unsigned long long n_recs = 0;
+        CU(cudaMemcpyAsync(&n_recs, z_total.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (z > 0 && n_recs < 64) break;  // coarse enough: a viewer reads the previous level in one go
+        z_out.ensure(std::max<uint64_t>(n_recs, 1) * BW_ZOOM_BYTES);
+        za.out = z_out.as<uint8_t>();
+        CU(launch_bw_zoom_compact(za, n_recs, ctx.sm_count, st));
+        std::vector<uint64_t> chrom_first_rec(n_chrom + 1);
+        CU(cudaMemcpyAsync(chrom_first_rec.data(), z_chrom_first.p, (n_chrom + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        zooms.emplace_back(new BwLevel());
+        BwLevel &lv = *zooms.back();
+        lv.reduction = (uint32_t)reduction;
+        const uint32_t zoom_lags[4] = {4, 28, 32, 0};  // min = max (4), start = previous end (28), same field of the previous record (32)
+        encode(lv, z_out.as<uint8_t>(), chrom_first_rec, BW_ZOOM_BYTES, 0, zoom_lags, false);
+        if (n_recs < 64) break;
+      }
+    }
+
+    // ---- file layout ----
+    bwl::Buf head;  // header (64) + zoom headers + total summary, then the chromosome tree
+    head.pad_to(64 + bwl::MAX_ZOOM * 24 + 40);
+    const uint64_t chrom_tree_off = head.d.size();
+    bwl::write_chrom_tree(head, chroms);
+    const uint64_t data_off = head.d.size();
+    head.u64(data.secs.size());
+    const uint64_t data_blob_off = head.d.size();
+    for (auto &sc : data.secs) sc.offset += data_blob_off;
+    const uint64_t index_off = data_blob_off + data.bytes;
+    bwl::Buf index;
+    {
+      bwl::Buf tmp;
+      tmp.pad_to(index_off);  // offsets inside the R-tree are absolute: build it at its final position
+      tmp.d.resize(index_off);
+      bwl::write_rtree(tmp, data.secs, index_off);
+      index.d.assign(tmp.d.begin() + (std::ptrdiff_t)index_off, tmp.d.end());
+    }
+    struct ZoomPlace {
+      uint64_t data_off, blob_off, index_off;
+      std::vector<uint8_t> index;
+    };
+    std::vector<ZoomPlace> zp(zooms.size());
+    uint64_t cur = index_off + index.d.size();
+    for (size_t z = 0; z < zooms.size(); z++) {
+      BwLevel &lv = *zooms[z];
+      zp[z].data_off = cur;
+      zp[z].blob_off = cur + 4;  // u32 record count in front of a level's sections, as UCSC writers put it
+      for (auto &sc : lv.secs) sc.offset += zp[z].blob_off;
+      zp[z].index_off = zp[z].blob_off + lv.bytes;
+      bwl::Buf tmp;
+      tmp.d.resize(zp[z].index_off);
+      bwl::write_rtree(tmp, lv.secs, zp[z].index_off);
+      zp[z].index.assign(tmp.d.begin() + (std::ptrdiff_t)zp[z].index_off, tmp.d.end());
+      cur = zp[z].index_off + zp[z].index.size();
+    }
+    file_bytes = cur + 4;  // trailing magic
+    {
+      bwl::Buf hd;
+      hd.u32(0x888FFC26);
+      hd.u16(4);
+      hd.u16((uint16_t)zooms.size());
+      hd.u64(chrom_tree_off);
+      hd.u64(data_off);
+      hd.u64(index_off);
+      hd.u16(0), hd.u16(0);
+      hd.u64(0);
+      hd.u64(64 + bwl::MAX_ZOOM * 24);  // total summary offset: after the (reserved) zoom headers
+      hd.u32(compress ? max_raw : 0);   // uncompressBufSize: size of the largest inflated section; 0 = sections are stored raw
+      hd.u64(0);
+      for (uint32_t z = 0; z < bwl::MAX_ZOOM; z++) {
+        const bool on = z < zooms.size();
+        hd.u32(on ? zooms[z]->reduction : 0), hd.u32(0);
+        hd.u64(on ? zp[z].data_off : 0), hd.u64(on ? zp[z].index_off : 0);
+      }
+      hd.u64(covered), hd.f64(mn), hd.f64(mx), hd.f64(sum), hd.f64(sumsq);
+      memcpy(head.d.data(), hd.d.data(), hd.d.size());
+    }
+    fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) fail("cannot create " + path);
+    if (posix_fallocate(fd, 0, (off_t)file_bytes) != 0) fail("cannot allocate " + path);
+    void *m = mmap(nullptr, file_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (m == MAP_FAILED) fail("cannot map " + path);
+    map = (char *)m;
+    memcpy(map, head.d.data(), head.d.size());
+    memcpy(map + index_off, index.d.data(), index.d.size());
+    for (size_t z = 0; z < zooms.size(); z++) {
+      const uint32_t n = (uint32_t)std::min<uint64_t>(zooms[z]->n_units, 0xffffffffull);
+      memcpy(map + zp[z].data_off, &n, 4);
+      memcpy(map + zp[z].index_off, zp[z].index.data(), zp[z].index.size());
+    }
+    const uint32_t magic = 0x888FFC26;
+    memcpy(map + file_bytes - 4, &magic, 4);
+    const unsigned hw = host_cores_share();
+    const int writers = (int)env_u64("BND_WRITERS", std::min(32u, std::max(4u, hw)));
+    auto drain_level = [&](BwLevel &lv, uint64_t off) {
+      if (!lv.bytes) return;
+      std::vector<TextPiece> one{TextPiece{0, lv.bytes, off}};
+      char *base = map;
+      drain_text(ctx, lv.blob.as<uint8_t>(), lv.bytes, one, writers, [base](const uint8_t *src, uint64_t len, uint64_t o) { memcpy(base + o, src, len); });
+    };
+    drain_level(data, data_blob_off);
+    for (size_t z = 0; z < zooms.size(); z++) drain_level(*zooms[z], zp[z].blob_off);
+  } catch (...) {
+    release();
+    if (map) munmap(map, file_bytes);
+    if (fd >= 0) close(fd);
+    throw;
+  }
+  release();
+  g_unmapper.submit(map, file_bytes);
+  if (close(fd) != 0) fail("write error on " + path);
+  tm_.text_ms = now_ms() - t0;
+  if (env_u64("BND_DEBUG_TIMING", 0))
+    fprintf(stderr, "[bnd] to_bigwig: %llu sections, %llu bytes of data sections, %zu zoom levels, %.2f ms after the pile-up\n",
+            (unsigned long long)data.secs.size(), (unsigned long long)data.bytes, zooms.size(), now_ms() - t0);
 }
 
 // Sharded jobs write ONE bedGraph (write_bedgraph, coverage_analysis.rs:43-75): every rank formats its rows on the device and

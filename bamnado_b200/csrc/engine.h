@@ -35,6 +35,7 @@ class Pileup {
 
   // --- whole-object operations (mirror BamPileup) ---
   void to_bedgraph(const std::string &path);
+  void to_bigwig(const std::string &path);
   void runs(std::vector<RunRow> &out);                      // all rows of this shard, (ref_id, start) order
   void chromosome(const std::string &chrom, std::vector<RunRow> &out);
   void signal(const std::string &chrom, std::vector<float> &out);

@@ -3,6 +3,12 @@
 #pragma once
 #include <stdint.h>
 
+#if defined(__CUDACC__)
+#define BND_HD __host__ __device__
+#else
+#define BND_HD
+#endif
+
 namespace bnd {
 
 // status codes written per block
@@ -258,6 +264,79 @@ struct BinMatrixArgs {
   unsigned long long *matrix;     // [n_rows][n_samples]
   uint64_t bins_per_chunk_grid;   // L / bin: grid bins spanned by one genomic chunk
   uint32_t n_samples, sample;
+};
+
+
+// ---- BigWig on the device (bigwig.cuh) ---------------------------------------------------------------------------------
+constexpr uint32_t BW_ITEMS = 1024;                          // items per section (itemsPerSlot of bigtools / UCSC writers)
+constexpr uint32_t BW_ITEM_BYTES = 12;                       // bedGraph item: u32 start, u32 end, f32 value
+constexpr uint32_t BW_SEC_HEADER = 24;
+constexpr uint32_t BW_ZOOM_BYTES = 32;                       // zoom record: chrom, start, end, valid, min, max, sum, sumsq
+constexpr uint32_t BW_RAW_MAX = BW_ZOOM_BYTES * BW_ITEMS;    // largest uncompressed section (zoom): 32 KiB
+// worst case of the fixed-Huffman stream: 2 (zlib header) + (3 + 9 bits per byte + 7 end-of-block, rounded up) + 4 (Adler-32)
+BND_HD constexpr uint32_t bw_comp_bound(uint32_t raw) { return 2 + (3 + 9 * raw + 7 + 7) / 8 + 4; }
+constexpr int BW_THREADS = 256;
+
+struct BwItem {  // what a bedGraph section stores per interval; coordinates are 0-based (both ends - 1)
+  uint32_t start, end;
+  float val;
+};
+
+struct BwItemArgs {  // runs -> items of the kept references
+  const uint64_t *run_bin;
+  const uint32_t *run_val;
+  uint64_t n_runs;
+  GeomDev g;
+  const uint64_t *row_first;   // [n_ref + 1] first run of each reference
+  const uint64_t *item_first;  // [n_ref + 1] first item of each reference (dropped references own no items)
+  const uint8_t *ref_skip;     // [n_ref]
+  double factor;
+  BwItem *items;
+  unsigned int *range_error;   // set when a coordinate does not fit the format's u32
+};
+
+struct BwSection {  // one section to encode: `count` units starting at unit `first`
+  uint64_t first;
+  uint32_t count;
+  uint32_t chrom;  // dense chromosome id
+};
+
+struct BwDeflateArgs {
+  const uint8_t *units;         // BwItem[] or zoom records
+  const BwSection *sections;
+  uint32_t n_sections;
+  uint32_t unit_bytes;          // 12 or 32
+  uint32_t header_bytes;        // 24 (bedGraph section header, built here) or 0
+  uint32_t stride;              // bytes reserved per section in `staging`
+  uint32_t dist[4];             // match distances tried at every byte (0 = unused): record-structured data repeats at fixed lags
+  int compress;                 // 0: sections are stored raw
+  uint8_t *staging;             // [n_sections][stride]
+  uint32_t *comp_size;          // [n_sections]
+  uint32_t *bounds;             // [n_sections][2]: first start, last end (for the R-tree)
+  double *stats;                // [n_sections][5]: covered bases, min, max, sum, sum of squares (bedGraph sections only)
+};
+
+struct BwCompactArgs {
+  const uint8_t *staging;
+  const uint32_t *comp_size;
+  const uint64_t *offset;  // [n_sections] exclusive scan of comp_size
+  uint32_t n_sections, stride;
+  uint8_t *blob;
+};
+
+struct BwZoomArgs {
+  const BwItem *items;
+  const uint64_t *item_first;  // [n_chrom + 1] per dense chromosome
+  const uint64_t *win_first;   // [n_chrom + 1] first window of each chromosome at this level
+  uint32_t n_chrom;
+  uint32_t reduction;
+  uint64_t n_windows;
+  uint8_t *recs;               // [n_windows][32] dense, one slot per window
+  uint8_t *flags;              // [n_windows] 1 = the window holds data
+  uint64_t *tile_count;        // [n_tiles] windows with data per tile of BW_THREADS -> exclusive offsets after the scan
+  uint32_t n_tiles;
+  uint8_t *out;                // compacted records
+  uint64_t *chrom_first_rec;   // [n_chrom + 1] first compacted record of each chromosome
 };
 
 }  // namespace bnd

@@ -11,6 +11,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #endif
 
+#include "bigwig.cuh"
 #include "collapse.cuh"
 #include "finalize.cuh"
 #include "inflate_spec.cuh"
@@ -208,6 +209,51 @@ cudaError_t launch_multi_emit(const MultiArgs &a, int sm_count, cudaStream_t s) 
 cudaError_t launch_multi_rows(const RunArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_runs == 0) return cudaSuccess;
   BND_LAUNCH(multi_rows_kernel, dim3(grid_for(a.n_runs, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+
+// ---- BigWig (bigwig.cuh) ------------------------------------------------------------------------------------------------
+cudaError_t launch_bw_row_first(const uint64_t *run_bin, uint64_t n_runs, const GeomDev &g, uint64_t *row_first, cudaStream_t s) {
+  BND_LAUNCH(bw_row_first_kernel, dim3((unsigned)((g.n_ref + 1 + 127) / 128)), dim3(128), 0, s, run_bin, n_runs, g, row_first);
+  return launched();
+}
+cudaError_t launch_bw_items(const BwItemArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_runs == 0) return cudaSuccess;
+  BND_LAUNCH(bw_items_kernel, dim3(grid_for(a.n_runs, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+size_t bw_deflate_smem_bytes(uint32_t header_bytes, uint32_t unit_bytes) {
+  const uint32_t raw = header_bytes + unit_bytes * BW_ITEMS;
+  return ((raw + 3u) & ~3u) + ((bw_comp_bound(raw) + 3) / 4 + 1) * 4;
+}
+cudaError_t launch_bw_deflate(const BwDeflateArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_sections == 0) return cudaSuccess;
+  const size_t smem = bw_deflate_smem_bytes(a.header_bytes, a.unit_bytes);
+  static size_t attr_done = 0;
+  if (smem > attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(bw_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = smem;
+  }
+  BND_LAUNCH(bw_deflate_kernel, dim3(grid_for(a.n_sections, 1, (uint64_t)sm_count * 8)), dim3(BW_THREADS), smem, s, a);
+  return launched();
+}
+cudaError_t launch_bw_compact(const BwCompactArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_sections == 0) return cudaSuccess;
+  BND_LAUNCH(bw_compact_kernel, dim3(grid_for(a.n_sections, 8, (uint64_t)sm_count * 8)), dim3(256), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bw_zoom_windows(const BwZoomArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bw_zoom_windows_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(BW_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bw_zoom_compact(const BwZoomArgs &a, unsigned long long total, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bw_zoom_compact_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(BW_THREADS), 0, s, a);
+  cudaError_t e = launched();
+  if (e != cudaSuccess) return e;
+  BND_LAUNCH(bw_zoom_chrom_first_kernel, dim3((a.n_chrom + 1 + 127) / 128), dim3(128), 0, s, a, total);
   return launched();
 }
 

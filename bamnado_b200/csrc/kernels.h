@@ -38,6 +38,13 @@ cudaError_t launch_bin_matrix(const BinMatrixArgs &a, int sm_count, cudaStream_t
 cudaError_t launch_multi_count(const MultiArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_emit(const MultiArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_rows(const RunArgs &a, int sm_count, cudaStream_t s);
+// BigWig on the device (bigwig.cuh): items, sections + zlib streams, zoom summaries
+cudaError_t launch_bw_row_first(const uint64_t *run_bin, uint64_t n_runs, const GeomDev &g, uint64_t *row_first, cudaStream_t s);
+cudaError_t launch_bw_items(const BwItemArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bw_deflate(const BwDeflateArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bw_compact(const BwCompactArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bw_zoom_windows(const BwZoomArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bw_zoom_compact(const BwZoomArgs &a, unsigned long long total, int sm_count, cudaStream_t s);
 // stable sort permutation of rows by (chrom rank, start): CUB radix sort (library) — only used when the input is unsorted
 cudaError_t sort_rows_by_chrom_start(const uint32_t *d_chrom, const long long *d_start, uint64_t n, uint32_t *d_perm, cudaStream_t s);
 

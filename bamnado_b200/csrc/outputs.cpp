@@ -15,192 +15,6 @@ namespace bnd {
 
 namespace {
 
-// ---- little-endian writer ---------------------------------------------------------------------------------------------
-struct Buf {
-  std::vector<uint8_t> d;
-  void u8(uint8_t v) { d.push_back(v); }
-  void u16(uint16_t v) {
-    for (int i = 0; i < 2; i++) d.push_back((uint8_t)(v >> (8 * i)));
-  }
-  void u32(uint32_t v) {
-    for (int i = 0; i < 4; i++) d.push_back((uint8_t)(v >> (8 * i)));
-  }
-  void u64(uint64_t v) {
-    for (int i = 0; i < 8; i++) d.push_back((uint8_t)(v >> (8 * i)));
-  }
-  void f32(float v) {
-    uint32_t b;
-    memcpy(&b, &v, 4);
-    u32(b);
-  }
-  void f64(double v) {
-    uint64_t b;
-    memcpy(&b, &v, 8);
-    u64(b);
-  }
-  void bytes(const void *p, size_t n) { d.insert(d.end(), (const uint8_t *)p, (const uint8_t *)p + n); }
-  void pad_to(size_t n) { d.resize(std::max(d.size(), n), 0); }
-  void put_u64_at(size_t off, uint64_t v) {
-    for (int i = 0; i < 8; i++) d[off + i] = (uint8_t)(v >> (8 * i));
-  }
-};
-
-struct Section {  // one BigWig data section (<= ITEMS_PER_SLOT bedGraph items of one chromosome)
-  uint32_t chrom, start, end;
-  uint64_t offset, size;
-};
-constexpr uint32_t ITEMS_PER_SLOT = 1024, BLOCK = 256, MAX_ZOOM = 10;
-
-// B+ tree over (name -> id, size), keys sorted bytewise
-void write_chrom_tree(Buf &b, std::vector<std::tuple<std::string, uint32_t, uint32_t>> items) {
-  std::sort(items.begin(), items.end());
-  uint32_t key_size = 1;
-  for (auto &it : items) key_size = std::max<uint32_t>(key_size, (uint32_t)std::get<0>(it).size());
-  const uint64_t n = items.size();
-  b.u32(0x78CA8C91);
-  b.u32(BLOCK);
-  b.u32(key_size);
-  b.u32(8);
-  b.u64(n);
-  b.u64(0);
-  // levels: leaves hold up to BLOCK items; each upper node up to BLOCK children
-  std::vector<uint64_t> level_nodes;  // nodes per level, leaf level first
-  uint64_t cnt = std::max<uint64_t>(n, 1);
-  level_nodes.push_back((cnt + BLOCK - 1) / BLOCK);
-  while (level_nodes.back() > 1) level_nodes.push_back((level_nodes.back() + BLOCK - 1) / BLOCK);
-  const int levels = (int)level_nodes.size();
-  const uint64_t leaf_item = key_size + 8, inner_item = key_size + 8;
-  // items covered by one node at level l (0 = leaf)
-  auto span = [&](int l) {
-    uint64_t s = BLOCK;
-    for (int i = 0; i < l; i++) s *= BLOCK;
-    return s;
-  };
-  // offsets of each level (root first in the file)
-  std::vector<uint64_t> level_off(levels);
-  uint64_t off = b.d.size();
-  for (int l = levels - 1; l >= 0; l--) {
-    level_off[l] = off;
-    uint64_t nodes = level_nodes[l];
-    // every node is written at full size so child offsets are arithmetic
-    off += nodes * (4 + (uint64_t)BLOCK * (l == 0 ? leaf_item : inner_item));
-  }
-  auto key = [&](const std::string &s) {
-    std::string k = s;
-    k.resize(key_size, '\0');
-    return k;
-  };
-  for (int l = levels - 1; l >= 0; l--) {
-    const uint64_t nodes = level_nodes[l], per = span(l), item_sz = l == 0 ? leaf_item : inner_item;
-    for (uint64_t nd = 0; nd < nodes; nd++) {
-      const uint64_t first = nd * per;
-      uint64_t children;
-      if (l == 0) children = n > first ? std::min<uint64_t>(BLOCK, n - first) : 0;
-      else {
-        const uint64_t child_span = span(l - 1);
-        children = n > first ? std::min<uint64_t>(BLOCK, (n - first + child_span - 1) / child_span) : 0;
-      }
-      b.u8(l == 0 ? 1 : 0);
-      b.u8(0);
-      b.u16((uint16_t)children);
-      for (uint64_t c = 0; c < BLOCK; c++) {
-        if (c < children) {
-          if (l == 0) {
-            auto &it = items[first + c];
-            b.bytes(key(std::get<0>(it)).data(), key_size);
-            b.u32(std::get<1>(it));
-            b.u32(std::get<2>(it));
-          } else {
-            const uint64_t child_span = span(l - 1), child = nd * BLOCK + c;
-            b.bytes(key(std::get<0>(items[first + c * child_span])).data(), key_size);
-            b.u64(level_off[l - 1] + child * (4 + (uint64_t)BLOCK * (l - 1 == 0 ? leaf_item : inner_item)));
-          }
-        } else {
-          for (uint64_t z = 0; z < item_sz; z++) b.u8(0);
-        }
-      }
-    }
-  }
-}
-
-// cirTree (R-tree) over the sections, built bottom-up with full-size nodes
-void write_rtree(Buf &b, const std::vector<Section> &secs, uint64_t end_file_offset) {
-  const uint64_t n = secs.size();
-  b.u32(0x2468ACE0);
-  b.u32(BLOCK);
-  b.u64(n);
-  b.u32(n ? secs.front().chrom : 0);
-  b.u32(n ? secs.front().start : 0);
-  b.u32(n ? secs.back().chrom : 0);
-  b.u32(n ? secs.back().end : 0);
-  b.u64(end_file_offset);
-  b.u32(ITEMS_PER_SLOT);
-  b.u32(0);
-  struct Node {
-    uint32_t sc, sb, ec, eb;
-  };
-  // level 0 = leaf nodes over sections
-  std::vector<std::vector<Node>> bounds;  // per level: bounding box of each node
-  std::vector<uint64_t> level_nodes;
-  uint64_t cnt = std::max<uint64_t>(n, 1);
-  level_nodes.push_back((cnt + BLOCK - 1) / BLOCK);
-  while (level_nodes.back() > 1) level_nodes.push_back((level_nodes.back() + BLOCK - 1) / BLOCK);
-  const int levels = (int)level_nodes.size();
-  bounds.resize(levels);
-  auto merge = [](Node &a, const Node &x, bool first) {
-    if (first) {
-      a = x;
-      return;
-    }
-    if (x.sc < a.sc || (x.sc == a.sc && x.sb < a.sb)) a.sc = x.sc, a.sb = x.sb;
-    if (x.ec > a.ec || (x.ec == a.ec && x.eb > a.eb)) a.ec = x.ec, a.eb = x.eb;
-  };
-  for (int l = 0; l < levels; l++) {
-    bounds[l].resize(level_nodes[l]);
-    for (uint64_t nd = 0; nd < level_nodes[l]; nd++) {
-      Node box{0, 0, 0, 0};
-      bool first = true;
-      const uint64_t lo = nd * BLOCK, hi = l == 0 ? std::min<uint64_t>(n, lo + BLOCK) : std::min<uint64_t>(level_nodes[l - 1], lo + BLOCK);
-      for (uint64_t c = lo; c < hi; c++) {
-        Node x = l == 0 ? Node{secs[c].chrom, secs[c].start, secs[c].chrom, secs[c].end} : bounds[l - 1][c];
-        merge(box, x, first);
-        first = false;
-      }
-      bounds[l][nd] = box;
-    }
-  }
-  std::vector<uint64_t> level_off(levels);
-  uint64_t off = b.d.size();
-  for (int l = levels - 1; l >= 0; l--) {
-    level_off[l] = off;
-    off += level_nodes[l] * (4 + (uint64_t)BLOCK * (l == 0 ? 32 : 24));
-  }
-  for (int l = levels - 1; l >= 0; l--) {
-    for (uint64_t nd = 0; nd < level_nodes[l]; nd++) {
-      const uint64_t lo = nd * BLOCK, hi = l == 0 ? std::min<uint64_t>(n, lo + BLOCK) : std::min<uint64_t>(level_nodes[l - 1], lo + BLOCK);
-      const uint64_t children = hi > lo ? hi - lo : 0;
-      b.u8(l == 0 ? 1 : 0);
-      b.u8(0);
-      b.u16((uint16_t)children);
-      for (uint64_t c = 0; c < BLOCK; c++) {
-        if (c < children) {
-          if (l == 0) {
-            const Section &s = secs[lo + c];
-            b.u32(s.chrom), b.u32(s.start), b.u32(s.chrom), b.u32(s.end);
-            b.u64(s.offset), b.u64(s.size);
-          } else {
-            const Node &x = bounds[l - 1][lo + c];
-            b.u32(x.sc), b.u32(x.sb), b.u32(x.ec), b.u32(x.eb);
-            b.u64(level_off[l - 1] + (lo + c) * (4 + (uint64_t)BLOCK * (l - 1 == 0 ? 32 : 24)));
-          }
-        } else {
-          for (int z = 0; z < (l == 0 ? 32 : 24); z++) b.u8(0);
-        }
-      }
-    }
-  }
-}
-
 std::string lower(std::string s) {
   for (auto &c : s) c = (char)tolower((unsigned char)c);
   return s;
@@ -208,173 +22,9 @@ std::string lower(std::string s) {
 
 }  // namespace
 
-// ---- to_bigwig (coverage_analysis.rs:642-759) -------------------------------------------------------------------------------
-// Rows: optional scaffold drop, BAM header order, start-1 / end-1, score = (count as f64 * factor) as f32.
-// The file is a version-4 bigWig with bedGraph sections, zoom levels and uncompressed sections (uncompressBufSize 0).
-void pileup_to_bigwig(Pileup &p, const std::string &path) {
-  std::vector<RunRow> rows;
-  p.runs(rows);
-  const double factor = p.norm_factor();
-  const BamHeader &h = p.header();
-  const bool skip_scaffold = p.config().ignore_scaffold != 0;
-  const size_t n_ref = h.names.size();
-  std::vector<uint8_t> keep(n_ref, 1);
-  // chromosome ids are dense (0 .. kept - 1, header order): readers such as libBigWig index arrays of `itemCount`
-  // entries by id, so the BAM reference index cannot be used once references are dropped
-  std::vector<uint32_t> dense(n_ref, 0);
-  std::vector<std::tuple<std::string, uint32_t, uint32_t>> chroms;
-  for (size_t r = 0; r < n_ref; r++) {
-    if (skip_scaffold && is_scaffold(h.names[r])) keep[r] = 0;
-    if (h.lens[r] > 0xffffffffull) fail("chromosome too long for BigWig");
-    if (keep[r]) {
-      dense[r] = (uint32_t)chroms.size();
-      chroms.emplace_back(h.names[r], dense[r], (uint32_t)h.lens[r]);
-    }
-  }
-  Buf b;
-  b.pad_to(64 + MAX_ZOOM * 24 + 40);  // header, zoom headers, total summary: filled at the end
-  const uint64_t chrom_tree_off = b.d.size();
-  write_chrom_tree(b, chroms);
-  const uint64_t data_off = b.d.size();
-  b.u64(0);  // section count, patched below
-  std::vector<Section> secs;
-  struct Item {
-    uint32_t chrom, start, end;
-    float v;
-  };
-  std::vector<Item> items;  // what the zoom levels summarise
-  items.reserve(rows.size());
-  uint64_t covered = 0;
-  double mn = 0, mx = 0, sum = 0, sumsq = 0;
-  bool any = false;
-  size_t i = 0;
-  while (i < rows.size()) {
-    const int32_t ref = rows[i].ref_id;
-    size_t j = i;
-    while (j < rows.size() && rows[j].ref_id == ref) j++;
-    if (keep[ref]) {
-      for (size_t s0 = i; s0 < j; s0 += ITEMS_PER_SLOT) {
-        const size_t s1 = std::min(j, s0 + ITEMS_PER_SLOT);
-        Section sec;
-        sec.chrom = dense[ref];
-        sec.offset = b.d.size();
-        if (rows[s0].start == 0 || rows[s1 - 1].stop - 1 > 0xffffffffull) fail("interval out of range for BigWig");
-        sec.start = (uint32_t)(rows[s0].start - 1);
-        sec.end = (uint32_t)(rows[s1 - 1].stop - 1);
-        b.u32(sec.chrom), b.u32(sec.start), b.u32(sec.end);
-        b.u32(0), b.u32(0);
-        b.u8(1), b.u8(0);
-        b.u16((uint16_t)(s1 - s0));
-        for (size_t k = s0; k < s1; k++) {
-          const uint32_t st = (uint32_t)(rows[k].start - 1), en = (uint32_t)(rows[k].stop - 1);
-          const float v = (float)((double)rows[k].val * factor);
-          b.u32(st), b.u32(en), b.f32(v);
-          items.push_back(Item{dense[ref], st, en, v});
-          const double w = (double)(en - st), dv = (double)v;
-          covered += en - st;
-          sum += dv * w;
-          sumsq += dv * dv * w;
-          if (!any || dv < mn) mn = dv;
-          if (!any || dv > mx) mx = dv;
-          any = true;
-        }
-        sec.size = b.d.size() - sec.offset;
-        secs.push_back(sec);
-      }
-    }
-    i = j;
-  }
-  b.put_u64_at(data_off, secs.size());
-  const uint64_t index_off = b.d.size();
-  write_rtree(b, secs, index_off);
-  // Zoom levels (what bigtools / UCSC writers add for viewers): per level, every chromosome is cut into windows of
-  // `reduction` bases and each window that holds data gets one summary record (covered bases, min, max, sum, sum of
-  // squares); the first reduction is ~10x the mean item width, each further level 4x coarser, until a level is small.
-  struct ZoomHdr {
-    uint32_t reduction;
-    uint64_t data_off, index_off;
-  };
-  std::vector<ZoomHdr> zooms;
-  if (!items.empty()) {
-    uint64_t reduction = std::max<uint64_t>(10, covered / items.size() * 10);
-    for (uint32_t z = 0; z < MAX_ZOOM && reduction <= 0x7fffffffull; z++, reduction *= 4) {
-      struct Rec {
-        uint32_t chrom, start, end, valid;
-        float mn, mx, sum, sumsq;
-      };
-      std::vector<Rec> recs;
-      for (const Item &it : items) {
-        for (uint64_t w = it.start / reduction; w * reduction < it.end; w++) {  // windows the item overlaps
-          const uint32_t a = (uint32_t)std::max<uint64_t>(it.start, w * reduction), e = (uint32_t)std::min<uint64_t>(it.end, (w + 1) * reduction);
-          const float n = (float)(e - a);
-          if (!recs.empty() && recs.back().chrom == it.chrom && recs.back().start / reduction == w) {
-            Rec &r = recs.back();
-            r.end = e;
-            r.valid += e - a;
-            r.mn = std::min(r.mn, it.v);
-            r.mx = std::max(r.mx, it.v);
-            r.sum += it.v * n;
-            r.sumsq += it.v * it.v * n;
-          } else {
-            recs.push_back(Rec{it.chrom, a, e, e - a, it.v, it.v, it.v * n, it.v * it.v * n});
-          }
-        }
-      }
-      if (z > 0 && recs.size() < 64) break;  // coarse enough: a viewer reads the previous level in one go
-      ZoomHdr zh;
-      zh.reduction = (uint32_t)reduction;
-      zh.data_off = b.d.size();
-      b.u32((uint32_t)std::min<uint64_t>(recs.size(), 0xffffffffull));
-      std::vector<Section> zsecs;
-      for (size_t r0 = 0; r0 < recs.size();) {
-        size_t r1 = r0;
-        while (r1 < recs.size() && r1 - r0 < ITEMS_PER_SLOT && recs[r1].chrom == recs[r0].chrom) r1++;
-        Section sec;
-        sec.chrom = recs[r0].chrom;
-        sec.start = recs[r0].start;
-        sec.end = recs[r1 - 1].end;
-        sec.offset = b.d.size();
-        for (size_t k = r0; k < r1; k++) {
-          const Rec &r = recs[k];
-          b.u32(r.chrom), b.u32(r.start), b.u32(r.end), b.u32(r.valid);
-          b.f32(r.mn), b.f32(r.mx), b.f32(r.sum), b.f32(r.sumsq);
-        }
-        sec.size = b.d.size() - sec.offset;
-        zsecs.push_back(sec);
-        r0 = r1;
-      }
-      zh.index_off = b.d.size();
-      write_rtree(b, zsecs, zh.index_off);
-      zooms.push_back(zh);
-      if (recs.size() < 64) break;
-    }
-  }
-  // header
-  Buf hd;
-  hd.u32(0x888FFC26);
-  hd.u16(4);
-  hd.u16((uint16_t)zooms.size());
-  hd.u64(chrom_tree_off);
-  hd.u64(data_off);
-  hd.u64(index_off);
-  hd.u16(0), hd.u16(0);
-  hd.u64(0);
-  hd.u64(64 + MAX_ZOOM * 24);  // total summary offset: after the (reserved) zoom headers
-  hd.u32(0);   // uncompressBufSize: sections are stored raw
-  hd.u64(0);
-  for (uint32_t z = 0; z < MAX_ZOOM; z++) {
-    const bool on = z < zooms.size();
-    hd.u32(on ? zooms[z].reduction : 0), hd.u32(0);
-    hd.u64(on ? zooms[z].data_off : 0), hd.u64(on ? zooms[z].index_off : 0);
-  }
-  hd.u64(covered), hd.f64(mn), hd.f64(mx), hd.f64(sum), hd.f64(sumsq);
-  memcpy(b.d.data(), hd.d.data(), hd.d.size());
-  b.u32(0x888FFC26);  // trailing magic, as UCSC writers append
-  FILE *f = fopen(path.c_str(), "wb");
-  if (!f) fail("cannot create " + path);
-  size_t w = fwrite(b.d.data(), 1, b.d.size(), f);
-  if (fclose(f) != 0 || w != b.d.size()) fail("write error on " + path);
-}
+// ---- to_bigwig (coverage_analysis.rs:642-759): items, sections, zlib streams and zoom summaries are built on the device
+// (bigwig.cuh, Pileup::to_bigwig in engine.cpp); bigwig_layout.h holds the host-side file layout (B+ tree, R-tree).
+void pileup_to_bigwig(Pileup &p, const std::string &path) { p.to_bigwig(path); }
 
 // ---- MultiBamPileup::to_tsv (coverage_analysis.rs:783-864), intended semantics ------------------------------------
 void multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int n, const char *out) {

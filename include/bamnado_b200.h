@@ -97,7 +97,8 @@ bnd_pileup *bnd_pileup_create(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *f
 void bnd_pileup_destroy(bnd_pileup *p);
 /* to_bedgraph (coverage_analysis.rs:618-632) */
 int bnd_pileup_to_bedgraph(bnd_pileup *p, const char *out_path);
-/* to_bigwig (coverage_analysis.rs:642-759); BigWig encoding runs on the host */
+/* to_bigwig (coverage_analysis.rs:642-759, replaces the bigtools writer at :748-755): items, 1 024-item sections, one zlib
+ * stream per section and the zoom summaries are built on the device; the host lays out header, chromosome tree and R-trees */
 int bnd_pileup_to_bigwig(bnd_pileup *p, const char *out_path);
 /* pileup_chromosome (coverage_analysis.rs:337-430): runs of one contig; unknown contig -> BND_ERR_NOT_FOUND */
 int bnd_pileup_chromosome(bnd_pileup *p, const char *chrom, bnd_run **runs, uint64_t *n_runs);

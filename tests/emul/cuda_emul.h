@@ -198,6 +198,20 @@ inline void __threadfence() {}
 inline void __threadfence_block() {}
 
 // ---- integer intrinsics ----------------------------------------------------------------------------------------
+inline unsigned __float_as_uint(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+// round-to-nearest single operations (the emulator build uses -ffp-contract=off semantics: separate statements)
+inline float __fmul_rn(float a, float b) {
+  volatile float r = a * b;
+  return r;
+}
+inline float __fadd_rn(float a, float b) {
+  volatile float r = a + b;
+  return r;
+}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

@@ -82,6 +82,38 @@ def test_bigwig_ignore_scaffold_and_large(backend, oracle, tmp_path, make_bam):
     assert bw["intervals"] == exp
 
 
+def test_bigwig_sections_are_zlib_streams_written_on_the_device(backend, oracle, tmp_path, make_bam, monkeypatch):
+    # every data / zoom section is one zlib stream (fixed-Huffman DEFLATE block + Adler-32, bigwig.cuh): Python's zlib accepts
+    # each of them (the reader inflates all sections), the header's uncompressBufSize bounds every inflated section, the
+    # streams are smaller than the raw sections, and the stored-raw mode holds the same rows
+    import struct
+    import zlib
+
+    bam = make_bam("pe", "--pairs", 20000, "--odd")
+    pile, filt = dict(bam_path=bam, bin_size=50, norm="cpm"), CLI_FILTER
+    a, b = tmp_path / "z.bw", tmp_path / "raw.bw"
+    with backend.pileup(pile, filt) as h:
+        h.to_bigwig(a)
+    monkeypatch.setenv("BND_BIGWIG_COMPRESS", "0")
+    with backend.pileup(pile, filt) as h:
+        h.to_bigwig(b)
+    monkeypatch.delenv("BND_BIGWIG_COMPRESS")
+    za, zb = read_bigwig(a), read_bigwig(b)
+    assert za["intervals"] == zb["intervals"] and len(za["intervals"]) > 10000
+    assert [z["records"] for z in za["zoom"]] == [z["records"] for z in zb["zoom"]]
+    da = open(a, "rb").read()
+    ubuf = struct.unpack_from("<I", da, 52)[0]
+    assert ubuf >= 24 + 12 * min(1024, len(za["intervals"])) and struct.unpack_from("<I", open(b, "rb").read(), 52)[0] == 0
+    assert a.stat().st_size < 0.75 * b.stat().st_size
+    # a stream cut out of the file by hand: header bytes 0x78 0x9c, one final fixed-Huffman block
+    index_off = struct.unpack_from("<Q", da, 24)[0]
+    data_off = struct.unpack_from("<Q", da, 16)[0]
+    assert da[data_off + 8: data_off + 10] == b"\x78\x9c" and (da[data_off + 10] & 7) == 3
+    d = zlib.decompressobj()
+    first = d.decompress(da[data_off + 8: index_off])
+    assert d.eof and len(first) <= ubuf and struct.unpack_from("<B", first, 20)[0] == 1
+
+
 def _rows(path):
     lines = open(path).read().splitlines()
     return lines[0], sorted(lines[1:])
