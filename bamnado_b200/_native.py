@@ -30,7 +30,7 @@ EXPORTS = [
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
     "bnd_pileup_timings", "bnd_pileup_shape", "bnd_pileup_format_bedgraph", "bnd_pileup_write_bedgraph_pieces", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
-    "bnd_multi_change_flags", "bnd_multi_compact", "bnd_pileup_refs", "bnd_collapse_bedgraph",
+    "bnd_multi_change_bits", "bnd_multi_or_bits", "bnd_multi_compact_column", "bnd_multi_format_tsv", "bnd_multi_write_tsv_pieces", "bnd_pileup_refs", "bnd_collapse_bedgraph",
     "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
 ]
 
@@ -155,8 +155,11 @@ class Native:
                                                 C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_uint64)]
         L.bnd_multi_to_tsv.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg), C.c_int32, C.c_char_p]
         L.bnd_multi_prepare.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-        L.bnd_multi_change_flags.argtypes = [C.c_void_p, C.c_void_p]
-        L.bnd_multi_compact.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(Run)), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
+        L.bnd_multi_change_bits.argtypes = [C.c_void_p, C.c_void_p]
+        L.bnd_multi_or_bits.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
+        L.bnd_multi_compact_column.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+        L.bnd_multi_format_tsv.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]
+        L.bnd_multi_write_tsv_pieces.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
         L.bnd_pileup_refs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
         L.bnd_collapse_bedgraph.argtypes = [C.c_char_p, C.c_char_p]
         L.bnd_scale_factor.restype = C.c_double
@@ -219,6 +222,10 @@ class Native:
         arr = np.ctypeslib.as_array(out, shape=(n.value,)).copy() if n.value else np.zeros(0, np.float32)
         self.L.bnd_free(out)
         return arr
+
+    def multi_or_bits(self, device: int, dst_ptr: int, src_ptr: int, n_src: int, n_words: int):
+        """dst[w] = OR over n_src masks of n_words u32 laid out back to back at src (device pointers; dst may alias mask 0)."""
+        self.check(self.L.bnd_multi_or_bits(device, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), n_src, n_words))
 
     def multi_to_tsv(self, pileups: list, filters: list, out_path):
         n = len(pileups)
@@ -366,15 +373,26 @@ class PileupHandle:
         self.n.check(self.n.L.bnd_multi_prepare(self.h, C.byref(n)))
         return n.value
 
-    def multi_change_flags(self, dev_ptr: int):
-        self.n.check(self.n.L.bnd_multi_change_flags(self.h, C.c_void_p(dev_ptr)))
+    def multi_change_bits(self, dev_ptr: int):
+        """dev_ptr: ceil(n_bins / 32) u32 words of device memory; bit i = bin i opens a new row for this BAM."""
+        self.n.check(self.n.L.bnd_multi_change_bits(self.h, C.c_void_p(dev_ptr)))
 
-    def multi_compact(self, dev_ptr: int):
-        ptr, vals, n = C.POINTER(Run)(), C.POINTER(C.c_uint32)(), C.c_uint64()
-        self.n.check(self.n.L.bnd_multi_compact(self.h, C.c_void_p(dev_ptr), C.byref(ptr), C.byref(vals), C.byref(n)))
-        v = np.ctypeslib.as_array(vals, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
-        self.n.L.bnd_free(vals)
-        return self._rows(ptr, n.value), v
+    def multi_compact_column(self, dev_bits_ptr: int):
+        """-> (n_rows, device pointer of this BAM's u32 counts at the shared row heads; owned by the handle)."""
+        n, vals = C.c_uint64(), C.c_void_p()
+        self.n.check(self.n.L.bnd_multi_compact_column(self.h, C.c_void_p(dev_bits_ptr), C.byref(n), C.byref(vals)))
+        return n.value, vals.value or 0
+
+    def multi_format_tsv(self, dev_cols_ptr: int, col_stride: int, n_cols: int, row_lo: int, row_hi: int) -> list:
+        names, _ = self.refs()
+        sizes = (C.c_uint64 * max(len(names), 1))()
+        self.n.check(self.n.L.bnd_multi_format_tsv(self.h, C.c_void_p(dev_cols_ptr), col_stride, n_cols, row_lo, row_hi, sizes, len(names)))
+        return [int(sizes[i]) for i in range(len(names))]
+
+    def multi_write_tsv_pieces(self, path, header: str, tables: list, rank: int):
+        world, n_ref = len(tables), len(tables[0])
+        flat = (C.c_uint64 * max(world * n_ref, 1))(*[v for t in tables for v in t])
+        self.n.check(self.n.L.bnd_multi_write_tsv_pieces(self.h, _b(path), header.encode(), flat, world, rank))
 
     def timings(self) -> dict:
         ms = (C.c_double * 8)()

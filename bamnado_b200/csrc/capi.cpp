@@ -201,19 +201,30 @@ int bnd_bin_counts(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, in
 int bnd_multi_prepare(bnd_pileup *p, uint64_t *n_bins) {
   return guarded([&] { *n_bins = P(p)->multi_prepare(); });
 }
-int bnd_multi_change_flags(bnd_pileup *p, void *dev_flags) {
-  return guarded([&] { P(p)->multi_change_flags((uint8_t *)dev_flags); });
+int bnd_multi_change_bits(bnd_pileup *p, void *dev_bits) {
+  return guarded([&] { P(p)->multi_change_bits((uint32_t *)dev_bits); });
 }
-int bnd_multi_compact(bnd_pileup *p, const void *dev_flags, bnd_run **rows, uint32_t **vals, uint64_t *n_rows) {
+int bnd_multi_or_bits(int32_t device, void *dev_dst, const void *dev_src, uint32_t n_src, uint64_t n_words) {
+  return guarded([&] { bnd::Pileup::multi_or_bits(device, (uint32_t *)dev_dst, (const uint32_t *)dev_src, n_src, n_words); });
+}
+int bnd_multi_compact_column(bnd_pileup *p, const void *dev_bits, uint64_t *n_rows, const void **dev_vals) {
   return guarded([&] {
-    std::vector<bnd::RunRow> r;
-    std::vector<uint32_t> v;
-    P(p)->multi_compact((const uint8_t *)dev_flags, r, v);
-    rows_out(r, rows, n_rows);
-    *vals = (uint32_t *)malloc(std::max<size_t>(v.size(), 1) * sizeof(uint32_t));
-    if (!*vals) throw std::bad_alloc();
-    if (!v.empty()) memcpy(*vals, v.data(), v.size() * sizeof(uint32_t));
+    const uint32_t *v = nullptr;
+    *n_rows = P(p)->multi_compact_column((const uint32_t *)dev_bits, &v);
+    if (dev_vals) *dev_vals = v;
   });
+}
+int bnd_multi_format_tsv(bnd_pileup *p, const void *dev_cols, uint64_t col_stride, int32_t n_cols, uint64_t row_lo, uint64_t row_hi,
+                         uint64_t *bytes_per_ref, uint64_t n_refs) {
+  return guarded([&] {
+    std::vector<uint64_t> v;
+    P(p)->multi_format_tsv((const uint32_t *)dev_cols, col_stride, n_cols, row_lo, row_hi, v);
+    if (v.size() != n_refs) bnd::fail("n_refs does not match the BAM header", bnd::ERR_INVALID);
+    for (size_t i = 0; i < v.size(); i++) bytes_per_ref[i] = v[i];
+  });
+}
+int bnd_multi_write_tsv_pieces(bnd_pileup *p, const char *out_path, const char *header, const uint64_t *bytes_all, int32_t world, int32_t rank) {
+  return guarded([&] { P(p)->multi_write_tsv_pieces(out_path, header, bytes_all, world, rank); });
 }
 
 int bnd_collapse_bedgraph(const char *in_path, const char *out_path) {

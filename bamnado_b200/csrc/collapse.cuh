@@ -80,25 +80,44 @@ __global__ void __launch_bounds__(COL_THREADS) bdg_emit_kernel(BdgArgs a) {
 }
 
 // ---- multi-BAM equal-bin collapse --------------------------------------------------------------------------------
-__device__ __forceinline__ bool multi_is_head(const MultiArgs &a, uint64_t i, bool ref_start) {
-  if (a.flags) return a.flags[i] != 0;
-  if (ref_start) return true;
-  for (int b = 0; b < a.n_bams; b++)
-    if (a.counts[b][i] != a.counts[b][i - 1]) return true;
-  return false;
-}
-
 __device__ __forceinline__ bool bin_is_ref_start(const GeomDev &g, uint64_t gbin) {
   int32_t r = ref_of_bin(g, gbin);
   return __ldg(g.ref_first_bin + r) == gbin;
 }
 
-// per-bin head flags of the BAMs held by this rank; ranks OR them together (all-reduce MAX) to get the shared run heads
-__global__ void __launch_bounds__(COL_THREADS) multi_flags_kernel(MultiArgs a) {
-  for (uint64_t i = blockIdx.x * (uint64_t)COL_THREADS + threadIdx.x; i < a.n_bins; i += (uint64_t)gridDim.x * COL_THREADS) {
-    bool h = i == 0 || bin_is_ref_start(a.g, i + a.g.bin_lo);
-    for (int b = 0; b < a.n_bams && !h; b++) h = a.counts[b][i] != a.counts[b][i - 1];
-    a.flags_out[i] = h ? 1 : 0;
+__device__ __forceinline__ bool multi_local_head(const MultiArgs &a, uint64_t i) {
+  if (i == 0 || bin_is_ref_start(a.g, i + a.g.bin_lo)) return true;
+  for (int b = 0; b < a.n_bams; b++)
+    if (a.counts[b][i] != a.counts[b][i - 1]) return true;
+  return false;
+}
+
+__device__ __forceinline__ bool multi_is_head(const MultiArgs &a, uint64_t i) {
+  if (a.bits) return (a.bits[i >> 5] >> (i & 31u)) & 1u;
+  return multi_local_head(a, i);
+}
+
+// Head flags of the BAMs held by this rank, one bit per bin (a warp ballot packs 32 bins into a word).  With one BAM per
+// rank the masks of all ranks are OR-ed (multi_or_kernel over the gathered masks) to get the shared run heads: 1 bit per
+// bin on the wire instead of a byte (hg38 at bin 1: 387 MB instead of 3.1 GB).
+__global__ void __launch_bounds__(COL_THREADS) multi_bits_kernel(MultiArgs a) {
+  const uint64_t n_words = (a.n_bins + 31) / 32;
+  const uint64_t warp = (blockIdx.x * (uint64_t)COL_THREADS + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * COL_THREADS) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint64_t w = warp; w < n_words; w += n_warps) {
+    const uint64_t i = w * 32 + lane;
+    const bool h = i < a.n_bins && multi_local_head(a, i);
+    const unsigned m = __ballot_sync(0xffffffffu, h);
+    if (lane == 0) a.bits_out[w] = m;
+  }
+}
+
+// dst[w] = OR over the n_src masks laid out back to back (src[k * n_words + w]); dst may alias mask 0
+__global__ void __launch_bounds__(COL_THREADS) multi_or_kernel(uint32_t *dst, const uint32_t *src, uint32_t n_src, uint64_t n_words) {
+  for (uint64_t w = blockIdx.x * (uint64_t)COL_THREADS + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * COL_THREADS) {
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < n_src; k++) v |= src[(uint64_t)k * n_words + w];
+    dst[w] = v;
   }
 }
 
@@ -106,7 +125,7 @@ __global__ void __launch_bounds__(COL_THREADS) multi_count_kernel(MultiArgs a) {
   __shared__ uint64_t scratch[COL_THREADS / 32 + 1];
   for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     uint64_t i = (uint64_t)t * COL_THREADS + threadIdx.x;
-    uint64_t h = i < a.n_bins && multi_is_head(a, i, i == 0 || bin_is_ref_start(a.g, i + a.g.bin_lo)) ? 1 : 0, total;
+    uint64_t h = i < a.n_bins && multi_is_head(a, i) ? 1 : 0, total;
     block_exclusive_scan<COL_THREADS, uint64_t>(h, scratch, total);
     if (threadIdx.x == 0) a.tile_heads[t] = total;
   }
@@ -117,7 +136,7 @@ __global__ void __launch_bounds__(COL_THREADS) multi_emit_kernel(MultiArgs a) {
   for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     uint64_t i = (uint64_t)t * COL_THREADS + threadIdx.x;
     bool in = i < a.n_bins;
-    uint64_t h = in && multi_is_head(a, i, i == 0 || bin_is_ref_start(a.g, i + a.g.bin_lo)) ? 1 : 0, total;
+    uint64_t h = in && multi_is_head(a, i) ? 1 : 0, total;
     uint64_t ex = block_exclusive_scan<COL_THREADS, uint64_t>(h, scratch, total);
     if (h) {
       uint64_t j = a.tile_heads[t] + ex;
@@ -139,6 +158,72 @@ __global__ void __launch_bounds__(256) multi_rows_kernel(RunArgs a) {
     run_coords(a.g, nx - 1, nx, ref2, start_unused, r.stop);
     r.val = 0;
     a.rows[j] = r;
+  }
+}
+
+// ---- TSV text of the multi-BAM table on the device ---------------------------------------------------------------------
+__device__ __forceinline__ void multi_row_coords(const GeomDev &g, uint64_t gb, uint64_t nx, int32_t &ref, uint64_t &start, uint64_t &stop) {
+  uint64_t unused;
+  int32_t ref2;
+  run_coords(g, gb, gb + 1, ref, start, unused);
+  run_coords(g, nx - 1, nx, ref2, unused, stop);
+}
+
+__global__ void __launch_bounds__(TEXT_THREADS) multi_text_len_kernel(MultiTextArgs a) {
+  __shared__ uint64_t s_part[TEXT_THREADS / 32];
+  const int tid = (int)threadIdx.x;
+  for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const uint64_t k = (uint64_t)t * TEXT_THREADS + (uint64_t)tid;  // row inside the slice
+    uint32_t len = 0;
+    if (k < a.n_rows) {
+      const uint64_t j = a.row_lo + k;
+      const uint64_t gb = a.run_bin[j], nx = j + 1 < a.n_runs ? a.run_bin[j + 1] : a.g.bin_hi;
+      int32_t ref;
+      uint64_t start, stop;
+      multi_row_coords(a.g, gb, nx, ref, start, stop);
+      len = (a.name_off[ref + 1] - a.name_off[ref]) + dec_len(start) + dec_len(stop) + 3;
+      for (int c = 0; c < a.n_cols; c++) len += 1 + dec_len(a.vals[(uint64_t)c * a.stride + k]);
+      a.row_len[k] = (uint16_t)len;
+    }
+    uint64_t s = warp_sum((uint64_t)len);
+    if ((tid & 31) == 0) s_part[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+      uint64_t S = 0;
+      for (int w = 0; w < TEXT_THREADS / 32; w++) S += s_part[w];
+      a.tile_off[t] = S;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(TEXT_THREADS) multi_text_write_kernel(MultiTextArgs a) {
+  __shared__ uint64_t scratch[TEXT_THREADS / 32 + 1];
+  const int tid = (int)threadIdx.x;
+  for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const uint64_t k = (uint64_t)t * TEXT_THREADS + (uint64_t)tid;
+    uint64_t len = k < a.n_rows ? a.row_len[k] : 0, total;
+    const uint64_t off = a.tile_off[t] + block_exclusive_scan<TEXT_THREADS, uint64_t>(len, scratch, total);
+    if (k < a.n_rows) {
+      const uint64_t j = a.row_lo + k;
+      const uint64_t gb = a.run_bin[j], nx = j + 1 < a.n_runs ? a.run_bin[j + 1] : a.g.bin_hi;
+      int32_t ref;
+      uint64_t start, stop;
+      multi_row_coords(a.g, gb, nx, ref, start, stop);
+      // first row of a reference inside this slice: where that reference's text begins (a reference's first bin is always a head)
+      if (k == 0 || gb == tmax<uint64_t>(__ldg(a.g.ref_first_bin + ref), a.g.bin_lo)) a.ref_text_off[ref] = off;
+      char *p = a.text + off;
+      for (uint32_t q = a.name_off[ref]; q < a.name_off[ref + 1]; q++) *p++ = a.names[q];
+      *p++ = '\t';
+      p = put_dec(p, start);
+      *p++ = '\t';
+      p = put_dec(p, stop);
+      for (int c = 0; c < a.n_cols; c++) {
+        *p++ = '\t';
+        p = put_dec(p, a.vals[(uint64_t)c * a.stride + k]);
+      }
+      *p++ = '\n';
+    }
   }
 }
 

@@ -379,6 +379,29 @@ struct Pileup::TextJob {
   }
 };
 
+// Unmaps finished output mappings off the caller's critical path.  The threads are joined when the next job starts and
+// when the library is unloaded, so no thread of ours outlives the code it runs.
+namespace {
+struct Unmapper {
+  std::mutex mu;
+  std::vector<std::thread> threads;
+  void reap() {
+    std::vector<std::thread> t;
+    {
+      std::lock_guard<std::mutex> g(mu);
+      t.swap(threads);
+    }
+    for (auto &x : t)
+      if (x.joinable()) x.join();
+  }
+  void submit(char *map, uint64_t len) {
+    std::lock_guard<std::mutex> g(mu);
+    threads.emplace_back([map, len] { munmap(map, len); });
+  }
+  ~Unmapper() { reap(); }
+} g_unmapper;
+}  // namespace
+
 // ---- Pileup::Impl: device state of one pileup ------------------------------------------------------------------------
 struct Pileup::Impl {
   DeviceCtx *ctx = nullptr;
@@ -393,8 +416,8 @@ struct Pileup::Impl {
   // accumulators
   DevBuf d_diff, d_stats, d_probe, d_err;
   // finalize products
-  DevBuf d_tile_sum, d_tile_heads, d_run_bin, d_run_val, d_counts, d_fs;
-  uint64_t n_runs = 0;
+  DevBuf d_tile_sum, d_tile_heads, d_run_bin, d_run_val, d_counts, d_fs, d_multi_vals;
+  uint64_t n_runs = 0, multi_rows = 0;
   uint32_t max_val = 0;
   uint64_t fin_bins = 0;
   // device text between format_bedgraph and write_bedgraph_pieces
@@ -407,7 +430,7 @@ struct Pileup::Impl {
     if (fd >= 0) close(fd);
     for (DevBuf *b : {&d_ref_len, &d_first_bin, &d_first_chunk, &d_rg, &d_tagv, &d_bl_off, &d_bl_starts, &d_bl_stops, &d_bc_table,
                       &d_bc_off, &d_bc_pool, &d_diff, &d_stats, &d_probe, &d_err, &d_tile_sum, &d_tile_heads, &d_run_bin, &d_run_val,
-                      &d_counts, &d_fs, &d_resident})
+                      &d_counts, &d_fs, &d_multi_vals, &d_resident})
       b->release();
   }
 };
@@ -1264,9 +1287,46 @@ bool Pileup::is_paired_end() {
 }
 
 // ---- MultiBamPileup ---------------------------------------------------------------------------------------------------------
-void Pileup::multi_collapse(std::vector<Pileup *> &bams, std::vector<RunRow> &rows, std::vector<uint32_t> &vals) {
-  rows.clear();
-  vals.clear();
+namespace {
+// Shared run heads of the table described by `a` (its own head test, or the precomputed bit mask) -> run_bin[n_rows] and the
+// counts of every BAM of `a` at those heads -> vals[n_bams][n_rows].  Returns n_rows.
+uint64_t multi_emit_table(DeviceCtx &ctx, MultiArgs &a, DevBuf &run_bin, DevBuf &vals, cudaStream_t st) {
+  const uint64_t n_tiles64 = (a.n_bins + 255) / 256;
+  if (n_tiles64 > 0xffffffffull) fail("too many bins for one shard");
+  a.n_tiles = (uint32_t)n_tiles64;
+  if (a.n_bins == 0) return 0;
+  DevBuf d_tiles, d_total;
+  unsigned long long n_runs = 0;
+  try {
+    d_tiles.ensure((size_t)a.n_tiles * 8 + 16);
+    d_total.ensure(16);
+    a.tile_heads = d_tiles.as<uint64_t>();
+    CU(launch_multi_count(a, ctx.sm_count, st));
+    CU(launch_u64_scan(a.tile_heads, a.n_tiles, d_total.as<unsigned long long>(), st));
+    CU(cudaMemcpyAsync(&n_runs, d_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    run_bin.ensure(n_runs * 8 + 16);
+    vals.ensure(n_runs * 4 * (size_t)a.n_bams + 16);
+    a.run_bin = run_bin.as<uint64_t>();
+    a.out_vals = vals.as<uint32_t>();
+    a.n_runs_cap = n_runs;
+    CU(launch_multi_emit(a, ctx.sm_count, st));
+    CU(cudaStreamSynchronize(st));
+  } catch (...) {
+    d_tiles.release();
+    d_total.release();
+    throw;
+  }
+  d_tiles.release();
+  d_total.release();
+  return n_runs;
+}
+}  // namespace
+
+// MultiBamPileup::to_tsv with every BAM on this device (coverage_analysis.rs:783-864): per-BAM raw counts (one u32 per bin stays
+// in HBM for every BAM), shared run heads, and the TSV text itself are produced on the device; the host writes the header line
+// and moves the per-reference pieces into (chrom byte string, start) order like collapse_equal_bins sorts them.
+void Pileup::multi_to_tsv(std::vector<Pileup *> &bams, const std::string &path) {
   if (bams.empty()) fail("At least one BAM pileup is required", ERR_INVALID);
   if ((int)bams.size() > MULTI_MAX_BAMS) fail("too many BAM files for one multi-bam-coverage call", ERR_INVALID);
   Pileup &first = *bams[0];
@@ -1277,7 +1337,6 @@ void Pileup::multi_collapse(std::vector<Pileup *> &bams, std::vector<RunRow> &ro
       fail("multi-bam-coverage on the B200 path needs BAMs with the same reference dictionary and chunk length");
     if (b->im_->ctx != first.im_->ctx) fail("all BAMs of one multi-bam-coverage call must use the same device", ERR_INVALID);
   }
-  // per-BAM raw counts; the scan runs in place so every BAM keeps one u32 per bin in HBM
   MultiArgs a{};
   a.n_bams = (int)bams.size();
   for (size_t i = 0; i < bams.size(); i++) {
@@ -1286,55 +1345,21 @@ void Pileup::multi_collapse(std::vector<Pileup *> &bams, std::vector<RunRow> &ro
     b.finalize_range(true, false);
     a.counts[i] = b.im_->d_counts.as<uint32_t>();
   }
-  DeviceCtx &ctx = *first.im_->ctx;
-  std::lock_guard<std::mutex> lock(ctx.mu);
-  CU(cudaSetDevice(ctx.device));
-  cudaStream_t st = ctx.sets[0].stream;
-  a.g = first.im_->gdev;
-  a.n_bins = a.g.bin_hi - a.g.bin_lo;
-  const uint64_t n_tiles64 = (a.n_bins + 255) / 256;
-  if (n_tiles64 > 0xffffffffull) fail("too many bins for one shard");
-  a.n_tiles = (uint32_t)n_tiles64;
-  if (a.n_bins == 0) return;
-  DevBuf d_tiles, d_total, d_run_bin, d_vals, d_rows;
-  auto release = [&] {
-    for (DevBuf *b : {&d_tiles, &d_total, &d_run_bin, &d_vals, &d_rows}) b->release();
-  };
-  try {
-    d_tiles.ensure((size_t)a.n_tiles * 8 + 16);
-    d_total.ensure(16);
-    a.tile_heads = d_tiles.as<uint64_t>();
-    CU(launch_multi_count(a, ctx.sm_count, st));
-    CU(launch_u64_scan(a.tile_heads, a.n_tiles, d_total.as<unsigned long long>(), st));
-    unsigned long long n_runs = 0;
-    CU(cudaMemcpyAsync(&n_runs, d_total.p, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    d_run_bin.ensure(n_runs * 8 + 16);
-    d_vals.ensure(n_runs * 4 * bams.size() + 16);
-    d_rows.ensure(n_runs * sizeof(RunRow) + 16);
-    a.run_bin = d_run_bin.as<uint64_t>();
-    a.out_vals = d_vals.as<uint32_t>();
-    a.n_runs_cap = n_runs;
-    CU(launch_multi_emit(a, ctx.sm_count, st));
-    RunArgs ra{};
-    ra.run_bin = a.run_bin;
-    ra.run_val = nullptr;
-    ra.n_runs = n_runs;
-    ra.g = a.g;
-    ra.rows = d_rows.as<RunRow>();
-    CU(launch_multi_rows(ra, ctx.sm_count, st));
-    rows.resize(n_runs);
-    vals.resize(n_runs * bams.size());
-    if (n_runs) {
-      CU(cudaMemcpyAsync(rows.data(), d_rows.p, n_runs * sizeof(RunRow), cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(vals.data(), d_vals.p, n_runs * 4 * bams.size(), cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaStreamSynchronize(st));
-  } catch (...) {
-    release();
-    throw;
+  std::string header = "chrom\tstart\tend";
+  for (Pileup *b : bams) header += "\t" + b->bam_path_;
+  header.push_back('\n');
+  Impl &im = *first.im_;
+  DeviceCtx &ctx = *im.ctx;
+  std::vector<uint64_t> mine;
+  {
+    std::lock_guard<std::mutex> lock(ctx.mu);
+    CU(cudaSetDevice(ctx.device));
+    a.g = im.gdev;
+    a.n_bins = a.g.bin_hi - a.g.bin_lo;
+    im.multi_rows = multi_emit_table(ctx, a, im.d_run_bin, im.d_multi_vals, ctx.sets[0].stream);
   }
-  release();
+  first.multi_format_tsv(im.d_multi_vals.as<uint32_t>(), im.multi_rows, (int)bams.size(), 0, im.multi_rows, mine);
+  first.multi_write_tsv_pieces(path, header.c_str(), mine.data(), 1, 0);
 }
 
 // bin_counts::count_bins (bamnado/src/bin_counts.rs:100-289).  Every sample runs the ordinary pile-up without collapsing
@@ -1447,10 +1472,17 @@ uint64_t Pileup::multi_prepare() {
   return im_->gdev.bin_hi - im_->gdev.bin_lo;
 }
 
-void Pileup::multi_change_flags(uint8_t *dev_flags) {
+// ---- one BAM per rank --------------------------------------------------------------------------------------------
+// 1. multi_prepare: pile-up + dense raw counts;  2. multi_change_bits: "my count changes here", one BIT per bin;  3. the caller
+// gathers the masks of all ranks (NCCL all-gather over NVLink; hg38 at bin 1: 387 MB per rank) and multi_or_bits folds them into
+// the shared run heads;  4. multi_compact_column: this rank's counts at those heads stay on the device;  5. the caller exchanges
+// column slices (all-to-all: every rank receives rows [k n / world, (k + 1) n / world) of every column);  6. multi_format_tsv
+// writes the text of that slice on the device;  7. after an all-gather of the per-reference byte counts every rank fills its
+// pieces of the one TSV (multi_write_tsv_pieces).
+void Pileup::multi_change_bits(uint32_t *dev_bits) {
   Impl &im = *im_;
   DeviceCtx &ctx = *im.ctx;
-  if (!finalized_ || !im.d_counts.p) fail("multi_change_flags called before multi_prepare", ERR_INVALID);
+  if (!finalized_ || !im.d_counts.p) fail("multi_change_bits called before multi_prepare", ERR_INVALID);
   std::lock_guard<std::mutex> lock(ctx.mu);
   CU(cudaSetDevice(ctx.device));
   MultiArgs a{};
@@ -1458,66 +1490,137 @@ void Pileup::multi_change_flags(uint8_t *dev_flags) {
   a.counts[0] = im.d_counts.as<uint32_t>();
   a.g = im.gdev;
   a.n_bins = a.g.bin_hi - a.g.bin_lo;
-  a.flags_out = dev_flags;
-  CU(launch_multi_flags(a, ctx.sm_count, ctx.sets[0].stream));
+  a.bits_out = dev_bits;
+  CU(launch_multi_bits(a, ctx.sm_count, ctx.sets[0].stream));
   CU(cudaStreamSynchronize(ctx.sets[0].stream));
 }
 
-void Pileup::multi_compact(const uint8_t *dev_flags, std::vector<RunRow> &rows, std::vector<uint32_t> &vals) {
+void Pileup::multi_or_bits(int device, uint32_t *dst, const uint32_t *src, uint32_t n_src, uint64_t n_words) {
+  DeviceCtx &ctx = ctx_for(device);
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(launch_multi_or(dst, src, n_src, n_words, ctx.sm_count, ctx.sets[0].stream));
+  CU(cudaStreamSynchronize(ctx.sets[0].stream));
+}
+
+uint64_t Pileup::multi_compact_column(const uint32_t *dev_bits, const uint32_t **dev_vals) {
   Impl &im = *im_;
   DeviceCtx &ctx = *im.ctx;
-  if (!finalized_ || !im.d_counts.p) fail("multi_compact called before multi_prepare", ERR_INVALID);
-  rows.clear();
-  vals.clear();
+  if (!finalized_ || !im.d_counts.p) fail("multi_compact_column called before multi_prepare", ERR_INVALID);
   std::lock_guard<std::mutex> lock(ctx.mu);
   CU(cudaSetDevice(ctx.device));
-  cudaStream_t st = ctx.sets[0].stream;
   MultiArgs a{};
   a.n_bams = 1;
   a.counts[0] = im.d_counts.as<uint32_t>();
   a.g = im.gdev;
   a.n_bins = a.g.bin_hi - a.g.bin_lo;
-  a.flags = dev_flags;
-  if (a.n_bins == 0) return;
-  a.n_tiles = (uint32_t)((a.n_bins + 255) / 256);
-  DevBuf d_tiles, d_total, d_run_bin, d_vals, d_rows;
-  auto release = [&] {
-    for (DevBuf *b : {&d_tiles, &d_total, &d_run_bin, &d_vals, &d_rows}) b->release();
-  };
+  a.bits = dev_bits;
+  im.multi_rows = multi_emit_table(ctx, a, im.d_run_bin, im.d_multi_vals, ctx.sets[0].stream);
+  if (dev_vals) *dev_vals = im.d_multi_vals.as<uint32_t>();
+  return im.multi_rows;
+}
+
+// TSV text of rows [row_lo, row_hi) of the shared table; dev_cols[c * stride + (row - row_lo)] is BAM c's count of that row.
+void Pileup::multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_cols, uint64_t row_lo, uint64_t row_hi, std::vector<uint64_t> &bytes_per_ref) {
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  const size_t n_ref = hdr_.names.size();
+  if (row_lo > row_hi || row_hi > im.multi_rows) fail("row slice outside the multi-BAM table", ERR_INVALID);
+  if (n_cols < 1 || n_cols > MULTI_MAX_BAMS) fail("bad column count", ERR_INVALID);
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  cudaStream_t st = ctx.sets[0].stream;
+  im.text_job.reset(new TextJob());
+  TextJob &job = *im.text_job;
+  job.span.assign(n_ref, {0, 0});
+  bytes_per_ref.assign(n_ref, 0);
+  const uint64_t n_rows = row_hi - row_lo;
+  if (n_rows == 0) return;
   try {
-    d_tiles.ensure((size_t)a.n_tiles * 8 + 16);
-    d_total.ensure(16);
-    a.tile_heads = d_tiles.as<uint64_t>();
-    CU(launch_multi_count(a, ctx.sm_count, st));
-    CU(launch_u64_scan(a.tile_heads, a.n_tiles, d_total.as<unsigned long long>(), st));
-    unsigned long long n_runs = 0;
-    CU(cudaMemcpyAsync(&n_runs, d_total.p, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    d_run_bin.ensure(n_runs * 8 + 16);
-    d_vals.ensure(n_runs * 4 + 16);
-    d_rows.ensure(n_runs * sizeof(RunRow) + 16);
-    a.run_bin = d_run_bin.as<uint64_t>();
-    a.out_vals = d_vals.as<uint32_t>();
-    a.n_runs_cap = n_runs;
-    CU(launch_multi_emit(a, ctx.sm_count, st));
-    RunArgs ra{};
-    ra.run_bin = a.run_bin;
-    ra.n_runs = n_runs;
-    ra.g = a.g;
-    ra.rows = d_rows.as<RunRow>();
-    CU(launch_multi_rows(ra, ctx.sm_count, st));
-    rows.resize(n_runs);
-    vals.resize(n_runs);
-    if (n_runs) {
-      CU(cudaMemcpyAsync(rows.data(), d_rows.p, n_runs * sizeof(RunRow), cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(vals.data(), d_vals.p, n_runs * 4, cudaMemcpyDeviceToHost, st));
+    std::string names;
+    std::vector<uint32_t> name_off(n_ref + 1, 0);
+    for (size_t r = 0; r < n_ref; r++) {
+      names += hdr_.names[r];
+      name_off[r + 1] = (uint32_t)names.size();
     }
+    upload(job.d_names, names.data(), names.size());
+    upload(job.d_name_off, name_off.data(), name_off.size());
+    const uint64_t n_tiles64 = (n_rows + TEXT_THREADS - 1) / TEXT_THREADS;
+    if (n_tiles64 > 0xffffffffull) fail("too many rows for one shard");
+    job.d_row_len.ensure(n_rows * 2 + 16);
+    job.d_tile_off.ensure(n_tiles64 * 8 + 16);
+    job.d_ref_off.ensure((n_ref + 1) * 8);
+    job.d_skip.ensure(16);  // total
+    CU(cudaMemsetAsync(job.d_ref_off.p, 0xff, (n_ref + 1) * 8, st));
+    MultiTextArgs a{};
+    a.run_bin = im.d_run_bin.as<uint64_t>();
+    a.n_runs = im.multi_rows;
+    a.row_lo = row_lo;
+    a.n_rows = n_rows;
+    a.vals = dev_cols;
+    a.stride = stride;
+    a.n_cols = n_cols;
+    a.g = im.gdev;
+    a.names = job.d_names.as<char>();
+    a.name_off = job.d_name_off.as<uint32_t>();
+    a.row_len = job.d_row_len.as<uint16_t>();
+    a.tile_off = job.d_tile_off.as<uint64_t>();
+    a.n_tiles = (uint32_t)n_tiles64;
+    a.ref_text_off = job.d_ref_off.as<uint64_t>();
+    CU(launch_multi_text_len(a, ctx.sm_count, st));
+    CU(launch_u64_scan(a.tile_off, a.n_tiles, job.d_skip.as<unsigned long long>(), st));
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, job.d_skip.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    job.nbytes = total;
+    job.d_text.ensure(job.nbytes + 16);
+    a.text = job.d_text.as<char>();
+    CU(launch_multi_text_write(a, ctx.sm_count, st));
+    std::vector<uint64_t> ref_off(n_ref + 1);
+    CU(cudaMemcpyAsync(ref_off.data(), job.d_ref_off.p, (n_ref + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint64_t next = job.nbytes;
+    for (size_t r = n_ref; r-- > 0;)
+      if (ref_off[r] != ~0ull) {
+        job.span[r] = {ref_off[r], next};
+        next = ref_off[r];
+      }
+    for (size_t r = 0; r < n_ref; r++) bytes_per_ref[r] = job.span[r].second - job.span[r].first;
   } catch (...) {
-    release();
+    im.text_job.reset();
     throw;
   }
-  release();
+}
+
+// Every rank fills its pieces of the one TSV: header line (written by rank 0), then the references in byte-string order and
+// inside a reference the row slices in rank order.  bytes_all is [world][n_refs].
+void Pileup::multi_write_tsv_pieces(const std::string &path, const char *header, const uint64_t *bytes_all, int world, int rank) {
+  Impl &im = *im_;
+  if (!im.text_job) fail("multi_write_tsv_pieces called before multi_format_tsv", ERR_INVALID);
+  if (world < 1 || rank < 0 || rank >= world || !bytes_all) fail("bad shard table", ERR_INVALID);
+  g_unmapper.reap();
+  std::lock_guard<std::mutex> lock(im.ctx->mu);
+  std::unique_ptr<TextJob> job = std::move(im.text_job);
+  const uint64_t base = header ? strlen(header) : 0;
+  const uint64_t total = place_pieces(*job, bytes_all, world, rank, base);
+  int fd = ::open(path.c_str(), O_RDWR | O_CREAT, 0644);
+  if (fd < 0) fail("cannot create " + path);
+  struct stat st;
+  if (fstat(fd, &st) != 0 || ((uint64_t)st.st_size != total && ftruncate(fd, (off_t)total) != 0)) {
+    close(fd);
+    fail("cannot size " + path);
+  }
+  if (rank == 0 && base) {
+    uint64_t done = 0;
+    while (done < base) {
+      ssize_t w = pwrite(fd, header + done, base - done, (off_t)done);
+      if (w <= 0) {
+        close(fd);
+        fail("write error on " + path);
+      }
+      done += (uint64_t)w;
+    }
+  }
+  write_pieces(*job, fd, path, total, 0, false);
 }
 
 // ---- collapse-bedgraph ------------------------------------------------------------------------------------------------------
@@ -1721,13 +1824,13 @@ void Pileup::format_text(TextJob &job) {
 // write_bedgraph sorts by (chrom as a byte string, start) (coverage_analysis.rs:63): the output is the references in name
 // order, and inside one reference the shards in rank order (a shard is a contiguous range of genomic chunks).
 // bytes_all[k * n_ref + r] = text bytes shard k holds for reference r.  Returns the size of the whole file.
-uint64_t Pileup::place_pieces(TextJob &job, const uint64_t *bytes_all, int world, int rank) const {
+uint64_t Pileup::place_pieces(TextJob &job, const uint64_t *bytes_all, int world, int rank, uint64_t base) const {
   const size_t n_ref = hdr_.names.size();
   std::vector<int> order(n_ref);
   for (size_t r = 0; r < n_ref; r++) order[r] = (int)r;
   std::sort(order.begin(), order.end(), [&](int x, int y) { return hdr_.names[x] < hdr_.names[y]; });
   job.pieces.clear();
-  uint64_t out_off = 0;
+  uint64_t out_off = base;
   for (int r : order)
     for (int k = 0; k < world; k++) {
       const uint64_t n = bytes_all[(size_t)k * n_ref + (size_t)r];
@@ -1848,29 +1951,6 @@ void Pileup::bedgraph_text(std::string &out) {
              [dst](const uint8_t *src, uint64_t len, uint64_t off) { memcpy(dst + off, src, len); });
   tm_.text_ms = now_ms() - t0;
 }
-
-// Unmaps finished output mappings off the caller's critical path.  The threads are joined when the next job starts and
-// when the library is unloaded, so no thread of ours outlives the code it runs.
-namespace {
-struct Unmapper {
-  std::mutex mu;
-  std::vector<std::thread> threads;
-  void reap() {
-    std::vector<std::thread> t;
-    {
-      std::lock_guard<std::mutex> g(mu);
-      t.swap(threads);
-    }
-    for (auto &x : t)
-      if (x.joinable()) x.join();
-  }
-  void submit(char *map, uint64_t len) {
-    std::lock_guard<std::mutex> g(mu);
-    threads.emplace_back([map, len] { munmap(map, len); });
-  }
-  ~Unmapper() { reap(); }
-} g_unmapper;
-}  // namespace
 
 // Fills this shard's pieces into the output file `fd` (size `total`; the first `prealloc` bytes already have pages) and
 // closes it.  Regular files: the writer threads memcpy into a shared mapping (parallel page-cache fills; pwrite would

@@ -63,10 +63,17 @@ class Pileup {
   // BamStats::is_paired_end (bam_utils.rs:564-582): any of the first ~1000 records carries the 0x1 flag
   bool is_paired_end();
   // MultiBamPileup (coverage_analysis.rs:783-848): raw per-bin counts of every BAM, collapsed where all samples agree
-  static void multi_collapse(std::vector<Pileup *> &bams, std::vector<RunRow> &rows, std::vector<uint32_t> &vals);
-  // one BAM per rank: raw dense counts stay on the device, the ranks OR their per-bin change flags together
-  // (NCCL all-reduce MAX over device memory owned by the caller), then every rank compacts its own column
+  // and written as TSV text formatted on the device
+  static void multi_to_tsv(std::vector<Pileup *> &bams, const std::string &path);
+  // one BAM per rank: raw dense counts stay on the device, every rank marks "my count changes here" with one bit per
+  // bin, the masks of all ranks are OR-ed (gathered over NVLink by the caller), every rank compacts its own column at the shared
+  // heads, receives its slice of rows of every column and formats + writes that slice of the one TSV
   uint64_t multi_prepare();
+  void multi_change_bits(uint32_t *dev_bits);
+  static void multi_or_bits(int device, uint32_t *dst, const uint32_t *src, uint32_t n_src, uint64_t n_words);
+  uint64_t multi_compact_column(const uint32_t *dev_bits, const uint32_t **dev_vals);
+  void multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_cols, uint64_t row_lo, uint64_t row_hi, std::vector<uint64_t> &bytes_per_ref);
+  void multi_write_tsv_pieces(const std::string &path, const char *header, const uint64_t *bytes_all, int world, int rank);
   // bin_counts::count_bins (bin_counts.rs:100-289): samples x bins matrix of raw counts on the grid shared by all BAMs
   struct BinCounts {
     uint64_t bin_size = 0, n_bins = 0;
@@ -77,8 +84,6 @@ class Pileup {
     std::vector<uint64_t> library_sizes;    // reads kept by each sample's filter (per read and chunk, like the pile-up)
   };
   static void count_bins(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int n_samples, BinCounts &out);
-  void multi_change_flags(uint8_t *dev_flags);
-  void multi_compact(const uint8_t *dev_flags, std::vector<RunRow> &rows, std::vector<uint32_t> &vals);
 
  private:
   struct Range {  // what part of the file / genome a pass covers
@@ -93,7 +98,7 @@ class Pileup {
   struct TextJob;
   std::unique_ptr<Impl> im_;
   void format_text(TextJob &job);
-  uint64_t place_pieces(TextJob &job, const uint64_t *bytes_all, int world, int rank) const;
+  uint64_t place_pieces(TextJob &job, const uint64_t *bytes_all, int world, int rank, uint64_t base = 0) const;
   void write_pieces(TextJob &job, int fd, const std::string &path, uint64_t total, uint64_t prealloc, bool truncate_at_end);
 
   void open();

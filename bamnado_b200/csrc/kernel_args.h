@@ -216,7 +216,7 @@ struct TextArgs {
   const uint8_t *ref_skip;   // [n_ref] 1 = drop rows of this reference (--ignore-scaffold)
   const char *score_text;    // [n_scores][SCORE_W]: byte 0 = length, then the text
   uint32_t n_scores;
-  uint16_t *row_len;         // [n_runs]
+  uint16_t *row_len;         // [n_rows]
   uint64_t *tile_off;        // [n_text_tiles] -> exclusive offsets after the scan
   uint32_t n_tiles;
   char *text;
@@ -251,8 +251,26 @@ struct MultiArgs {
   uint64_t *run_bin;
   uint32_t *out_vals;  // [n_bams][n_runs_cap]
   uint64_t n_runs_cap;
-  const uint8_t *flags;  // optional: precomputed head flags (OR-reduced over ranks when every rank holds one BAM)
-  uint8_t *flags_out;    // multi_flags_kernel output
+  const uint32_t *bits;  // optional: precomputed head flags, one bit per bin (OR-ed over ranks when every rank holds one BAM)
+  uint32_t *bits_out;    // multi_bits_kernel output: ceil(n_bins / 32) words
+};
+
+// TSV rows of MultiBamPileup::to_tsv formatted on the device: name \t start \t end (\t count)* \n
+struct MultiTextArgs {
+  const uint64_t *run_bin;   // [n_runs] head bin of every row of the table
+  uint64_t n_runs;
+  uint64_t row_lo, n_rows;   // the slice of rows formatted by this call: [row_lo, row_lo + n_rows)
+  const uint32_t *vals;      // [n_cols][stride]: counts of the slice's rows, one column per BAM
+  uint64_t stride;
+  int n_cols;
+  GeomDev g;
+  const char *names;         // concatenated reference names
+  const uint32_t *name_off;  // [n_ref + 1]
+  uint16_t *row_len;         // [n_rows]
+  uint64_t *tile_off;        // [n_tiles] -> exclusive offsets after the scan
+  uint32_t n_tiles;
+  char *text;
+  uint64_t *ref_text_off;    // [n_ref + 1] byte offset of each reference's first row
 };
 
 // bin_counts::count_bins (bin_counts.rs:254-262): one sample's dense per-bin counts scattered into its column of the

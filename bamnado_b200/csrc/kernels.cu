@@ -191,9 +191,24 @@ cudaError_t launch_bin_matrix(const BinMatrixArgs &a, int sm_count, cudaStream_t
   BND_LAUNCH(bin_matrix_kernel, dim3(grid_for(n, COL_THREADS, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
   return launched();
 }
-cudaError_t launch_multi_flags(const MultiArgs &a, int sm_count, cudaStream_t s) {
+cudaError_t launch_multi_bits(const MultiArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_bins == 0) return cudaSuccess;
-  BND_LAUNCH(multi_flags_kernel, dim3(grid_for(a.n_bins, COL_THREADS, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  BND_LAUNCH(multi_bits_kernel, dim3(grid_for(a.n_bins, COL_THREADS, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_multi_or(uint32_t *dst, const uint32_t *src, uint32_t n_src, uint64_t n_words, int sm_count, cudaStream_t s) {
+  if (n_words == 0) return cudaSuccess;
+  BND_LAUNCH(multi_or_kernel, dim3(grid_for(n_words, COL_THREADS, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, dst, src, n_src, n_words);
+  return launched();
+}
+cudaError_t launch_multi_text_len(const MultiTextArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(multi_text_len_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(TEXT_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_multi_text_write(const MultiTextArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(multi_text_write_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(TEXT_THREADS), 0, s, a);
   return launched();
 }
 cudaError_t launch_multi_count(const MultiArgs &a, int sm_count, cudaStream_t s) {

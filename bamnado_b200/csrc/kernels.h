@@ -33,7 +33,10 @@ cudaError_t launch_bdg_sorted_check(const BdgArgs &a, int sm_count, cudaStream_t
 cudaError_t launch_bdg_count(const BdgArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_bdg_emit(const BdgArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_u64_scan(uint64_t *v, uint32_t n, unsigned long long *total_out, cudaStream_t s);
-cudaError_t launch_multi_flags(const MultiArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_multi_bits(const MultiArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_multi_or(uint32_t *dst, const uint32_t *src, uint32_t n_src, uint64_t n_words, int sm_count, cudaStream_t s);
+cudaError_t launch_multi_text_len(const MultiTextArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_multi_text_write(const MultiTextArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_bin_matrix(const BinMatrixArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_count(const MultiArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_emit(const MultiArgs &a, int sm_count, cudaStream_t s);

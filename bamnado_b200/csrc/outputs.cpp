@@ -35,42 +35,7 @@ void multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int
     owned.emplace_back(new Pileup(&cfgs[i], filters ? &filters[i] : nullptr));
     bams.push_back(owned.back().get());
   }
-  std::vector<RunRow> rows;
-  std::vector<uint32_t> vals;
-  Pileup::multi_collapse(bams, rows, vals);
-  const BamHeader &h = bams[0]->header();
-  // rows come in header order; report them sorted by (chrom byte string, start) like collapse_equal_bins sorts
-  std::vector<int> order(h.names.size());
-  for (size_t r = 0; r < order.size(); r++) order[r] = (int)r;
-  std::sort(order.begin(), order.end(), [&](int x, int y) { return h.names[x] < h.names[y]; });
-  std::vector<size_t> first(h.names.size() + 1, 0);
-  for (auto &r : rows) first[r.ref_id + 1]++;
-  for (size_t r = 0; r < h.names.size(); r++) first[r + 1] += first[r];
-  std::string text = "chrom\tstart\tend";
-  for (int i = 0; i < n; i++) {
-    text.push_back('\t');
-    text += bams[i]->bam_path();
-  }
-  text.push_back('\n');
-  const size_t n_rows = rows.size();
-  for (int ref : order) {
-    for (size_t k = first[ref]; k < first[ref + 1]; k++) {
-      text += h.names[ref];
-      text.push_back('\t');
-      text += std::to_string(rows[k].start);
-      text.push_back('\t');
-      text += std::to_string(rows[k].stop);
-      for (int i = 0; i < n; i++) {
-        text.push_back('\t');
-        text += std::to_string(vals[(size_t)i * n_rows + k]);
-      }
-      text.push_back('\n');
-    }
-  }
-  FILE *f = fopen(out, "wb");
-  if (!f) fail(std::string("cannot create ") + out);
-  size_t w = fwrite(text.data(), 1, text.size(), f);
-  if (fclose(f) != 0 || w != text.size()) fail(std::string("write error on ") + out);
+  Pileup::multi_to_tsv(bams, out);
 }
 
 // ---- collapse-bedgraph (src/cli.rs:1149-1205) -----------------------------------------------------------------------------------

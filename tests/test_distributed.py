@@ -68,7 +68,7 @@ def test_two_rank_gloo_sharded_coverage(oracle, make_bam, tmp_path, native_emul)
 
 
 def test_multi_bam_one_bam_per_rank_gloo(oracle, make_bam, tmp_path, native_emul):
-    # §8(e): one BAM per rank, all-reduce(MAX) of the change flags, gather of the compacted columns -> MultiBamPileup TSV
+    # §8(e): one BAM per rank, all-gather + OR of the 1-bit change masks, all-to-all of the compacted column slices, every rank writes its pieces -> MultiBamPileup TSV
     bams = [make_bam("m0", "--pairs", 8000, "--seed", 11, "--mode", "se"), make_bam("m1", "--pairs", 8000, "--seed", 12, "--mode", "se")]
     out = tmp_path / "dist.tsv"
     env = dict(os.environ, BND_EMUL_WORKERS="2", OMP_NUM_THREADS="1")
@@ -81,3 +81,7 @@ def test_multi_bam_one_bam_per_rank_gloo(oracle, make_bam, tmp_path, native_emul
     oracle.multi_to_tsv([dict(bam_path=b, bin_size=500, collapse=False) for b in bams], [filt, filt], ref)
     a, b = out.read_text().splitlines(), ref.read_text().splitlines()
     assert a[0] == b[0] and sorted(a[1:]) == sorted(b[1:])
+    # the file the two ranks wrote together is byte for byte what one process holding both BAMs writes
+    single = tmp_path / "single.tsv"
+    native_emul.multi_to_tsv([dict(bam_path=b, bin_size=500, collapse=False) for b in bams], [filt, filt], single)
+    assert out.read_bytes() == single.read_bytes()
