@@ -14,8 +14,9 @@
 //                  scan of the per-thread bit counts gives every thread its bit offset, and the bits are OR-ed into a shared
 //                  memory image of the stream.  Adler-32, section bounds and the summary statistics come out of the same pass.
 //   bw_compact     packs the sections back to back (offsets from a scan of their sizes)
-//   bw_zoom_*      one thread per zoom window: binary search of the first item overlapping the window, sequential f32
-//                  accumulation in item order (deterministic), then stream compaction of the windows that hold data
+//   bw_zoom_*      one thread per zoom window.  First level: binary search of the first item overlapping the window, sequential
+//                  f32 accumulation in item order (about ten items per window); every further level folds the four finer windows
+//                  of the level below (deterministic order); then stream compaction of the windows that hold data
 // All of it is byte/integer streaming work: HBM- and shared-memory-bound, no tensor-core shape.
 #pragma once
 #include "common.cuh"
@@ -304,6 +305,34 @@ __global__ void __launch_bounds__(BW_THREADS) bw_zoom_windows_kernel(BwZoomArgs 
         else hi = mid;
       }
       const uint32_t c = lo;
+      if (a.prev_recs) {
+        // level z from level z - 1 (reduction x4, windows of both levels start at base 0 of the chromosome): fold the up to four
+        // finer windows that hold data, in order
+        const uint64_t w = wi - a.win_first[c];
+        const uint64_t p0 = a.prev_win_first[c] + 4 * w, p1 = tmin<uint64_t>(p0 + 4, a.prev_win_first[c + 1]);
+        uint32_t rs = 0, re = 0, valid = 0;
+        float mn = 0.f, mx = 0.f, sum = 0.f, sq = 0.f;
+        for (uint64_t q = p0; q < p1; q++) {
+          if (!a.prev_flags[q]) continue;
+          const uint32_t *r = reinterpret_cast<const uint32_t *>(a.prev_recs + q * BW_ZOOM_BYTES);
+          const float qmn = __uint_as_float(r[4]), qmx = __uint_as_float(r[5]), qs = __uint_as_float(r[6]), qq = __uint_as_float(r[7]);
+          if (!flag) {
+            rs = r[1], mn = qmn, mx = qmx, sum = qs, sq = qq;
+            flag = 1;
+          } else {
+            mn = fminf(mn, qmn), mx = fmaxf(mx, qmx);
+            sum = __fadd_rn(sum, qs), sq = __fadd_rn(sq, qq);
+          }
+          re = r[2];
+          valid += r[3];
+        }
+        if (flag) {
+          uint32_t *r = reinterpret_cast<uint32_t *>(a.recs + wi * BW_ZOOM_BYTES);
+          r[0] = c, r[1] = rs, r[2] = re, r[3] = valid;
+          r[4] = __float_as_uint(mn), r[5] = __float_as_uint(mx), r[6] = __float_as_uint(sum), r[7] = __float_as_uint(sq);
+        }
+        a.flags[wi] = (uint8_t)flag;
+      } else {
       const uint64_t ws = (wi - a.win_first[c]) * (uint64_t)a.reduction, we = ws + a.reduction;
       uint64_t i0 = a.item_first[c], i1 = a.item_first[c + 1];
       uint64_t l = i0, h = i1;  // first item whose end lies beyond the window start
@@ -340,6 +369,7 @@ __global__ void __launch_bounds__(BW_THREADS) bw_zoom_windows_kernel(BwZoomArgs 
         r[4] = __float_as_uint(mn), r[5] = __float_as_uint(mx), r[6] = __float_as_uint(sum), r[7] = __float_as_uint(sq);
       }
       a.flags[wi] = (uint8_t)flag;
+      }
     }
     uint64_t total;
     block_exclusive_scan<BW_THREADS, uint64_t>(flag, scratch, total);

@@ -121,8 +121,9 @@ inline void write_chrom_tree(Buf &b, std::vector<std::tuple<std::string, uint32_
   }
 }
 
-// cirTree (R-tree) over the sections, built bottom-up with full-size nodes
-inline void write_rtree(Buf &b, const std::vector<Section> &secs, uint64_t end_file_offset) {
+// cirTree (R-tree) over the sections, built bottom-up with full-size nodes.  Child offsets inside the tree are absolute file
+// offsets: `base` is where b's first byte will sit in the file.
+inline void write_rtree(Buf &b, const std::vector<Section> &secs, uint64_t end_file_offset, uint64_t base) {
   const uint64_t n = secs.size();
   b.u32(0x2468ACE0);
   b.u32(BLOCK);
@@ -168,7 +169,7 @@ inline void write_rtree(Buf &b, const std::vector<Section> &secs, uint64_t end_f
     }
   }
   std::vector<uint64_t> level_off(levels);
-  uint64_t off = b.d.size();
+  uint64_t off = base + b.d.size();
   for (int l = levels - 1; l >= 0; l--) {
     level_off[l] = off;
     off += level_nodes[l] * (4 + (uint64_t)BLOCK * (l == 0 ? 32 : 24));

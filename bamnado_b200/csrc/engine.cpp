@@ -2121,10 +2121,10 @@ void Pileup::to_bigwig(const std::string &path) {
   const uint32_t n_chrom = (uint32_t)chroms.size();
 
   DevBuf d_row_first, d_item_first, d_skip, d_items, d_flag, d_secs, d_staging, d_sizes, d_bounds, d_stats, d_offsets;
-  DevBuf z_item_first, z_win_first, z_recs, z_flags, z_tiles, z_total, z_out, z_chrom_first;
+  DevBuf z_item_first, z_win_first, z_win_first2, z_recs, z_recs2, z_flags, z_flags2, z_tiles, z_total, z_out, z_chrom_first;
   auto release = [&] {
     for (DevBuf *b : {&d_row_first, &d_item_first, &d_skip, &d_items, &d_flag, &d_secs, &d_staging, &d_sizes, &d_bounds, &d_stats, &d_offsets, &z_item_first,
-                      &z_win_first, &z_recs, &z_flags, &z_tiles, &z_total, &z_out, &z_chrom_first})
+                      &z_win_first, &z_win_first2, &z_recs, &z_recs2, &z_flags, &z_flags2, &z_tiles, &z_total, &z_out, &z_chrom_first})
       b->release();
   };
   BwLevel data;
@@ -2243,36 +2243,46 @@ void Pileup::to_bigwig(const std::string &path) {
       CU(cudaStreamSynchronize(st));  // d_secs / d_staging are reused by the next level
     };
     const uint32_t item_lags[4] = {4, 8, 12, 24};  // start = previous end (lag 8), fields of the previous items (12, 24), zero / equal halves (4)
+    const double t_items = now_ms();
     encode(data, d_items.as<uint8_t>(), chrom_item_first, BW_ITEM_BYTES, BW_SEC_HEADER, item_lags, true);
+    const double t_data = now_ms();
 
-    // ---- zoom levels: first reduction ~10x the mean item width, then 4x per level, until a level is small ----
+    // ---- zoom levels: first reduction ~10x the mean item width, then 4x per level, until a level is small.  The first level
+    // is summarised from the items, every further one from the dense window slots of the level below. ----
+    const double t_zoom0 = now_ms();
     if (n_items) {
       upload(z_item_first, chrom_item_first.data(), chrom_item_first.size());
       uint64_t reduction = std::max<uint64_t>(10, covered / n_items * 10);
+      DevBuf *recs_cur = &z_recs, *recs_prev = &z_recs2, *flags_cur = &z_flags, *flags_prev = &z_flags2, *wf_cur = &z_win_first, *wf_prev = &z_win_first2;
       for (uint32_t z = 0; z < bwl::MAX_ZOOM && reduction <= 0x7fffffffull; z++, reduction *= 4) {
         std::vector<uint64_t> win_first(n_chrom + 1, 0);
         for (uint32_t c = 0; c < n_chrom; c++) win_first[c + 1] = win_first[c] + ((uint64_t)std::get<2>(chroms[c]) + reduction - 1) / reduction;
         const uint64_t n_win = win_first[n_chrom];
         const uint64_t n_tiles64 = (n_win + BW_THREADS - 1) / BW_THREADS;
         if (n_tiles64 > 0xffffffffull) fail("too many zoom windows");
-        upload(z_win_first, win_first.data(), win_first.size());
-        z_recs.ensure(std::max<uint64_t>(n_win, 1) * BW_ZOOM_BYTES);
-        z_flags.ensure(n_win + 16);
+        upload(*wf_cur, win_first.data(), win_first.size());
+        recs_cur->ensure(std::max<uint64_t>(n_win, 1) * BW_ZOOM_BYTES);
+        flags_cur->ensure(n_win + 16);
         z_tiles.ensure(n_tiles64 * 8 + 16);
         z_total.ensure(16);
         z_chrom_first.ensure((n_chrom + 1) * 8);
         BwZoomArgs za{};
         za.items = d_items.as<BwItem>();
         za.item_first = z_item_first.as<uint64_t>();
-        za.win_first = z_win_first.as<uint64_t>();
+        za.win_first = wf_cur->as<uint64_t>();
         za.n_chrom = n_chrom;
         za.reduction = (uint32_t)reduction;
         za.n_windows = n_win;
-        za.recs = z_recs.as<uint8_t>();
-        za.flags = z_flags.as<uint8_t>();
+        za.recs = recs_cur->as<uint8_t>();
+        za.flags = flags_cur->as<uint8_t>();
         za.tile_count = z_tiles.as<uint64_t>();
         za.n_tiles = (uint32_t)n_tiles64;
         za.chrom_first_rec = z_chrom_first.as<uint64_t>();
+        if (z > 0) {
+          za.prev_recs = recs_prev->as<uint8_t>();
+          za.prev_flags = flags_prev->as<uint8_t>();
+          za.prev_win_first = wf_prev->as<uint64_t>();
+        }
         CU(launch_bw_zoom_windows(za, ctx.sm_count, st));
         CU(launch_u64_scan(za.tile_count, za.n_tiles, z_total.as<unsigned long long>(), st));
         unsigned long long n_recs = 0;
@@ -2291,8 +2301,12 @@ void Pileup::to_bigwig(const std::string &path) {
         const uint32_t zoom_lags[4] = {4, 28, 32, 0};  // min = max (4), start = previous end (28), same field of the previous record (32)
         encode(lv, z_out.as<uint8_t>(), chrom_first_rec, BW_ZOOM_BYTES, 0, zoom_lags, false);
         if (n_recs < 64) break;
+        std::swap(recs_cur, recs_prev);
+        std::swap(flags_cur, flags_prev);
+        std::swap(wf_cur, wf_prev);
       }
     }
+    const double t_zoom1 = now_ms();
 
     // ---- file layout ----
     bwl::Buf head;  // header (64) + zoom headers + total summary, then the chromosome tree
@@ -2305,13 +2319,7 @@ void Pileup::to_bigwig(const std::string &path) {
     for (auto &sc : data.secs) sc.offset += data_blob_off;
     const uint64_t index_off = data_blob_off + data.bytes;
     bwl::Buf index;
-    {
-      bwl::Buf tmp;
-      tmp.pad_to(index_off);  // offsets inside the R-tree are absolute: build it at its final position
-      tmp.d.resize(index_off);
-      bwl::write_rtree(tmp, data.secs, index_off);
-      index.d.assign(tmp.d.begin() + (std::ptrdiff_t)index_off, tmp.d.end());
-    }
+    bwl::write_rtree(index, data.secs, index_off, index_off);
     struct ZoomPlace {
       uint64_t data_off, blob_off, index_off;
       std::vector<uint8_t> index;
@@ -2325,9 +2333,8 @@ void Pileup::to_bigwig(const std::string &path) {
       for (auto &sc : lv.secs) sc.offset += zp[z].blob_off;
       zp[z].index_off = zp[z].blob_off + lv.bytes;
       bwl::Buf tmp;
-      tmp.d.resize(zp[z].index_off);
-      bwl::write_rtree(tmp, lv.secs, zp[z].index_off);
-      zp[z].index.assign(tmp.d.begin() + (std::ptrdiff_t)zp[z].index_off, tmp.d.end());
+      bwl::write_rtree(tmp, lv.secs, zp[z].index_off, zp[z].index_off);
+      zp[z].index.swap(tmp.d);
       cur = zp[z].index_off + zp[z].index.size();
     }
     file_bytes = cur + 4;  // trailing magic
@@ -2375,8 +2382,12 @@ void Pileup::to_bigwig(const std::string &path) {
       char *base = map;
       drain_text(ctx, lv.blob.as<uint8_t>(), lv.bytes, one, writers, [base](const uint8_t *src, uint64_t len, uint64_t o) { memcpy(base + o, src, len); });
     };
+    const double t_layout = now_ms();
     drain_level(data, data_blob_off);
     for (size_t z = 0; z < zooms.size(); z++) drain_level(*zooms[z], zp[z].blob_off);
+    if (env_u64("BND_DEBUG_TIMING", 0))
+      fprintf(stderr, "[bnd] to_bigwig: items %.2f ms, data sections %.2f ms, zoom levels %.2f ms, layout + file %.2f ms, drain %.2f ms\n", t_items - t0, t_data - t_items,
+              t_zoom1 - t_zoom0, t_layout - t_zoom1, now_ms() - t_layout);
   } catch (...) {
     release();
     if (map) munmap(map, file_bytes);

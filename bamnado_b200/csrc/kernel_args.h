@@ -355,6 +355,9 @@ struct BwZoomArgs {
   uint32_t n_tiles;
   uint8_t *out;                // compacted records
   uint64_t *chrom_first_rec;   // [n_chrom + 1] first compacted record of each chromosome
+  const uint8_t *prev_recs;    // level below (dense slots, reduction / 4), or null: build this level from the items
+  const uint8_t *prev_flags;
+  const uint64_t *prev_win_first;
 };
 
 }  // namespace bnd

@@ -198,6 +198,11 @@ inline void __threadfence() {}
 inline void __threadfence_block() {}
 
 // ---- integer intrinsics ----------------------------------------------------------------------------------------
+inline float __uint_as_float(unsigned u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
 inline unsigned __float_as_uint(float f) {
   unsigned u;
   memcpy(&u, &f, 4);
