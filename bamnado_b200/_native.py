@@ -30,7 +30,7 @@ EXPORTS = [
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
     "bnd_pileup_timings", "bnd_pileup_shape", "bnd_pileup_format_bedgraph", "bnd_pileup_write_bedgraph_pieces", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
-    "bnd_multi_change_bits", "bnd_multi_or_bits", "bnd_multi_compact_column", "bnd_multi_format_tsv", "bnd_multi_write_tsv_pieces", "bnd_pileup_refs", "bnd_collapse_bedgraph",
+    "bnd_multi_prepare_resident", "bnd_multi_change_bits", "bnd_multi_or_bits", "bnd_multi_compact_columns", "bnd_multi_format_tsv", "bnd_multi_write_tsv_pieces", "bnd_pileup_refs", "bnd_collapse_bedgraph",
     "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
 ]
 
@@ -155,10 +155,11 @@ class Native:
                                                 C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_uint64)]
         L.bnd_multi_to_tsv.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg), C.c_int32, C.c_char_p]
         L.bnd_multi_prepare.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-        L.bnd_multi_change_bits.argtypes = [C.c_void_p, C.c_void_p]
+        L.bnd_multi_prepare_resident.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.bnd_multi_change_bits.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]
         L.bnd_multi_or_bits.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
-        L.bnd_multi_compact_column.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
-        L.bnd_multi_format_tsv.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]
+        L.bnd_multi_compact_columns.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+        L.bnd_multi_format_tsv.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_int32), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]
         L.bnd_multi_write_tsv_pieces.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
         L.bnd_pileup_refs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
         L.bnd_collapse_bedgraph.argtypes = [C.c_char_p, C.c_char_p]
@@ -222,6 +223,18 @@ class Native:
         arr = np.ctypeslib.as_array(out, shape=(n.value,)).copy() if n.value else np.zeros(0, np.float32)
         self.L.bnd_free(out)
         return arr
+
+    def multi_change_bits(self, handles: list, dev_ptr: int):
+        """dev_ptr: ceil(n_bins / 32) u32 words of device memory; bit i = bin i opens a new row for one of these BAMs."""
+        hs = (C.c_void_p * len(handles))(*[h.h for h in handles])
+        self.check(self.L.bnd_multi_change_bits(hs, len(handles), C.c_void_p(dev_ptr)))
+
+    def multi_compact_columns(self, handles: list, dev_bits_ptr: int):
+        """-> (n_rows, device pointer of u32[len(handles)][n_rows]: the BAMs' counts at the shared row heads; owned by handles[0])."""
+        hs = (C.c_void_p * len(handles))(*[h.h for h in handles])
+        n, vals = C.c_uint64(), C.c_void_p()
+        self.check(self.L.bnd_multi_compact_columns(hs, len(handles), C.c_void_p(dev_bits_ptr), C.byref(n), C.byref(vals)))
+        return n.value, vals.value or 0
 
     def multi_or_bits(self, device: int, dst_ptr: int, src_ptr: int, n_src: int, n_words: int):
         """dst[w] = OR over n_src masks of n_words u32 laid out back to back at src (device pointers; dst may alias mask 0)."""
@@ -368,25 +381,18 @@ class PileupHandle:
         return out
 
     # ---- one BAM per rank (multi-bam-coverage across GPUs) ----
-    def multi_prepare(self) -> int:
+    def multi_prepare(self, resident: bool = False) -> int:
         n = C.c_uint64()
-        self.n.check(self.n.L.bnd_multi_prepare(self.h, C.byref(n)))
+        f = self.n.L.bnd_multi_prepare_resident if resident else self.n.L.bnd_multi_prepare
+        self.n.check(f(self.h, C.byref(n)))
         return n.value
 
-    def multi_change_bits(self, dev_ptr: int):
-        """dev_ptr: ceil(n_bins / 32) u32 words of device memory; bit i = bin i opens a new row for this BAM."""
-        self.n.check(self.n.L.bnd_multi_change_bits(self.h, C.c_void_p(dev_ptr)))
-
-    def multi_compact_column(self, dev_bits_ptr: int):
-        """-> (n_rows, device pointer of this BAM's u32 counts at the shared row heads; owned by the handle)."""
-        n, vals = C.c_uint64(), C.c_void_p()
-        self.n.check(self.n.L.bnd_multi_compact_column(self.h, C.c_void_p(dev_bits_ptr), C.byref(n), C.byref(vals)))
-        return n.value, vals.value or 0
-
-    def multi_format_tsv(self, dev_cols_ptr: int, col_stride: int, n_cols: int, row_lo: int, row_hi: int) -> list:
+    def multi_format_tsv(self, dev_cols_ptr: int, col_stride: int, n_cols: int, row_lo: int, row_hi: int, col_order=None) -> list:
+        """BAM c's count of row r is dev_cols[col_order[c] * col_stride + (r - row_lo)] (col_order None = identity)."""
         names, _ = self.refs()
         sizes = (C.c_uint64 * max(len(names), 1))()
-        self.n.check(self.n.L.bnd_multi_format_tsv(self.h, C.c_void_p(dev_cols_ptr), col_stride, n_cols, row_lo, row_hi, sizes, len(names)))
+        order = (C.c_int32 * n_cols)(*col_order) if col_order is not None else None
+        self.n.check(self.n.L.bnd_multi_format_tsv(self.h, C.c_void_p(dev_cols_ptr), col_stride, n_cols, order, row_lo, row_hi, sizes, len(names)))
         return [int(sizes[i]) for i in range(len(names))]
 
     def multi_write_tsv_pieces(self, path, header: str, tables: list, rank: int):

@@ -199,26 +199,35 @@ int bnd_bin_counts(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, in
 }
 
 int bnd_multi_prepare(bnd_pileup *p, uint64_t *n_bins) {
-  return guarded([&] { *n_bins = P(p)->multi_prepare(); });
+  return guarded([&] { *n_bins = P(p)->multi_prepare(false); });
 }
-int bnd_multi_change_bits(bnd_pileup *p, void *dev_bits) {
-  return guarded([&] { P(p)->multi_change_bits((uint32_t *)dev_bits); });
+int bnd_multi_prepare_resident(bnd_pileup *p, uint64_t *n_bins) {
+  return guarded([&] { *n_bins = P(p)->multi_prepare(true); });
+}
+int bnd_multi_change_bits(bnd_pileup *const *ps, int32_t n, void *dev_bits) {
+  return guarded([&] {
+    std::vector<bnd::Pileup *> v;
+    for (int i = 0; ps && i < n; i++) v.push_back(P(ps[i]));
+    bnd::Pileup::multi_change_bits(v.data(), (int)v.size(), (uint32_t *)dev_bits);
+  });
 }
 int bnd_multi_or_bits(int32_t device, void *dev_dst, const void *dev_src, uint32_t n_src, uint64_t n_words) {
   return guarded([&] { bnd::Pileup::multi_or_bits(device, (uint32_t *)dev_dst, (const uint32_t *)dev_src, n_src, n_words); });
 }
-int bnd_multi_compact_column(bnd_pileup *p, const void *dev_bits, uint64_t *n_rows, const void **dev_vals) {
+int bnd_multi_compact_columns(bnd_pileup *const *ps, int32_t n, const void *dev_bits, uint64_t *n_rows, const void **dev_vals) {
   return guarded([&] {
-    const uint32_t *v = nullptr;
-    *n_rows = P(p)->multi_compact_column((const uint32_t *)dev_bits, &v);
-    if (dev_vals) *dev_vals = v;
+    std::vector<bnd::Pileup *> v;
+    for (int i = 0; ps && i < n; i++) v.push_back(P(ps[i]));
+    const uint32_t *vals = nullptr;
+    *n_rows = bnd::Pileup::multi_compact_columns(v.data(), (int)v.size(), (const uint32_t *)dev_bits, &vals);
+    if (dev_vals) *dev_vals = vals;
   });
 }
-int bnd_multi_format_tsv(bnd_pileup *p, const void *dev_cols, uint64_t col_stride, int32_t n_cols, uint64_t row_lo, uint64_t row_hi,
-                         uint64_t *bytes_per_ref, uint64_t n_refs) {
+int bnd_multi_format_tsv(bnd_pileup *p, const void *dev_cols, uint64_t col_stride, int32_t n_cols, const int32_t *col_order, uint64_t row_lo,
+                         uint64_t row_hi, uint64_t *bytes_per_ref, uint64_t n_refs) {
   return guarded([&] {
     std::vector<uint64_t> v;
-    P(p)->multi_format_tsv((const uint32_t *)dev_cols, col_stride, n_cols, row_lo, row_hi, v);
+    P(p)->multi_format_tsv((const uint32_t *)dev_cols, col_stride, n_cols, col_order, row_lo, row_hi, v);
     if (v.size() != n_refs) bnd::fail("n_refs does not match the BAM header", bnd::ERR_INVALID);
     for (size_t i = 0; i < v.size(); i++) bytes_per_ref[i] = v[i];
   });

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(TEXT_THREADS) multi_text_len_kernel(MultiTextA
       uint64_t start, stop;
       multi_row_coords(a.g, gb, nx, ref, start, stop);
       len = (a.name_off[ref + 1] - a.name_off[ref]) + dec_len(start) + dec_len(stop) + 3;
-      for (int c = 0; c < a.n_cols; c++) len += 1 + dec_len(a.vals[(uint64_t)c * a.stride + k]);
+      for (int c = 0; c < a.n_cols; c++) len += 1 + dec_len(a.vals[(uint64_t)a.col_pos[c] * a.stride + k]);
       a.row_len[k] = (uint16_t)len;
     }
     uint64_t s = warp_sum((uint64_t)len);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(TEXT_THREADS) multi_text_write_kernel(MultiTex
       p = put_dec(p, stop);
       for (int c = 0; c < a.n_cols; c++) {
         *p++ = '\t';
-        p = put_dec(p, a.vals[(uint64_t)c * a.stride + k]);
+        p = put_dec(p, a.vals[(uint64_t)a.col_pos[c] * a.stride + k]);
       }
       *p++ = '\n';
     }

@@ -1341,8 +1341,7 @@ void Pileup::multi_to_tsv(std::vector<Pileup *> &bams, const std::string &path) 
   a.n_bams = (int)bams.size();
   for (size_t i = 0; i < bams.size(); i++) {
     Pileup &b = *bams[i];
-    b.run_pass(b.shard_, false);
-    b.finalize_range(true, false);
+    b.multi_prepare(false);
     a.counts[i] = b.im_->d_counts.as<uint32_t>();
   }
   std::string header = "chrom\tstart\tend";
@@ -1358,7 +1357,7 @@ void Pileup::multi_to_tsv(std::vector<Pileup *> &bams, const std::string &path) 
     a.n_bins = a.g.bin_hi - a.g.bin_lo;
     im.multi_rows = multi_emit_table(ctx, a, im.d_run_bin, im.d_multi_vals, ctx.sets[0].stream);
   }
-  first.multi_format_tsv(im.d_multi_vals.as<uint32_t>(), im.multi_rows, (int)bams.size(), 0, im.multi_rows, mine);
+  first.multi_format_tsv(im.d_multi_vals.as<uint32_t>(), im.multi_rows, (int)bams.size(), nullptr, 0, im.multi_rows, mine);
   first.multi_write_tsv_pieces(path, header.c_str(), mine.data(), 1, 0);
 }
 
@@ -1465,10 +1464,18 @@ void Pileup::count_bins(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filter
   release();
 }
 
-uint64_t Pileup::multi_prepare() {
+uint64_t Pileup::multi_prepare(bool resident) {
   if (cfg_.collapse) fail("All BAM pileups must have collapse set to false", ERR_INVALID);
-  run_pass(shard_, false);
+  if (resident && im_->res_segs.empty() && shard_.byte_end > shard_.byte_begin) fail("multi_prepare_resident called before stage", ERR_INVALID);
+  run_pass(shard_, resident);
   finalize_range(true, false);
+  // only the dense counts are needed from here on: the difference array (as large as the counts; 12.4 GB for hg38 at bin 1) goes
+  // back to the buffer pool so that the next BAM of this rank reuses it
+  {
+    std::lock_guard<std::mutex> lock(im_->ctx->mu);
+    im_->d_diff.release();
+  }
+  accumulated_ = false;  // the accumulators are gone; a later whole-object call runs its own pass
   return im_->gdev.bin_hi - im_->gdev.bin_lo;
 }
 
@@ -1479,15 +1486,27 @@ uint64_t Pileup::multi_prepare() {
 // column slices (all-to-all: every rank receives rows [k n / world, (k + 1) n / world) of every column);  6. multi_format_tsv
 // writes the text of that slice on the device;  7. after an all-gather of the per-reference byte counts every rank fills its
 // pieces of the one TSV (multi_write_tsv_pieces).
-void Pileup::multi_change_bits(uint32_t *dev_bits) {
-  Impl &im = *im_;
+namespace {
+void check_multi_group(Pileup *const *ps, int n) {
+  if (n < 1 || !ps) fail("At least one BAM pileup is required", ERR_INVALID);
+  if (n > MULTI_MAX_BAMS) fail("too many BAM files for one multi-bam-coverage call", ERR_INVALID);
+}
+}  // namespace
+
+void Pileup::multi_change_bits(Pileup *const *ps, int n, uint32_t *dev_bits) {
+  check_multi_group(ps, n);
+  Impl &im = *ps[0]->im_;
   DeviceCtx &ctx = *im.ctx;
-  if (!finalized_ || !im.d_counts.p) fail("multi_change_bits called before multi_prepare", ERR_INVALID);
+  MultiArgs a{};
+  a.n_bams = n;
+  for (int i = 0; i < n; i++) {
+    Impl &q = *ps[i]->im_;
+    if (!ps[i]->finalized_ || !q.d_counts.p) fail("multi_change_bits called before multi_prepare", ERR_INVALID);
+    if (q.ctx != im.ctx || q.gdev.bin_lo != im.gdev.bin_lo || q.gdev.bin_hi != im.gdev.bin_hi) fail("the BAMs of one rank must share device and bin grid", ERR_INVALID);
+    a.counts[i] = q.d_counts.as<uint32_t>();
+  }
   std::lock_guard<std::mutex> lock(ctx.mu);
   CU(cudaSetDevice(ctx.device));
-  MultiArgs a{};
-  a.n_bams = 1;
-  a.counts[0] = im.d_counts.as<uint32_t>();
   a.g = im.gdev;
   a.n_bins = a.g.bin_hi - a.g.bin_lo;
   a.bits_out = dev_bits;
@@ -1502,15 +1521,21 @@ void Pileup::multi_or_bits(int device, uint32_t *dst, const uint32_t *src, uint3
   CU(cudaStreamSynchronize(ctx.sets[0].stream));
 }
 
-uint64_t Pileup::multi_compact_column(const uint32_t *dev_bits, const uint32_t **dev_vals) {
-  Impl &im = *im_;
+// counts of the n BAMs of this rank at the shared row heads: vals[n][n_rows], kept (with the head bins) in ps[0]
+uint64_t Pileup::multi_compact_columns(Pileup *const *ps, int n, const uint32_t *dev_bits, const uint32_t **dev_vals) {
+  check_multi_group(ps, n);
+  Impl &im = *ps[0]->im_;
   DeviceCtx &ctx = *im.ctx;
-  if (!finalized_ || !im.d_counts.p) fail("multi_compact_column called before multi_prepare", ERR_INVALID);
+  MultiArgs a{};
+  a.n_bams = n;
+  for (int i = 0; i < n; i++) {
+    Impl &q = *ps[i]->im_;
+    if (!ps[i]->finalized_ || !q.d_counts.p) fail("multi_compact_columns called before multi_prepare", ERR_INVALID);
+    if (q.ctx != im.ctx) fail("the BAMs of one rank must share the device", ERR_INVALID);
+    a.counts[i] = q.d_counts.as<uint32_t>();
+  }
   std::lock_guard<std::mutex> lock(ctx.mu);
   CU(cudaSetDevice(ctx.device));
-  MultiArgs a{};
-  a.n_bams = 1;
-  a.counts[0] = im.d_counts.as<uint32_t>();
   a.g = im.gdev;
   a.n_bins = a.g.bin_hi - a.g.bin_lo;
   a.bits = dev_bits;
@@ -1520,7 +1545,8 @@ uint64_t Pileup::multi_compact_column(const uint32_t *dev_bits, const uint32_t *
 }
 
 // TSV text of rows [row_lo, row_hi) of the shared table; dev_cols[c * stride + (row - row_lo)] is BAM c's count of that row.
-void Pileup::multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_cols, uint64_t row_lo, uint64_t row_hi, std::vector<uint64_t> &bytes_per_ref) {
+void Pileup::multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_cols, const int32_t *col_order, uint64_t row_lo, uint64_t row_hi,
+                              std::vector<uint64_t> &bytes_per_ref) {
   Impl &im = *im_;
   DeviceCtx &ctx = *im.ctx;
   const size_t n_ref = hdr_.names.size();
@@ -1559,6 +1585,11 @@ void Pileup::multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_c
     a.vals = dev_cols;
     a.stride = stride;
     a.n_cols = n_cols;
+    for (int c = 0; c < n_cols; c++) {
+      const int pos = col_order ? col_order[c] : c;
+      if (pos < 0 || pos >= n_cols) fail("bad column order", ERR_INVALID);
+      a.col_pos[c] = (uint8_t)pos;
+    }
     a.g = im.gdev;
     a.names = job.d_names.as<char>();
     a.name_off = job.d_name_off.as<uint32_t>();

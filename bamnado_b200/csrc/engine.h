@@ -68,11 +68,13 @@ class Pileup {
   // one BAM per rank: raw dense counts stay on the device, every rank marks "my count changes here" with one bit per
   // bin, the masks of all ranks are OR-ed (gathered over NVLink by the caller), every rank compacts its own column at the shared
   // heads, receives its slice of rows of every column and formats + writes that slice of the one TSV
-  uint64_t multi_prepare();
-  void multi_change_bits(uint32_t *dev_bits);
+  // (a rank may hold several BAMs: the group functions take all of them, the shared table lives in the first handle)
+  uint64_t multi_prepare(bool resident = false);
+  static void multi_change_bits(Pileup *const *ps, int n, uint32_t *dev_bits);
   static void multi_or_bits(int device, uint32_t *dst, const uint32_t *src, uint32_t n_src, uint64_t n_words);
-  uint64_t multi_compact_column(const uint32_t *dev_bits, const uint32_t **dev_vals);
-  void multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_cols, uint64_t row_lo, uint64_t row_hi, std::vector<uint64_t> &bytes_per_ref);
+  static uint64_t multi_compact_columns(Pileup *const *ps, int n, const uint32_t *dev_bits, const uint32_t **dev_vals);
+  void multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_cols, const int32_t *col_order, uint64_t row_lo, uint64_t row_hi,
+                        std::vector<uint64_t> &bytes_per_ref);
   void multi_write_tsv_pieces(const std::string &path, const char *header, const uint64_t *bytes_all, int world, int rank);
   // bin_counts::count_bins (bin_counts.rs:100-289): samples x bins matrix of raw counts on the grid shared by all BAMs
   struct BinCounts {

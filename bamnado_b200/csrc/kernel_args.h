@@ -263,6 +263,7 @@ struct MultiTextArgs {
   const uint32_t *vals;      // [n_cols][stride]: counts of the slice's rows, one column per BAM
   uint64_t stride;
   int n_cols;
+  uint8_t col_pos[MULTI_MAX_BAMS];  // column c of the output (BAM c) is vals[col_pos[c]][..]
   GeomDev g;
   const char *names;         // concatenated reference names
   const uint32_t *name_off;  // [n_ref + 1]

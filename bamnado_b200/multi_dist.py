@@ -1,10 +1,11 @@
-"""multi-bam-coverage with one BAM per rank (MultiBamPileup::to_tsv, bamnado/src/coverage_analysis.rs:783-864).
+"""multi-bam-coverage sharded by BAM across ranks (MultiBamPileup::to_tsv, bamnado/src/coverage_analysis.rs:783-864).
 
-Every rank piles up its own BAM (raw counts, no collapse) on its own GPU.  What crosses NVLink:
+Rank r piles up BAMs [r k, (r + 1) k) of the list (k = n_bams / world; one BAM per GPU at world = n_bams) on its own GPU: raw
+counts, no collapse.  What crosses NVLink:
 
-  masks    one BIT per bin "my count changes here" (hg38 at bin 1: 387 MB per rank), all-gathered and OR-ed on the device
-  columns  every rank compacts its column at the shared row heads and receives rows [k n / world, (k + 1) n / world) of every
-           column (all-to-all, 4 B per row and BAM)
+  masks    one BIT per bin "one of my BAMs changes here" (hg38 at bin 1: 387 MB per rank), all-gathered and OR-ed on the device
+  columns  every rank compacts its columns at the shared row heads and receives rows [j n / world, (j + 1) n / world) of every
+           column (one all-to-all per local column, 4 B per row and BAM, straight out of the compacted column: no send copy)
   tables   n_refs x u64 text bytes per reference, all-gathered, so that every rank knows where its pieces go
 
 Every rank then formats its slice of rows on the device and fills its pieces of the ONE TSV file.  torch.distributed is the
@@ -18,69 +19,108 @@ import torch
 import torch.distributed as dist
 
 
-def multi_bam_to_tsv(N, bams: list, pile: dict, filt: dict, out_path, *, rank: int, world: int, device: torch.device, timings: dict | None = None) -> dict:
-    """Runs steps 1-7 of include/bamnado_b200.h's one-BAM-per-rank protocol.  `pile` holds bin_size etc. (collapse is forced
-    off like MultiBamPileup requires); returns {"rows", "bins", "nvlink_bytes", "tsv_bytes"} (job-wide)."""
-    if len(bams) != world:
-        raise ValueError("one BAM per rank: pass exactly WORLD_SIZE BAMs")
-    cuda = device.type == "cuda"
+class MultiJob:
+    """Handles of this rank's BAMs, kept open so that a bench can stage the compressed bytes once (resident timing)."""
 
-    def sync():
-        if cuda:
-            torch.cuda.synchronize(device)
+    def __init__(self, N, bams: list, pile: dict, filt: dict, *, rank: int, world: int, device: torch.device):
+        if len(bams) % world:
+            raise ValueError("the number of BAMs must be a multiple of the number of ranks")
+        self.N, self.bams, self.rank, self.world, self.device = N, [str(b) for b in bams], rank, world, device
+        self.k = len(bams) // world
+        self.cuda = device.type == "cuda"
+        mine = self.bams[rank * self.k:(rank + 1) * self.k]
+        self.handles = [N.pileup(dict(pile, bam_path=b, collapse=False, device=device.index if self.cuda else -1, shard_rank=0, shard_world=1), filt)
+                        for b in mine]
 
-    t0 = time.perf_counter()
-    cfg = dict(pile, bam_path=str(bams[rank]), collapse=False, device=device.index if cuda else -1, shard_rank=0, shard_world=1)
-    with N.pileup(cfg, filt) as h:
-        n_bins = h.multi_prepare()
+    def close(self):
+        for h in self.handles:
+            h.close()
+
+    def stage(self):
+        for h in self.handles:
+            h.stage()
+
+    def _sync(self):
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
+
+    def table(self, resident: bool = False) -> dict:
+        """Steps 1-5: pile-ups, masks, shared heads, column slices.  Leaves this rank's slice of all columns in self.recv."""
+        N, world, rank, k, dev = self.N, self.world, self.rank, self.k, self.device
+        t0 = time.perf_counter()
+        n_bins = 0
+        for h in self.handles:
+            n_bins = h.multi_prepare(resident)
         t1 = time.perf_counter()
-        nb = torch.tensor([n_bins, -n_bins], dtype=torch.int64, device=device)
-        dist.all_reduce(nb, op=dist.ReduceOp.MAX)
-        if int(nb[0]) != n_bins or int(nb[1]) != -n_bins:
-            raise RuntimeError("the BAMs do not share one bin grid (different reference dictionaries or chunk lengths)")
-        n_words = (n_bins + 31) // 32
-        masks = torch.empty((world, max(n_words, 1)), dtype=torch.int32, device=device)
-        mine = masks[rank]
-        h.multi_change_bits(mine.data_ptr())
         if world > 1:
-            dist.all_gather_into_tensor(masks.view(-1), mine.clone())
-            sync()
-            N.multi_or_bits(device.index if cuda else -1, masks.data_ptr(), masks.data_ptr(), world, max(n_words, 1))
-        n_rows, vals_ptr = h.multi_compact_column(masks.data_ptr())
+            nb = torch.tensor([n_bins, -n_bins], dtype=torch.int64, device=dev)
+            dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+            if int(nb[0]) != n_bins or int(nb[1]) != -n_bins:
+                raise RuntimeError("the BAMs do not share one bin grid (different reference dictionaries or chunk lengths)")
+        n_words = max((n_bins + 31) // 32, 1)
+        masks = torch.empty((world, n_words), dtype=torch.int32, device=dev)
+        N.multi_change_bits(self.handles, masks[rank].data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(masks.view(-1), masks[rank].clone())
+            self._sync()
+            N.multi_or_bits(dev.index if self.cuda else -1, masks.data_ptr(), masks.data_ptr(), world, n_words)
+        n_rows, vals_ptr = N.multi_compact_columns(self.handles, masks.data_ptr())
         del masks
-        # column slices: rank k formats rows [bounds[k], bounds[k + 1])
-        bounds = [n_rows * k // world for k in range(world + 1)]
-        stride = max(max(bounds[k + 1] - bounds[k] for k in range(world)), 1)
-        col = _wrap_u32(vals_ptr, n_rows, device)
-        send = torch.zeros((world, stride), dtype=torch.int32, device=device)
-        for k in range(world):
-            send[k, : bounds[k + 1] - bounds[k]] = col[bounds[k]:bounds[k + 1]]
-        recv = torch.empty_like(send)
-        if world > 1:
-            dist.all_to_all_single(recv.view(-1), send.view(-1))
+        bounds = [n_rows * j // world for j in range(world + 1)]
+        lo, hi = bounds[rank], bounds[rank + 1]
+        n_mine = hi - lo
+        if world == 1:
+            self.cols_ptr, self.stride, self.col_order, self.recv = vals_ptr, max(n_rows, 1), None, None
         else:
-            recv.copy_(send)
-        sync()
+            cols = _wrap_u32(vals_ptr, k * n_rows, dev).view(k, n_rows) if n_rows else torch.zeros((k, 0), dtype=torch.int32, device=dev)
+            # recv[c][i] = rows [lo, hi) of local column c of rank i = BAM i k + c
+            self.recv = torch.empty((k, world, max(n_mine, 1)), dtype=torch.int32, device=dev)
+            in_split = [bounds[j + 1] - bounds[j] for j in range(world)]
+            for c in range(k):
+                out = self.recv[c].view(-1)[: world * n_mine] if n_mine else self.recv[c].view(-1)[:0]
+                dist.all_to_all_single(out, cols[c], output_split_sizes=[n_mine] * world, input_split_sizes=in_split)
+            self._sync()
+            self.cols_ptr, self.stride = self.recv.data_ptr(), max(n_mine, 1)
+            self.col_order = [(g % k) * world + g // k for g in range(world * k)]
+        self.lo, self.hi, self.n_rows, self.n_bins = lo, hi, n_rows, n_bins
         t2 = time.perf_counter()
-        sizes = h.multi_format_tsv(recv.data_ptr(), stride, world, bounds[rank], bounds[rank + 1])
-        t = torch.tensor(sizes, dtype=torch.int64, device=device)
-        allv = [torch.empty_like(t) for _ in range(world)]
+        mask_bytes = 4 * n_words * (world - 1) * world  # all-gather: every rank receives world - 1 masks
+        col_bytes = 4 * n_rows * k * (world - 1)        # all-to-all: every column leaves its rank except its own slice
+        return {"rows": n_rows, "bins": n_bins, "nvlink_bytes": mask_bytes + col_bytes if world > 1 else 0, "pileup_s": t1 - t0, "exchange_s": t2 - t1}
+
+    def format(self) -> list:
+        """Step 6: TSV text of this rank's slice on the device -> text bytes per reference."""
+        return self.handles[0].multi_format_tsv(self.cols_ptr, self.stride, self.world * self.k, self.lo, self.hi, self.col_order)
+
+    def write(self, out_path, sizes: list) -> int:
+        """Step 7: all-gather of the byte tables, every rank fills its pieces.  Returns the size of the TSV."""
+        world, dev = self.world, self.device
         if world > 1:
+            t = torch.tensor(sizes, dtype=torch.int64, device=dev)
+            allv = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(allv, t)
+            tables = [[int(x) for x in v.tolist()] for v in allv]
         else:
-            allv = [t]
-        tables = [[int(x) for x in v.tolist()] for v in allv]
-        header = "chrom\tstart\tend\t" + "\t".join(str(b) for b in bams) + "\n"
-        h.multi_write_tsv_pieces(out_path, header, tables, rank)
+            tables = [sizes]
+        header = "chrom\tstart\tend\t" + "\t".join(self.bams) + "\n"
+        self.handles[0].multi_write_tsv_pieces(out_path, header, tables, self.rank)
+        self.recv = None
         if world > 1:
             dist.barrier()
-        t3 = time.perf_counter()
-    if timings is not None:
-        timings.update(pileup_s=t1 - t0, exchange_s=t2 - t1, text_s=t3 - t2)
-    mask_bytes = 4 * n_words * (world - 1) * world            # all-gather: every rank receives world - 1 masks
-    col_bytes = 4 * n_rows * (world - 1)                       # all-to-all: every column leaves its rank except its own slice
-    return {"rows": n_rows, "bins": n_bins, "nvlink_bytes": mask_bytes + col_bytes if world > 1 else 0,
-            "tsv_bytes": len(header.encode()) + sum(sum(t) for t in tables)}
+        return len(header.encode()) + sum(sum(t) for t in tables)
+
+
+def multi_bam_to_tsv(N, bams: list, pile: dict, filt: dict, out_path, *, rank: int, world: int, device: torch.device) -> dict:
+    """The whole job: {"rows", "bins", "nvlink_bytes", "tsv_bytes", "pileup_s", "exchange_s", "text_s"} (job-wide)."""
+    job = MultiJob(N, bams, pile, filt, rank=rank, world=world, device=device)
+    try:
+        res = job.table()
+        t0 = time.perf_counter()
+        res["tsv_bytes"] = job.write(out_path, job.format())
+        res["text_s"] = time.perf_counter() - t0
+    finally:
+        job.close()
+    return res
 
 
 def _wrap_u32(ptr: int, n: int, device: torch.device) -> torch.Tensor:
@@ -90,6 +130,7 @@ def _wrap_u32(ptr: int, n: int, device: torch.device) -> torch.Tensor:
     if device.type == "cuda":
         class _Arr:  # __cuda_array_interface__: zero-copy view of library-owned device memory
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, True), "version": 3}
+
         return torch.as_tensor(_Arr(), device=device)
     import ctypes
 

@@ -165,22 +165,27 @@ int bnd_bin_counts(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, in
  * per rank instead of the 3.1 GB of a byte mask), (b) slices of the compacted count columns, (c) n_refs x u64 byte counts.  The
  * collectives run on memory the caller owns (e.g. torch CUDA tensors over NCCL/NVLink); every pointer named dev_* is a DEVICE
  * pointer.
- *   1. bnd_multi_prepare          pile-up + dense raw counts; returns the number of bins (must agree on all ranks)
- *   2. bnd_multi_change_bits      dev_bits[ceil(n_bins / 32)] (u32 words, bit i = bin i opens a new row for this BAM)
+ * A rank may hold several BAMs (8 BAMs on 1, 2 or 4 GPUs): the group calls take all handles of the rank; the shared table
+ * (row heads + this rank's columns) is kept in ps[0], which is also the handle the text calls are made on.
+ *   1. bnd_multi_prepare          per BAM: pile-up + dense raw counts; returns the number of bins (must agree on all ranks);
+ *                                 _resident runs over bytes staged by bnd_pileup_stage (device-resident timing)
+ *   2. bnd_multi_change_bits      dev_bits[ceil(n_bins / 32)] (u32 words, bit i = bin i opens a new row for one of the rank's BAMs)
  *   3. (caller) all-gather the masks; bnd_multi_or_bits folds n_src masks laid out back to back into dev_dst (may alias mask 0)
- *   4. bnd_multi_compact_column   this BAM's counts at the shared row heads stay on the device: *dev_vals -> u32[n_rows]
+ *   4. bnd_multi_compact_columns  the rank's counts at the shared row heads stay on the device: *dev_vals -> u32[n][n_rows]
  *   5. (caller) all-to-all: rank k receives rows [row_lo, row_hi) = [k n / world, (k + 1) n / world) of every column
- *   6. bnd_multi_format_tsv       TSV text of that slice on the device; dev_cols[c * col_stride + (row - row_lo)];
+ *   6. bnd_multi_format_tsv       TSV text of that slice on the device; BAM c's count of row r is
+ *                                 dev_cols[col_order[c] * col_stride + (r - row_lo)] (col_order NULL = identity);
  *                                 returns the text bytes this rank holds per reference (header order)
  *   7. (caller) all-gather those tables; bnd_multi_write_tsv_pieces fills this rank's pieces of the ONE file (references in
  *      byte-string order like collapse_equal_bins sorts them, slices in rank order); rank 0 also writes `header`
  *      ("chrom\tstart\tend\t<bam>...\n", the same string on every rank).  The file is complete when all ranks have returned. */
 int bnd_multi_prepare(bnd_pileup *p, uint64_t *n_bins);
-int bnd_multi_change_bits(bnd_pileup *p, void *dev_bits);
+int bnd_multi_prepare_resident(bnd_pileup *p, uint64_t *n_bins);
+int bnd_multi_change_bits(bnd_pileup *const *ps, int32_t n, void *dev_bits);
 int bnd_multi_or_bits(int32_t device, void *dev_dst, const void *dev_src, uint32_t n_src, uint64_t n_words);
-int bnd_multi_compact_column(bnd_pileup *p, const void *dev_bits, uint64_t *n_rows, const void **dev_vals);
-int bnd_multi_format_tsv(bnd_pileup *p, const void *dev_cols, uint64_t col_stride, int32_t n_cols, uint64_t row_lo, uint64_t row_hi,
-                         uint64_t *bytes_per_ref, uint64_t n_refs);
+int bnd_multi_compact_columns(bnd_pileup *const *ps, int32_t n, const void *dev_bits, uint64_t *n_rows, const void **dev_vals);
+int bnd_multi_format_tsv(bnd_pileup *p, const void *dev_cols, uint64_t col_stride, int32_t n_cols, const int32_t *col_order, uint64_t row_lo,
+                         uint64_t row_hi, uint64_t *bytes_per_ref, uint64_t n_refs);
 int bnd_multi_write_tsv_pieces(bnd_pileup *p, const char *out_path, const char *header, const uint64_t *bytes_all, int32_t world, int32_t rank);
 
 /* ---- collapse-bedgraph (src/cli.rs:1149-1205 + bedgraph_utils.rs:5-45) ------------------------------------ */

@@ -2,6 +2,8 @@
 counters are summed with one all-reduce, and the concatenated rows equal the oracle's whole-genome rows."""
 import os
 import subprocess
+
+import pytest
 import sys
 import textwrap
 
@@ -67,21 +69,23 @@ def test_two_rank_gloo_sharded_coverage(oracle, make_bam, tmp_path, native_emul)
     assert open(out + ".merged.bdg", "rb").read() == ref.read_bytes()
 
 
-def test_multi_bam_one_bam_per_rank_gloo(oracle, make_bam, tmp_path, native_emul):
-    # §8(e): one BAM per rank, all-gather + OR of the 1-bit change masks, all-to-all of the compacted column slices, every rank writes its pieces -> MultiBamPileup TSV
-    bams = [make_bam("m0", "--pairs", 8000, "--seed", 11, "--mode", "se"), make_bam("m1", "--pairs", 8000, "--seed", 12, "--mode", "se")]
+@pytest.mark.parametrize("n_bams", [2, 4])
+def test_multi_bam_sharded_by_bam_gloo(oracle, make_bam, tmp_path, native_emul, n_bams):
+    # §8(e): BAMs sharded over ranks (1 or 2 per rank), all-gather + OR of the 1-bit change masks, all-to-all of the compacted column
+    # slices, every rank formats its rows and writes its pieces -> MultiBamPileup TSV
+    bams = [make_bam(f"m{i}", "--pairs", 8000 if i < 3 else 3000, "--seed", 11 + i, "--mode", "se") for i in range(n_bams)]
     out = tmp_path / "dist.tsv"
     env = dict(os.environ, BND_EMUL_WORKERS="2", OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29519", str(ROOT / "scripts" / "multi_bam_dist.py"), "--bams", *bams, "--bin-size", "500", "-o", str(out),
-                        "--backend", "gloo", "--emul"], env=env, capture_output=True, text=True, timeout=600)
+                        "--master-port", str(29519 + n_bams), str(ROOT / "scripts" / "multi_bam_dist.py"), "--bams", *bams, "--bin-size", "500", "-o", str(out),
+                        "--backend", "gloo", "--emul"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     ref = tmp_path / "oracle.tsv"
     filt = dict(min_mapq=20, min_length=20, max_length=1000)
-    oracle.multi_to_tsv([dict(bam_path=b, bin_size=500, collapse=False) for b in bams], [filt, filt], ref)
+    oracle.multi_to_tsv([dict(bam_path=b, bin_size=500, collapse=False) for b in bams], [filt] * n_bams, ref)
     a, b = out.read_text().splitlines(), ref.read_text().splitlines()
     assert a[0] == b[0] and sorted(a[1:]) == sorted(b[1:])
-    # the file the two ranks wrote together is byte for byte what one process holding both BAMs writes
+    # the file the two ranks wrote together is byte for byte what one process holding all BAMs writes
     single = tmp_path / "single.tsv"
-    native_emul.multi_to_tsv([dict(bam_path=b, bin_size=500, collapse=False) for b in bams], [filt, filt], single)
+    native_emul.multi_to_tsv([dict(bam_path=b, bin_size=500, collapse=False) for b in bams], [filt] * n_bams, single)
     assert out.read_bytes() == single.read_bytes()
