@@ -159,7 +159,7 @@ class Native:
         L.bnd_multi_change_bits.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]
         L.bnd_multi_or_bits.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
         L.bnd_multi_compact_columns.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
-        L.bnd_multi_format_tsv.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_int32), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]
+        L.bnd_multi_format_tsv.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_int32), C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64), C.c_uint64]
         L.bnd_multi_write_tsv_pieces.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
         L.bnd_pileup_refs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
         L.bnd_collapse_bedgraph.argtypes = [C.c_char_p, C.c_char_p]
@@ -387,12 +387,12 @@ class PileupHandle:
         self.n.check(f(self.h, C.byref(n)))
         return n.value
 
-    def multi_format_tsv(self, dev_cols_ptr: int, col_stride: int, n_cols: int, row_lo: int, row_hi: int, col_order=None) -> list:
+    def multi_format_tsv(self, dev_cols_ptr: int, col_stride: int, n_cols: int, row_lo: int, row_hi: int, col_order=None, sizes_only=False) -> list:
         """BAM c's count of row r is dev_cols[col_order[c] * col_stride + (r - row_lo)] (col_order None = identity)."""
         names, _ = self.refs()
         sizes = (C.c_uint64 * max(len(names), 1))()
         order = (C.c_int32 * n_cols)(*col_order) if col_order is not None else None
-        self.n.check(self.n.L.bnd_multi_format_tsv(self.h, C.c_void_p(dev_cols_ptr), col_stride, n_cols, order, row_lo, row_hi, sizes, len(names)))
+        self.n.check(self.n.L.bnd_multi_format_tsv(self.h, C.c_void_p(dev_cols_ptr), col_stride, n_cols, order, row_lo, row_hi, int(sizes_only), sizes, len(names)))
         return [int(sizes[i]) for i in range(len(names))]
 
     def multi_write_tsv_pieces(self, path, header: str, tables: list, rank: int):

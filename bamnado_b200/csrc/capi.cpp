@@ -224,10 +224,10 @@ int bnd_multi_compact_columns(bnd_pileup *const *ps, int32_t n, const void *dev_
   });
 }
 int bnd_multi_format_tsv(bnd_pileup *p, const void *dev_cols, uint64_t col_stride, int32_t n_cols, const int32_t *col_order, uint64_t row_lo,
-                         uint64_t row_hi, uint64_t *bytes_per_ref, uint64_t n_refs) {
+                         uint64_t row_hi, int32_t sizes_only, uint64_t *bytes_per_ref, uint64_t n_refs) {
   return guarded([&] {
     std::vector<uint64_t> v;
-    P(p)->multi_format_tsv((const uint32_t *)dev_cols, col_stride, n_cols, col_order, row_lo, row_hi, v);
+    P(p)->multi_format_tsv((const uint32_t *)dev_cols, col_stride, n_cols, col_order, row_lo, row_hi, v, sizes_only != 0);
     if (v.size() != n_refs) bnd::fail("n_refs does not match the BAM header", bnd::ERR_INVALID);
     for (size_t i = 0; i < v.size(); i++) bytes_per_ref[i] = v[i];
   });

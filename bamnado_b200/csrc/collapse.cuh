@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(TEXT_THREADS) multi_text_write_kernel(MultiTex
       multi_row_coords(a.g, gb, nx, ref, start, stop);
       // first row of a reference inside this slice: where that reference's text begins (a reference's first bin is always a head)
       if (k == 0 || gb == tmax<uint64_t>(__ldg(a.g.ref_first_bin + ref), a.g.bin_lo)) a.ref_text_off[ref] = off;
+      if (!a.text) continue;  // sizes only: the caller wants the bytes per reference, not the text
       char *p = a.text + off;
       for (uint32_t q = a.name_off[ref]; q < a.name_off[ref + 1]; q++) *p++ = a.names[q];
       *p++ = '\t';

@@ -1357,7 +1357,7 @@ void Pileup::multi_to_tsv(std::vector<Pileup *> &bams, const std::string &path) 
     a.n_bins = a.g.bin_hi - a.g.bin_lo;
     im.multi_rows = multi_emit_table(ctx, a, im.d_run_bin, im.d_multi_vals, ctx.sets[0].stream);
   }
-  first.multi_format_tsv(im.d_multi_vals.as<uint32_t>(), im.multi_rows, (int)bams.size(), nullptr, 0, im.multi_rows, mine);
+  first.multi_format_tsv(im.d_multi_vals.as<uint32_t>(), im.multi_rows, (int)bams.size(), nullptr, 0, im.multi_rows, mine, false);
   first.multi_write_tsv_pieces(path, header.c_str(), mine.data(), 1, 0);
 }
 
@@ -1546,7 +1546,7 @@ uint64_t Pileup::multi_compact_columns(Pileup *const *ps, int n, const uint32_t 
 
 // TSV text of rows [row_lo, row_hi) of the shared table; dev_cols[c * stride + (row - row_lo)] is BAM c's count of that row.
 void Pileup::multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_cols, const int32_t *col_order, uint64_t row_lo, uint64_t row_hi,
-                              std::vector<uint64_t> &bytes_per_ref) {
+                              std::vector<uint64_t> &bytes_per_ref, bool sizes_only) {
   Impl &im = *im_;
   DeviceCtx &ctx = *im.ctx;
   const size_t n_ref = hdr_.names.size();
@@ -1603,8 +1603,10 @@ void Pileup::multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_c
     CU(cudaMemcpyAsync(&total, job.d_skip.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     job.nbytes = total;
-    job.d_text.ensure(job.nbytes + 16);
-    a.text = job.d_text.as<char>();
+    if (!sizes_only) {
+      job.d_text.ensure(job.nbytes + 16);
+      a.text = job.d_text.as<char>();
+    }
     CU(launch_multi_text_write(a, ctx.sm_count, st));
     std::vector<uint64_t> ref_off(n_ref + 1);
     CU(cudaMemcpyAsync(ref_off.data(), job.d_ref_off.p, (n_ref + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -1620,6 +1622,7 @@ void Pileup::multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_c
     im.text_job.reset();
     throw;
   }
+  if (sizes_only) im.text_job.reset();
 }
 
 // Every rank fills its pieces of the one TSV: header line (written by rank 0), then the references in byte-string order and

@@ -74,7 +74,7 @@ class Pileup {
   static void multi_or_bits(int device, uint32_t *dst, const uint32_t *src, uint32_t n_src, uint64_t n_words);
   static uint64_t multi_compact_columns(Pileup *const *ps, int n, const uint32_t *dev_bits, const uint32_t **dev_vals);
   void multi_format_tsv(const uint32_t *dev_cols, uint64_t stride, int n_cols, const int32_t *col_order, uint64_t row_lo, uint64_t row_hi,
-                        std::vector<uint64_t> &bytes_per_ref);
+                        std::vector<uint64_t> &bytes_per_ref, bool sizes_only = false);
   void multi_write_tsv_pieces(const std::string &path, const char *header, const uint64_t *bytes_all, int world, int rank);
   // bin_counts::count_bins (bin_counts.rs:100-289): samples x bins matrix of raw counts on the grid shared by all BAMs
   struct BinCounts {

@@ -22,11 +22,12 @@ import torch.distributed as dist
 class MultiJob:
     """Handles of this rank's BAMs, kept open so that a bench can stage the compressed bytes once (resident timing)."""
 
-    def __init__(self, N, bams: list, pile: dict, filt: dict, *, rank: int, world: int, device: torch.device):
+    def __init__(self, N, bams: list, pile: dict, filt: dict, *, rank: int, world: int, device: torch.device, slice_rows: int = 64 << 20):
         if len(bams) % world:
             raise ValueError("the number of BAMs must be a multiple of the number of ranks")
         self.N, self.bams, self.rank, self.world, self.device = N, [str(b) for b in bams], rank, world, device
         self.k = len(bams) // world
+        self.slice_rows = max(1, slice_rows)
         self.cuda = device.type == "cuda"
         mine = self.bams[rank * self.k:(rank + 1) * self.k]
         self.handles = [N.pileup(dict(pile, bam_path=b, collapse=False, device=device.index if self.cuda else -1, shard_rank=0, shard_world=1), filt)
@@ -88,35 +89,51 @@ class MultiJob:
         col_bytes = 4 * n_rows * k * (world - 1)        # all-to-all: every column leaves its rank except its own slice
         return {"rows": n_rows, "bins": n_bins, "nvlink_bytes": mask_bytes + col_bytes if world > 1 else 0, "pileup_s": t1 - t0, "exchange_s": t2 - t1}
 
-    def format(self) -> list:
-        """Step 6: TSV text of this rank's slice on the device -> text bytes per reference."""
-        return self.handles[0].multi_format_tsv(self.cols_ptr, self.stride, self.world * self.k, self.lo, self.hi, self.col_order)
+    def _slices(self) -> list:
+        """This rank's rows cut into sub-slices of at most `slice_rows` rows (bounds the text held in HBM); the same count on every rank."""
+        world, n = self.world, self.n_rows
+        biggest = max(n * (j + 1) // world - n * j // world for j in range(world))
+        n_sub = max(1, -(-biggest // self.slice_rows))
+        mine = self.hi - self.lo
+        return [(self.lo + mine * s // n_sub, self.lo + mine * (s + 1) // n_sub) for s in range(n_sub)]
 
-    def write(self, out_path, sizes: list) -> int:
-        """Step 7: all-gather of the byte tables, every rank fills its pieces.  Returns the size of the TSV."""
+    def _format(self, lo: int, hi: int, sizes_only: bool) -> list:
+        # dev_cols holds this rank's rows from self.lo on: the sub-slice starts (lo - self.lo) rows into every column
+        return self.handles[0].multi_format_tsv(self.cols_ptr + 4 * (lo - self.lo), self.stride, self.world * self.k, lo, hi, self.col_order, sizes_only)
+
+    def format(self) -> list:
+        """Step 6 without keeping text (resident timing): TSV text of every sub-slice is produced on the device."""
+        return [self._format(lo, hi, False) for lo, hi in self._slices()]
+
+    def write(self, out_path) -> int:
+        """Steps 6 + 7: byte tables of all sub-slices (virtual ranks), all-gather, then format + fill piece by piece.  Returns the TSV size."""
         world, dev = self.world, self.device
+        subs = self._slices()
+        mine = [self._format(lo, hi, True) for lo, hi in subs]
         if world > 1:
-            t = torch.tensor(sizes, dtype=torch.int64, device=dev)
+            t = torch.tensor(mine, dtype=torch.int64, device=dev).view(-1)
             allv = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(allv, t)
-            tables = [[int(x) for x in v.tolist()] for v in allv]
+            tables = [row for v in allv for row in v.view(len(subs), -1).tolist()]
         else:
-            tables = [sizes]
+            tables = mine
         header = "chrom\tstart\tend\t" + "\t".join(self.bams) + "\n"
-        self.handles[0].multi_write_tsv_pieces(out_path, header, tables, self.rank)
+        for s, (lo, hi) in enumerate(subs):
+            self._format(lo, hi, False)
+            self.handles[0].multi_write_tsv_pieces(out_path, header, tables, self.rank * len(subs) + s)
         self.recv = None
         if world > 1:
             dist.barrier()
         return len(header.encode()) + sum(sum(t) for t in tables)
 
 
-def multi_bam_to_tsv(N, bams: list, pile: dict, filt: dict, out_path, *, rank: int, world: int, device: torch.device) -> dict:
+def multi_bam_to_tsv(N, bams: list, pile: dict, filt: dict, out_path, *, rank: int, world: int, device: torch.device, slice_rows: int = 64 << 20) -> dict:
     """The whole job: {"rows", "bins", "nvlink_bytes", "tsv_bytes", "pileup_s", "exchange_s", "text_s"} (job-wide)."""
-    job = MultiJob(N, bams, pile, filt, rank=rank, world=world, device=device)
+    job = MultiJob(N, bams, pile, filt, rank=rank, world=world, device=device, slice_rows=slice_rows)
     try:
         res = job.table()
         t0 = time.perf_counter()
-        res["tsv_bytes"] = job.write(out_path, job.format())
+        res["tsv_bytes"] = job.write(out_path)
         res["text_s"] = time.perf_counter() - t0
     finally:
         job.close()

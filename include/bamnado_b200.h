@@ -175,7 +175,9 @@ int bnd_bin_counts(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, in
  *   5. (caller) all-to-all: rank k receives rows [row_lo, row_hi) = [k n / world, (k + 1) n / world) of every column
  *   6. bnd_multi_format_tsv       TSV text of that slice on the device; BAM c's count of row r is
  *                                 dev_cols[col_order[c] * col_stride + (r - row_lo)] (col_order NULL = identity);
- *                                 returns the text bytes this rank holds per reference (header order)
+ *                                 returns the text bytes this rank holds per reference (header order).  A rank may cut its slice
+ *                                 into sub-slices to bound the text held in HBM: sizes_only = 1 computes the byte table without
+ *                                 keeping text; the sub-slices then take part in step 7 as consecutive virtual ranks
  *   7. (caller) all-gather those tables; bnd_multi_write_tsv_pieces fills this rank's pieces of the ONE file (references in
  *      byte-string order like collapse_equal_bins sorts them, slices in rank order); rank 0 also writes `header`
  *      ("chrom\tstart\tend\t<bam>...\n", the same string on every rank).  The file is complete when all ranks have returned. */
@@ -185,7 +187,7 @@ int bnd_multi_change_bits(bnd_pileup *const *ps, int32_t n, void *dev_bits);
 int bnd_multi_or_bits(int32_t device, void *dev_dst, const void *dev_src, uint32_t n_src, uint64_t n_words);
 int bnd_multi_compact_columns(bnd_pileup *const *ps, int32_t n, const void *dev_bits, uint64_t *n_rows, const void **dev_vals);
 int bnd_multi_format_tsv(bnd_pileup *p, const void *dev_cols, uint64_t col_stride, int32_t n_cols, const int32_t *col_order, uint64_t row_lo,
-                         uint64_t row_hi, uint64_t *bytes_per_ref, uint64_t n_refs);
+                         uint64_t row_hi, int32_t sizes_only, uint64_t *bytes_per_ref, uint64_t n_refs);
 int bnd_multi_write_tsv_pieces(bnd_pileup *p, const char *out_path, const char *header, const uint64_t *bytes_all, int32_t world, int32_t rank);
 
 /* ---- collapse-bedgraph (src/cli.rs:1149-1205 + bedgraph_utils.rs:5-45) ------------------------------------ */

@@ -1253,22 +1253,41 @@ int orc_multi_to_tsv(const orc_pileup_cfg *cfgs, const orc_filter_cfg *filters, 
       if (cfgs[i].bin_size != cfgs[0].bin_size) fail("All BAM pileups must have the same bin size");
       if (cfgs[i].collapse) fail("All BAM pileups must have collapse set to false");
     }
-    // sequential per-BAM raw pileups, full outer join on (chrom name, start, end)
-    struct Key {
-      std::string chrom;
-      uint64_t start, end;
-      bool operator<(const Key &o) const { return chrom != o.chrom ? chrom < o.chrom : start != o.start ? start < o.start : end < o.end; }
-    };
-    std::map<Key, std::vector<int64_t>> rows;  // -1 == null
+    // sequential per-BAM raw pileups, full outer join on (chrom name, start, end): every BAM's rows are sorted by that key
+    // (the order collapse_equal_bins sorts by), then merged; -1 == null (a key one BAM does not have)
+    std::vector<std::vector<Run>> per_bam((size_t)n_bams);
+    std::vector<std::vector<std::string>> names((size_t)n_bams);
     for (int b = 0; b < n_bams; b++) {
       uint64_t stats[ORC_N_COUNTERS];
       BamStats st;
-      auto runs = pileup_genome(&cfgs[b], &filters[b], stats, &st);
-      for (auto &r : runs) {
-        auto &v = rows[Key{st.header.names[r.ref_id], r.start, r.stop}];
-        if (v.empty()) v.assign((size_t)n_bams, -1);
-        v[b] = r.val;
+      per_bam[b] = pileup_genome(&cfgs[b], &filters[b], stats, &st);
+      names[b] = st.header.names;
+      const std::vector<std::string> &nm = names[b];
+      auto by_key = [&](const Run &x, const Run &y) {
+        if (x.ref_id != y.ref_id) return nm[x.ref_id] < nm[y.ref_id];
+        return x.start != y.start ? x.start < y.start : x.stop < y.stop;
+      };
+      // the rows arrive grouped by reference and ordered by start inside one: move whole references into name order, and only
+      // fall back to a full sort if that did not give the key order
+      {
+        std::vector<size_t> first(nm.size() + 1, 0);
+        for (const Run &r : per_bam[b]) first[(size_t)r.ref_id + 1]++;
+        for (size_t r = 0; r < nm.size(); r++) first[r + 1] += first[r];
+        std::vector<int> order(nm.size());
+        for (size_t r = 0; r < nm.size(); r++) order[r] = (int)r;
+        std::sort(order.begin(), order.end(), [&](int x, int y) { return nm[x] < nm[y]; });
+        std::vector<size_t> dst0(nm.size(), 0);
+        size_t off = 0;
+        for (int r : order) {
+          dst0[r] = off;
+          off += first[r + 1] - first[r];
+        }
+        std::vector<Run> sorted(per_bam[b].size());
+        std::vector<size_t> fill = dst0;
+        for (const Run &r : per_bam[b]) sorted[fill[r.ref_id]++] = r;
+        per_bam[b].swap(sorted);
       }
+      if (!std::is_sorted(per_bam[b].begin(), per_bam[b].end(), by_key)) std::sort(per_bam[b].begin(), per_bam[b].end(), by_key);
     }
     // collapse_equal_bins over all sample columns (nulls compare as "different")
     FileOut fo(out_path);
@@ -1279,36 +1298,58 @@ int orc_multi_to_tsv(const orc_pileup_cfg *cfgs, const orc_filter_cfg *filters, 
     }
     line.push_back('\n');
     fo.put(line);
-    const Key *gk = nullptr;
-    const std::vector<int64_t> *gv = nullptr;
+    bool have = false;
+    std::string gchrom;
+    std::vector<int64_t> gv((size_t)n_bams), cur((size_t)n_bams);
     uint64_t gs = 0, ge = 0;
     auto emit = [&] {
-      if (!gk) return;
-      line = gk->chrom + "\t" + std::to_string(gs) + "\t" + std::to_string(ge);
-      for (int64_t x : *gv) {
+      if (!have) return;
+      line = gchrom + "\t" + std::to_string(gs) + "\t" + std::to_string(ge);
+      for (int64_t x : gv) {
         line.push_back('\t');
         if (x >= 0) line += std::to_string(x);
       }
       line.push_back('\n');
       fo.put(line);
     };
-    for (auto &kv : rows) {
-      bool same = false;
-      if (gk && gk->chrom == kv.first.chrom) {
-        same = true;
-        for (size_t i = 0; i < kv.second.size(); i++)
-          if (kv.second[i] < 0 || (*gv)[i] < 0 || kv.second[i] != (*gv)[i]) same = false;
+    std::vector<size_t> at((size_t)n_bams, 0);
+    auto key_less = [&](int x, int y) {  // row at[x] of BAM x < row at[y] of BAM y
+      const Run &p = per_bam[x][at[x]], &q = per_bam[y][at[y]];
+      const std::string &pn = names[x][p.ref_id], &qn = names[y][q.ref_id];
+      if (pn != qn) return pn < qn;
+      return p.start != q.start ? p.start < q.start : p.stop < q.stop;
+    };
+    for (;;) {
+      int lead = -1;
+      for (int b = 0; b < n_bams; b++)
+        if (at[b] < per_bam[b].size() && (lead < 0 || key_less(b, lead))) lead = b;
+      if (lead < 0) break;
+      const Run k = per_bam[lead][at[lead]];
+      const std::string &kchrom = names[lead][k.ref_id];
+      for (int b = 0; b < n_bams; b++) {
+        cur[b] = -1;
+        if (at[b] < per_bam[b].size()) {
+          const Run &q = per_bam[b][at[b]];
+          if (q.start == k.start && q.stop == k.stop && names[b][q.ref_id] == kchrom) {
+            cur[b] = q.val;
+            at[b]++;
+          }
+        }
       }
+      bool same = have && gchrom == kchrom;
+      if (same)
+        for (int b = 0; b < n_bams; b++)
+          if (cur[b] < 0 || gv[b] < 0 || cur[b] != gv[b]) same = false;
       if (same) {
-        gs = std::min(gs, kv.first.start);
-        ge = std::max(ge, kv.first.end);
-        // `prev row` for the next comparison is this row; scores are equal so gv stays valid
+        gs = std::min(gs, k.start);
+        ge = std::max(ge, k.stop);
       } else {
         emit();
-        gk = &kv.first;
-        gv = &kv.second;
-        gs = kv.first.start;
-        ge = kv.first.end;
+        have = true;
+        gchrom = kchrom;
+        gv = cur;
+        gs = k.start;
+        ge = k.stop;
       }
     }
     emit();

@@ -17,6 +17,7 @@ ap.add_argument("-o", "--output", required=True)
 ap.add_argument("--backend", default="nccl")
 ap.add_argument("--emul", action="store_true")
 ap.add_argument("--min-mapq", type=int, default=20)
+ap.add_argument("--slice-rows", type=int, default=64 << 20, help="rows formatted per pass (bounds the TSV text held in HBM)")
 args = ap.parse_args()
 
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -36,7 +37,7 @@ if rank == 0 and os.path.exists(args.output):
     os.unlink(args.output)
 dist.barrier()
 res = multi_dist.multi_bam_to_tsv(N, args.bams, dict(bin_size=args.bin_size), dict(min_mapq=args.min_mapq, min_length=20, max_length=1000),
-                                  args.output, rank=rank, world=world, device=dev)
+                                  args.output, rank=rank, world=world, device=dev, slice_rows=args.slice_rows)
 if rank == 0:
     print(f"multi-bam-coverage x{world}: {res['rows']} rows, {res['bins']} bins, {res['nvlink_bytes']} B exchanged, {time.perf_counter() - t0:.3f} s", flush=True)
 dist.destroy_process_group()

@@ -78,7 +78,7 @@ def test_multi_bam_sharded_by_bam_gloo(oracle, make_bam, tmp_path, native_emul, 
     env = dict(os.environ, BND_EMUL_WORKERS="2", OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(29519 + n_bams), str(ROOT / "scripts" / "multi_bam_dist.py"), "--bams", *bams, "--bin-size", "500", "-o", str(out),
-                        "--backend", "gloo", "--emul"], env=env, capture_output=True, text=True, timeout=900)
+                        "--backend", "gloo", "--emul", "--slice-rows", "64000000" if n_bams == 2 else "1777"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     ref = tmp_path / "oracle.tsv"
     filt = dict(min_mapq=20, min_length=20, max_length=1000)
