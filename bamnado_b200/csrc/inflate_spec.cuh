@@ -571,14 +571,18 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
   return status;
 }
 
-template <int THREADS, int MIN_CTAS, int LB, int DB, int SPAN, int NT>
+// CRC_SMEM: the CRC tables (5 KB) are copied into the CTA's shared memory; one-warp CTAs (30 per SM) cannot afford the copy and
+// read them through L1 from global memory instead.  That shape was tried to let a finished warp hand its slot to the next
+// segment's launch without waiting for its nine CTA neighbours: measured 8 % slower at 40 M pairs (124.5 vs 115.5 ms per pass;
+// two-warp CTAs 121.7 ms), so blocks are not waiting for slots - the ten-warp shape stays (profiles/r2_sweeps.md).
+template <int THREADS, int MIN_CTAS, int LB, int DB, int SPAN, int NT, bool CRC_SMEM>
 __global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs a) {
   using Smem = SpecSmemT<LB, DB, NT, SPAN>;
   BND_DYN_SMEM(smem_raw);
   constexpr int WARPS = THREADS / 32;
   Smem *warps = reinterpret_cast<Smem *>(smem_raw);
-  CrcTables *crc_s = reinterpret_cast<CrcTables *>(smem_raw + sizeof(Smem) * WARPS);
-  SymTables *sym_s = reinterpret_cast<SymTables *>(smem_raw + sizeof(Smem) * WARPS + sizeof(CrcTables));
+  SymTables *sym_s = reinterpret_cast<SymTables *>(smem_raw + sizeof(Smem) * WARPS);
+  CrcTables *crc_s = reinterpret_cast<CrcTables *>(smem_raw + sizeof(Smem) * WARPS + sizeof(SymTables));
   if (threadIdx.x < 32) {
     const uint32_t s = threadIdx.x;
     const uint32_t eb = s < 8 ? 0u : s == 28 ? 0u : (s - 4) >> 2;
@@ -588,12 +592,13 @@ __global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs 
     const uint32_t dbase = s < 4 ? s + 1 : ((2 + (s & 1)) << deb) + 1;
     sym_s->dist_tab[s] = s < 30 ? (dbase | (deb << 16)) : 0u;
   }
-  {
+  if (CRC_SMEM) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(a.crc);
     uint32_t *dst = reinterpret_cast<uint32_t *>(crc_s);
     for (int i = threadIdx.x; i < (int)(sizeof(CrcTables) / 4); i += THREADS) dst[i] = src[i];
   }
   __syncthreads();
+  const CrcTables *crcT = CRC_SMEM ? crc_s : a.crc;
   Tile<32> tile;
   Smem &S = warps[threadIdx.x / 32];
   for (;;) {
@@ -603,7 +608,7 @@ __global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs 
     if (b >= a.n_blocks) break;
     const uint64_t c0 = a.blk_coff[b], c1 = a.blk_coff[b + 1];
     const uint64_t u0 = a.blk_uoff[b], u1 = a.blk_uoff[b + 1];
-    const int st = inflate_block_spec<Smem>(tile, S, *sym_s, a.comp + c0, (uint32_t)(c1 - c0), a.out + u0, (uint32_t)(u1 - u0), crc_s, a.verify_crc);
+    const int st = inflate_block_spec<Smem>(tile, S, *sym_s, a.comp + c0, (uint32_t)(c1 - c0), a.out + u0, (uint32_t)(u1 - u0), crcT, a.verify_crc);
     if (tile.lane == 0) {
       if (a.status) a.status[b] = st;
       if (st != INF_OK) atomicCAS(a.error_flag, 0, st | ((int)(b & 0xffffff) << 8));
@@ -613,8 +618,8 @@ __global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs 
 }
 
 template <int LB, int DB, int NT, int SPAN>
-constexpr size_t inflate_spec_smem_bytes(int warps) {
-  return sizeof(SpecSmemT<LB, DB, NT, SPAN>) * (size_t)warps + sizeof(CrcTables) + sizeof(SymTables);
+constexpr size_t inflate_spec_smem_bytes(int warps, bool crc_smem) {
+  return sizeof(SpecSmemT<LB, DB, NT, SPAN>) * (size_t)warps + sizeof(SymTables) + (crc_smem ? sizeof(CrcTables) : 0);
 }
 
 }  // namespace bnd

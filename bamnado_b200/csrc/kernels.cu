@@ -42,7 +42,7 @@ namespace {
 struct InflateShape {
   int threads, ctas_per_sm;
 };
-const InflateShape kShapes[] = {{320, 3}, {320, 3}, {256, 4}};
+const InflateShape kShapes[] = {{320, 3}, {320, 3}, {256, 4}, {32, 30}};
 int shape_index() {
   static int v = -1;
   if (v < 0) {
@@ -52,11 +52,11 @@ int shape_index() {
   }
   return v;
 }
-template <int T, int MINB, int LB, int DB, int SPAN, int NT>
+template <int T, int MINB, int LB, int DB, int SPAN, int NT, bool CRC_SMEM>
 cudaError_t launch_inflate_spec_t(const InflateArgs &a, int sm_count, int ctas_per_sm, cudaStream_t s) {
-  auto kern = bgzf_inflate_spec_kernel<T, MINB, LB, DB, SPAN, NT>;
+  auto kern = bgzf_inflate_spec_kernel<T, MINB, LB, DB, SPAN, NT, CRC_SMEM>;
   constexpr int warps = T / 32;
-  const size_t smem = inflate_spec_smem_bytes<LB, DB, NT, SPAN>(warps);
+  const size_t smem = inflate_spec_smem_bytes<LB, DB, NT, SPAN>(warps, CRC_SMEM);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -90,9 +90,10 @@ cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_blocks == 0) return cudaSuccess;
   const InflateShape &v = kShapes[shape_index()];
   switch (shape_index()) {
-    case 1: return launch_inflate_spec_t<320, 3, 9, 8, 256, 384>(a, sm_count, v.ctas_per_sm, s);  // round-1 shape: 256-bit spans
-    case 2: return launch_inflate_spec_t<256, 4, 9, 8, 256, 256>(a, sm_count, v.ctas_per_sm, s);  // short match list (tests)
-    default: return launch_inflate_spec_t<320, 3, 9, 8, 320, 384>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM, 320-bit spans
+    case 1: return launch_inflate_spec_t<320, 3, 9, 8, 256, 384, true>(a, sm_count, v.ctas_per_sm, s);  // round-1 shape: 256-bit spans, ten warps per CTA
+    case 2: return launch_inflate_spec_t<256, 4, 9, 8, 256, 256, true>(a, sm_count, v.ctas_per_sm, s);  // short match list (tests)
+    case 3: return launch_inflate_spec_t<32, 30, 9, 8, 320, 384, false>(a, sm_count, v.ctas_per_sm, s);  // 30 one-warp CTAs / SM, CRC tables through L1 (A/B: 8 % slower)
+    default: return launch_inflate_spec_t<320, 3, 9, 8, 320, 384, true>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM in three CTAs, 320-bit spans
   }
 }
 

@@ -132,10 +132,11 @@ def test_spec_inflate_zoo_on_gpu_many_copies(native_gpu):
     assert out == b"".join(expected)
 
 
-@pytest.mark.parametrize("variant", ["1", "2"])
+@pytest.mark.parametrize("variant", ["1", "2", "3"])
 def test_other_kernel_shapes_stay_correct(variant, tmp_path):
-    # BND_INFLATE_VARIANT is read once per process: 256-bit spans (1) and the 256-entry match list (2: lanes are dropped
-    # whenever a round holds more matches) run the zoo in a child process against the CPU emulator build
+    # BND_INFLATE_VARIANT is read once per process: 256-bit spans (1), the 256-entry match list (2: lanes are dropped
+    # whenever a round holds more matches) and one-warp CTAs reading the CRC tables from global memory (3) run the zoo in a child
+    # process against the CPU emulator build; the shipped shape (0) runs everywhere else
     import subprocess
     import sys
     from pathlib import Path
