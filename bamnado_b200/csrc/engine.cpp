@@ -47,6 +47,35 @@ double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Page cache -> pinned staging.  A copy whose destination is only read by the DMA engine afterwards should not pull the
+// destination lines into the cache first: with non-temporal stores 16 threads move 85 GB/s out of a mapping of the file on the
+// B200 hosts, against 61 GB/s for memcpy and 54 GB/s for pread (scripts/host_copy_probe.cu, profiles/r2_sweeps.md).
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void stream_copy_avx2(uint8_t *dst, const uint8_t *src, size_t n) {
+  while (n && ((uintptr_t)dst & 31)) *dst++ = *src++, n--;
+  const size_t v = n / 128;
+  for (size_t i = 0; i < v; i++) {
+    const __m256i a = _mm256_loadu_si256((const __m256i *)(src)), b = _mm256_loadu_si256((const __m256i *)(src + 32));
+    const __m256i c = _mm256_loadu_si256((const __m256i *)(src + 64)), d = _mm256_loadu_si256((const __m256i *)(src + 96));
+    _mm256_stream_si256((__m256i *)(dst), a);
+    _mm256_stream_si256((__m256i *)(dst + 32), b);
+    _mm256_stream_si256((__m256i *)(dst + 64), c);
+    _mm256_stream_si256((__m256i *)(dst + 96), d);
+    src += 128, dst += 128;
+  }
+  _mm_sfence();
+  memcpy(dst, src, n - v * 128);
+}
+static void stream_copy(uint8_t *dst, const uint8_t *src, size_t n) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) stream_copy_avx2(dst, src, n);
+  else memcpy(dst, src, n);
+}
+#else
+static void stream_copy(uint8_t *dst, const uint8_t *src, size_t n) { memcpy(dst, src, n); }
+#endif
+
 uint64_t env_u64(const char *name, uint64_t dflt) {
   const char *e = getenv(name);
   if (!e || !*e) return dflt;
@@ -266,6 +295,7 @@ struct ReaderPool {
     uint64_t off, len;  // piece inside the segment
   };
   int fd;
+  const uint8_t *map;  // read-only mapping of the whole file, or null (then the pieces are pread)
   DeviceCtx &ctx;
   const std::vector<Segment> &segs;
   std::mutex mu;
@@ -277,7 +307,7 @@ struct ReaderPool {
   bool stop = false;
   std::vector<std::thread> threads;
 
-  ReaderPool(int fd_, DeviceCtx &c, const std::vector<Segment> &s, int n_threads) : fd(fd_), ctx(c), segs(s) {
+  ReaderPool(int fd_, const uint8_t *map_, DeviceCtx &c, const std::vector<Segment> &s, int n_threads) : fd(fd_), map(map_), ctx(c), segs(s) {
     for (int i = 0; i < n_threads; i++) threads.emplace_back([this] { work(); });
   }
   ~ReaderPool() {
@@ -324,6 +354,10 @@ struct ReaderPool {
       StageSlot &slot = ctx.slots[j.slot];
       try {
         uint64_t got = 0;
+        if (map) {
+          stream_copy(slot.pin + j.off, map + s.begin + j.off, j.len);
+          got = j.len;
+        }
         while (got < j.len) {
           ssize_t r = pread(fd, slot.pin + j.off + got, j.len - got, (off_t)(s.begin + j.off + got));
           if (r < 0) fail("read error on BAM file");
@@ -406,6 +440,8 @@ struct Unmapper {
 struct Pileup::Impl {
   DeviceCtx *ctx = nullptr;
   int fd = -1;
+  const uint8_t *map = nullptr;      // read-only mapping of the BAM (the readers copy out of the page cache through it)
+  uint64_t map_len = 0;
   std::vector<uint64_t> cut_points;  // sorted BGZF block starts known from the index
   // geometry + filter tables on the device
   DevBuf d_ref_len, d_first_bin, d_first_chunk;
@@ -427,6 +463,7 @@ struct Pileup::Impl {
   std::vector<Segment> res_segs;
   std::vector<BlockTable> res_tabs;
   ~Impl() {
+    if (map) munmap(const_cast<uint8_t *>(map), map_len);
     if (fd >= 0) close(fd);
     for (DevBuf *b : {&d_ref_len, &d_first_bin, &d_first_chunk, &d_rg, &d_tagv, &d_bl_off, &d_bl_starts, &d_bl_stops, &d_bc_table,
                       &d_bc_off, &d_bc_pool, &d_diff, &d_stats, &d_probe, &d_err, &d_tile_sum, &d_tile_heads, &d_run_bin, &d_run_val,
@@ -633,6 +670,13 @@ void Pileup::open() {
   struct stat st;
   if (fstat(im.fd, &st) != 0) fail("cannot stat " + bam_path_);
   file_size_ = (uint64_t)st.st_size;
+  if (S_ISREG(st.st_mode) && file_size_ > 0) {
+    void *m = mmap(nullptr, file_size_, PROT_READ, MAP_SHARED, im.fd, 0);
+    if (m != MAP_FAILED) {
+      im.map = (const uint8_t *)m;
+      im.map_len = file_size_;
+    }
+  }
   const double t_o0 = now_ms();
   bai_ = read_bai(bam_path_ + ".bai");
   const double t_o1 = now_ms();
@@ -828,7 +872,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
     pool->submit(i, (int)(i % n_slots));
   };
   if (!resident) {
-    pool.reset(new ReaderPool(im.fd, ctx, segs, std::max(1, ctx.n_readers)));
+    pool.reset(new ReaderPool(im.fd, env_u64("BND_READ_MMAP", 1) ? im.map : nullptr, ctx, segs, std::max(1, ctx.n_readers)));
     for (size_t i = 0; i < segs.size() && i < (size_t)n_slots; i++) submit(i);
   }
 
