@@ -1702,58 +1702,90 @@ void Pileup::multi_write_tsv_pieces(const std::string &path, const char *header,
 }
 
 // ---- collapse-bedgraph ------------------------------------------------------------------------------------------------------
-void collapse_rows_device(const BdgRows &in, BdgRows &out, int device) {
-  out = BdgRows();
-  const uint64_t n = in.chrom.size();
-  if (n == 0) return;
-  DeviceCtx &ctx = ctx_for(device);
-  std::lock_guard<std::mutex> lock(ctx.mu);
-  cudaStream_t st = ctx.sets[0].stream;
-  DevBuf d_chrom, d_start, d_end, d_score, d_perm, d_flag, d_tiles, d_total, o_chrom, o_start, o_end, o_score;
+namespace {
+// host bytes -> device through the pinned staging slots: `threads` copy every 64 MiB piece into a slot (non-temporal stores), the
+// copy engine takes it from there while the next piece is being filled
+void upload_bytes(DeviceCtx &ctx, const uint8_t *src, uint64_t n, uint8_t *d_dst, cudaStream_t st) {
+  const uint64_t CH = 64ull << 20;
+  const int n_slots = (int)ctx.slots.size();
+  const int threads = (int)std::min<uint64_t>(16, std::max<uint64_t>(2, host_cores_share() * 3 / 4));
+  for (auto &sl : ctx.slots) sl.h2d_pending = false;
+  uint64_t k = 0;
+  for (uint64_t off = 0; off < n; off += CH, k++) {
+    StageSlot &slot = ctx.slots[k % n_slots];
+    if (slot.h2d_pending) {
+      CU(cudaEventSynchronize(slot.ev_h2d));
+      slot.h2d_pending = false;
+    }
+    const uint64_t len = std::min(CH, n - off);
+    slot.ensure(len + 64);
+    std::vector<std::thread> th;
+    const uint64_t per = (len + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+      const uint64_t a0 = std::min(len, per * t), a1 = std::min(len, a0 + per);
+      if (a1 > a0) th.emplace_back([&, a0, a1] { stream_copy(slot.pin + a0, src + off + a0, a1 - a0); });
+    }
+    for (auto &t : th) t.join();
+    CU(cudaMemcpyAsync(d_dst + off, slot.pin, len, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(slot.ev_h2d, st));
+    slot.h2d_pending = true;
+  }
+  CU(cudaStreamSynchronize(st));
+  for (auto &sl : ctx.slots) sl.h2d_pending = false;
+}
+
+// str::parse::<f64> for the spellings the device leaves to the host (more than 19 significant digits, large exponents, inf / nan)
+bool parse_f64_host(const char *p, size_t n, double &out) {
+  if (n == 0 || n > 4000) return false;
+  for (size_t i = 0; i < n; i++) {
+    const char c = p[i];
+    if (c == 'x' || c == 'X' || c == '(' || c == 'p' || c == 'P') return false;  // strtod's hex floats and nan(...) are not Rust floats
+  }
+  char buf[4001];
+  memcpy(buf, p, n);
+  buf[n] = 0;
+  char *end = nullptr;
+  out = strtod(buf, &end);
+  return end == buf + n;
+}
+
+// collapse_adjacent_bins over device columns sorted or not (bedgraph_utils.rs:5-45): head flags, scan, compaction
+void collapse_device_columns(DeviceCtx &ctx, cudaStream_t st, DevBuf &d_chrom, DevBuf &d_start, DevBuf &d_end, DevBuf &d_score, uint64_t n, BdgRows &out) {
+  DevBuf d_perm, d_flag, d_tiles, d_total, o_chrom, o_start, o_end, o_score, g_chrom, g_start, g_end, g_score;
   auto release = [&] {
-    for (DevBuf *b : {&d_chrom, &d_start, &d_end, &d_score, &d_perm, &d_flag, &d_tiles, &d_total, &o_chrom, &o_start, &o_end, &o_score}) b->release();
+    for (DevBuf *b : {&d_perm, &d_flag, &d_tiles, &d_total, &o_chrom, &o_start, &o_end, &o_score, &g_chrom, &g_start, &g_end, &g_score}) b->release();
   };
   try {
-    upload(d_chrom, in.chrom.data(), n);
-    upload(d_start, in.start.data(), n);
-    upload(d_end, in.end.data(), n);
-    upload(d_score, in.score.data(), n);
     d_flag.ensure(16);
-    CU(cudaMemset(d_flag.p, 0, 16));
+    CU(cudaMemsetAsync(d_flag.p, 0, 16, st));
     BdgArgs a{};
     a.chrom = d_chrom.as<uint32_t>();
     a.start = d_start.as<long long>();
     a.end = d_end.as<long long>();
     a.score = d_score.as<double>();
     a.n = n;
-    a.n_tiles = (uint32_t)((n + 255) / 256);
+    const uint64_t n_tiles64 = (n + 255) / 256;
+    if (n_tiles64 > 0xffffffffull) fail("too many bedGraph rows");
+    a.n_tiles = (uint32_t)n_tiles64;
     a.unsorted = d_flag.as<unsigned int>();
     CU(launch_bdg_sorted_check(a, ctx.sm_count, st));
     unsigned int unsorted = 0;
     CU(cudaMemcpyAsync(&unsorted, d_flag.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (unsorted) {
-      // sort (chrom, start): permutation from the device radix sort, columns gathered on the host side of the copy
+      // sort (chrom, start): permutation from the device radix sort (library), columns gathered on the device
       d_perm.ensure(n * 4);
       CU(sort_rows_by_chrom_start(a.chrom, a.start, n, d_perm.as<uint32_t>(), st));
-      std::vector<uint32_t> perm(n);
-      CU(cudaMemcpy(perm.data(), d_perm.p, n * 4, cudaMemcpyDeviceToHost));
-      BdgRows s;
-      s.chrom.resize(n), s.start.resize(n), s.end.resize(n), s.score.resize(n);
-      for (uint64_t i = 0; i < n; i++) {
-        s.chrom[i] = in.chrom[perm[i]];
-        s.start[i] = in.start[perm[i]];
-        s.end[i] = in.end[perm[i]];
-        s.score[i] = in.score[perm[i]];
-      }
-      upload(d_chrom, s.chrom.data(), n);
-      upload(d_start, s.start.data(), n);
-      upload(d_end, s.end.data(), n);
-      upload(d_score, s.score.data(), n);
-      a.chrom = d_chrom.as<uint32_t>();
-      a.start = d_start.as<long long>();
-      a.end = d_end.as<long long>();
-      a.score = d_score.as<double>();
+      g_chrom.ensure(n * 4);
+      g_start.ensure(n * 8);
+      g_end.ensure(n * 8);
+      g_score.ensure(n * 8);
+      CU(launch_bdg_gather_rows(d_perm.as<uint32_t>(), n, a.chrom, a.start, a.end, a.score, g_chrom.as<uint32_t>(), g_start.as<long long>(), g_end.as<long long>(),
+                                g_score.as<double>(), ctx.sm_count, st));
+      a.chrom = g_chrom.as<uint32_t>();
+      a.start = g_start.as<long long>();
+      a.end = g_end.as<long long>();
+      a.score = g_score.as<double>();
     }
     d_tiles.ensure((size_t)a.n_tiles * 8 + 16);
     d_total.ensure(16);
@@ -1781,6 +1813,201 @@ void collapse_rows_device(const BdgRows &in, BdgRows &out, int device) {
       CU(cudaMemcpyAsync(out.score.data(), o_score.p, m * 8, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
+  } catch (...) {
+    release();
+    throw;
+  }
+  release();
+}
+}  // namespace
+
+// The whole of `collapse-bedgraph` between the file read and the text write (src/cli.rs:1149-1205): the raw bytes go to HBM,
+// lines / fields / numbers are parsed there, chromosome names become ranks (the host only sees the handful of distinct names),
+// and the rows are collapsed.  `names` returns the chromosome names in byte-string order = the meaning of out.chrom.
+void collapse_bedgraph_text(const uint8_t *text, uint64_t n, std::vector<std::string> &names, BdgRows &out, int device) {
+  out = BdgRows();
+  names.clear();
+  if (n == 0) return;
+  DeviceCtx &ctx = ctx_for(device);
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  cudaStream_t st = ctx.sets[0].stream;
+  DevBuf d_text, d_tiles, d_total, d_line_off, d_state, d_start, d_end, d_score, d_name_off, d_name_len, d_slow, d_cnt, d_vals;
+  DevBuf r_start, r_end, r_score, r_name_off, r_name_len, d_flag, d_seg_off, d_seg_len, d_seg_rank, d_chrom;
+  auto release = [&] {
+    for (DevBuf *b : {&d_text, &d_tiles, &d_total, &d_line_off, &d_state, &d_start, &d_end, &d_score, &d_name_off, &d_name_len, &d_slow, &d_cnt, &d_vals, &r_start,
+                      &r_end, &r_score, &r_name_off, &r_name_len, &d_flag, &d_seg_off, &d_seg_len, &d_seg_rank, &d_chrom})
+      b->release();
+  };
+  const bool dbg = env_u64("BND_DEBUG_TIMING", 0) != 0;
+  const double t0 = now_ms();
+  try {
+    d_text.ensure(n + 64);
+    upload_bytes(ctx, text, n, d_text.as<uint8_t>(), st);
+    const double t1 = now_ms();
+    // ---- lines ----
+    const uint64_t n_tiles64 = (n + BDG_TILE - 1) / BDG_TILE;
+    if (n_tiles64 > 0xffffffffull) fail("bedGraph too large");
+    BdgParseArgs pa{};
+    pa.text = d_text.as<uint8_t>();
+    pa.n_bytes = n;
+    pa.n_tiles = (uint32_t)n_tiles64;
+    d_tiles.ensure(n_tiles64 * 8 + 16);
+    d_total.ensure(16);
+    pa.tile_count = d_tiles.as<uint64_t>();
+    CU(launch_bdg_newline_count(pa, ctx.sm_count, st));
+    CU(launch_u64_scan(pa.tile_count, pa.n_tiles, d_total.as<unsigned long long>(), st));
+    unsigned long long n_nl = 0;
+    CU(cudaMemcpyAsync(&n_nl, d_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const bool ends_nl = text[n - 1] == '\n';
+    const uint64_t n_lines = n_nl + (ends_nl ? 0 : 1);
+    pa.n_lines = n_lines;
+    d_line_off.ensure((n_lines + 1) * 8);
+    pa.line_off = d_line_off.as<uint64_t>();
+    CU(launch_bdg_line_starts(pa, ctx.sm_count, st));
+    const uint64_t sentinel = ends_nl ? n : n + 1;
+    CU(cudaMemcpyAsync(pa.line_off + n_lines, &sentinel, 8, cudaMemcpyHostToDevice, st));
+    // ---- fields and numbers ----
+    d_state.ensure(n_lines + 16);
+    d_start.ensure(n_lines * 8);
+    d_end.ensure(n_lines * 8);
+    d_score.ensure(n_lines * 8);
+    d_name_off.ensure(n_lines * 8);
+    d_name_len.ensure(n_lines * 4);
+    d_cnt.ensure(16);
+    pa.state = d_state.as<uint8_t>();
+    pa.start = d_start.as<long long>();
+    pa.end = d_end.as<long long>();
+    pa.score = d_score.as<double>();
+    pa.name_off = d_name_off.as<uint64_t>();
+    pa.name_len = d_name_len.as<uint32_t>();
+    pa.n_slow = d_cnt.as<unsigned long long>();
+    pa.bad_line = d_cnt.as<unsigned long long>() + 1;
+    unsigned long long cnt[2] = {0, 0};
+    pa.slow_cap = 1u << 20;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      d_slow.ensure(pa.slow_cap * sizeof(BdgSlow));
+      pa.slow = d_slow.as<BdgSlow>();
+      const unsigned long long init[2] = {0ull, ~0ull};
+      CU(cudaMemcpyAsync(d_cnt.p, init, 16, cudaMemcpyHostToDevice, st));
+      CU(launch_bdg_parse_lines(pa, ctx.sm_count, st));
+      CU(cudaMemcpyAsync(cnt, d_cnt.p, 16, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (cnt[0] <= pa.slow_cap) break;
+      pa.slow_cap = cnt[0];  // more scores for the host than the list holds: size it and parse again
+    }
+    auto line_text = [&](uint64_t li) {  // for error messages: the line as the reference would print it
+      std::vector<uint64_t> lo(2);
+      CU(cudaMemcpy(lo.data(), pa.line_off + li, 16, cudaMemcpyDeviceToHost));
+      uint64_t e = std::min<uint64_t>(lo[1] - 1, n);
+      return std::string((const char *)text + lo[0], (const char *)text + std::min(e, lo[0] + 200));
+    };
+    if (cnt[1] != ~0ull) fail("invalid bedGraph line: " + line_text(cnt[1]));
+    const uint64_t n_slow = cnt[0];
+    if (n_slow) {
+      std::vector<BdgSlow> slow(n_slow);
+      CU(cudaMemcpy(slow.data(), d_slow.p, n_slow * sizeof(BdgSlow), cudaMemcpyDeviceToHost));
+      std::vector<double> vals(n_slow);
+      std::atomic<uint64_t> bad{~0ull};
+      const int threads = (int)std::min<uint64_t>(std::max<uint64_t>(1, n_slow / 4096), std::max(2u, host_cores_share()));
+      std::vector<std::thread> th;
+      for (int t = 0; t < threads; t++)
+        th.emplace_back([&, t] {
+          for (uint64_t k = (uint64_t)t; k < n_slow; k += (uint64_t)threads)
+            if (!parse_f64_host((const char *)text + slow[k].off, slow[k].len, vals[k])) {
+              uint64_t cur = bad.load();
+              while (slow[k].line < cur && !bad.compare_exchange_weak(cur, slow[k].line)) {
+              }
+            }
+        });
+      for (auto &t : th) t.join();
+      if (bad.load() != ~0ull) fail("invalid bedGraph line: " + line_text(bad.load()));
+      upload(d_vals, vals.data(), n_slow);
+      CU(launch_bdg_scatter_slow(d_slow.as<BdgSlow>(), d_vals.as<double>(), n_slow, pa.score, ctx.sm_count, st));
+    }
+    const double t2 = now_ms();
+    // ---- rows: drop the skipped lines ----
+    BdgRowArgs ra{};
+    ra.state = pa.state;
+    ra.n_lines = n_lines;
+    const uint64_t lt64 = (n_lines + COL_TILE - 1) / COL_TILE;
+    if (lt64 > 0xffffffffull) fail("too many bedGraph lines");
+    ra.n_tiles = (uint32_t)lt64;
+    d_tiles.ensure(lt64 * 8 + 16);
+    ra.tile_count = d_tiles.as<uint64_t>();
+    CU(launch_bdg_row_count(ra, ctx.sm_count, st));
+    CU(launch_u64_scan(ra.tile_count, ra.n_tiles, d_total.as<unsigned long long>(), st));
+    unsigned long long n_rows = 0;
+    CU(cudaMemcpyAsync(&n_rows, d_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_rows == 0) {
+      release();
+      return;
+    }
+    DevBuf *c_start = &d_start, *c_end = &d_end, *c_score = &d_score, *c_name_off = &d_name_off, *c_name_len = &d_name_len;
+    if (n_rows != n_lines) {
+      r_start.ensure(n_rows * 8);
+      r_end.ensure(n_rows * 8);
+      r_score.ensure(n_rows * 8);
+      r_name_off.ensure(n_rows * 8);
+      r_name_len.ensure(n_rows * 4);
+      ra.start = pa.start, ra.end = pa.end, ra.score = pa.score, ra.name_off = pa.name_off, ra.name_len = pa.name_len;
+      ra.o_start = r_start.as<long long>(), ra.o_end = r_end.as<long long>(), ra.o_score = r_score.as<double>();
+      ra.o_name_off = r_name_off.as<uint64_t>(), ra.o_name_len = r_name_len.as<uint32_t>();
+      CU(launch_bdg_compact_rows(ra, ctx.sm_count, st));
+      c_start = &r_start, c_end = &r_end, c_score = &r_score, c_name_off = &r_name_off, c_name_len = &r_name_len;
+    }
+    // ---- chromosome names -> ranks in byte-string order (polars sorts the string column bytewise) ----
+    BdgNameArgs na{};
+    na.text = pa.text;
+    na.name_off = c_name_off->as<uint64_t>();
+    na.name_len = c_name_len->as<uint32_t>();
+    na.n = n_rows;
+    const uint64_t rt64 = (n_rows + COL_TILE - 1) / COL_TILE;
+    na.n_tiles = (uint32_t)rt64;
+    d_flag.ensure(n_rows + 16);
+    na.flag = d_flag.as<uint8_t>();
+    na.tile_count = d_tiles.as<uint64_t>();
+    CU(launch_bdg_name_heads(na, ctx.sm_count, st));
+    CU(launch_u64_scan(na.tile_count, na.n_tiles, d_total.as<unsigned long long>(), st));
+    unsigned long long n_seg = 0;
+    CU(cudaMemcpyAsync(&n_seg, d_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    d_seg_off.ensure(n_seg * 8);
+    d_seg_len.ensure(n_seg * 4);
+    na.seg_name_off = d_seg_off.as<uint64_t>();
+    na.seg_name_len = d_seg_len.as<uint32_t>();
+    CU(launch_bdg_name_segments(na, ctx.sm_count, st));
+    std::vector<uint64_t> seg_off(n_seg);
+    std::vector<uint32_t> seg_len(n_seg), seg_rank(n_seg);
+    CU(cudaMemcpyAsync(seg_off.data(), d_seg_off.p, n_seg * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(seg_len.data(), d_seg_len.p, n_seg * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    {
+      std::map<std::string, uint32_t> rank_of;
+      std::vector<std::map<std::string, uint32_t>::iterator> it_of(n_seg, rank_of.end());
+      for (uint64_t k = 0; k < n_seg; k++) it_of[k] = rank_of.emplace(std::string((const char *)text + seg_off[k], seg_len[k]), 0u).first;
+      uint32_t r = 0;
+      for (auto &kv : rank_of) {
+        kv.second = r++;
+        names.push_back(kv.first);
+      }
+      for (uint64_t k = 0; k < n_seg; k++) seg_rank[k] = it_of[k]->second;
+    }
+    upload(d_seg_rank, seg_rank.data(), n_seg);
+    na.seg_rank = d_seg_rank.as<uint32_t>();
+    d_chrom.ensure(n_rows * 4);
+    na.chrom = d_chrom.as<uint32_t>();
+    CU(launch_bdg_assign_chrom(na, ctx.sm_count, st));
+    const double t3 = now_ms();
+    // the text and the per-line scratch are no longer needed: make room for the sort / the output
+    for (DevBuf *b : {&d_text, &d_line_off, &d_state, &d_slow, &d_vals, &d_flag, &d_seg_off, &d_seg_len}) b->release();
+    collapse_device_columns(ctx, st, d_chrom, *c_start, *c_end, *c_score, n_rows, out);
+    if (dbg)
+      fprintf(stderr, "[bnd] collapse-bedgraph: %llu bytes, %llu lines, %llu rows, %llu scores parsed on the host, %llu name segments; upload %.2f ms, lines + parse %.2f ms, "
+                      "rows + names %.2f ms, collapse %.2f ms -> %zu rows\n",
+              (unsigned long long)n, (unsigned long long)n_lines, (unsigned long long)n_rows, (unsigned long long)n_slow, (unsigned long long)n_seg, t1 - t0, t2 - t1,
+              t3 - t2, now_ms() - t3, out.chrom.size());
   } catch (...) {
     release();
     throw;

@@ -131,13 +131,13 @@ void device_inflate(const uint8_t *bgzf, uint64_t n_bytes, std::vector<uint8_t> 
 
 int device_count();
 
-// collapse_adjacent_bins (bedgraph_utils.rs:5-45) on the device.  Inputs are rows in file order with the chromosome
-// as its rank in byte-string order; outputs are the collapsed groups in (chrom, start) order.
+// collapse-bedgraph (src/cli.rs:1149-1205 + bedgraph_utils.rs:5-45): the raw bytes of the bedGraph are parsed and collapsed on
+// the device.  Outputs are the collapsed groups in (chrom, start) order; out.chrom indexes `names` (byte-string order).
 struct BdgRows {
   std::vector<uint32_t> chrom;
   std::vector<long long> start, end;
   std::vector<double> score;
 };
-void collapse_rows_device(const BdgRows &in, BdgRows &out, int device);
+void collapse_bedgraph_text(const uint8_t *text, uint64_t n, std::vector<std::string> &names, BdgRows &out, int device);
 
 }  // namespace bnd

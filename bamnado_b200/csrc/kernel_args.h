@@ -240,6 +240,65 @@ struct BdgArgs {
   double *out_score;
 };
 
+// ---- collapse-bedgraph reader on the device (bedgraph_parse.cuh) ------------------------------------------------------------
+constexpr int COL_TILE = 256;  // rows per CTA pass of the head-flag / compaction kernels (collapse.cuh: COL_THREADS)
+constexpr int BDG_THREADS = 256;
+constexpr uint32_t BDG_PER_THREAD = 16;
+constexpr uint32_t BDG_TILE = BDG_THREADS * BDG_PER_THREAD;  // bytes per newline tile
+
+struct BdgSlow {  // a score the device does not convert itself: the host parses text[off, off + len)
+  uint64_t line, off;
+  uint32_t len, pad;
+};
+
+struct BdgParseArgs {
+  const uint8_t *text;
+  uint64_t n_bytes;
+  uint64_t *tile_count;  // [n_tiles] newlines per tile of BDG_TILE bytes -> exclusive offsets after the scan
+  uint32_t n_tiles;
+  uint64_t *line_off;    // [n_lines + 1]
+  uint64_t n_lines;
+  // per line
+  uint8_t *state;        // 0: skipped (blank, '#', fewer than four fields), 1: row, 2: row whose score the host converts, 3: bad integer
+  long long *start, *end;
+  double *score;
+  uint64_t *name_off;
+  uint32_t *name_len;
+  BdgSlow *slow;
+  unsigned long long *n_slow;
+  uint64_t slow_cap;
+  unsigned long long *bad_line;  // smallest line index with an unparsable start / end (initialised to ~0)
+};
+
+struct BdgRowArgs {  // lines -> rows (skipped lines dropped)
+  const uint8_t *state;
+  uint64_t n_lines;
+  uint64_t *tile_count;
+  uint32_t n_tiles;
+  const long long *start, *end;
+  const double *score;
+  const uint64_t *name_off;
+  const uint32_t *name_len;
+  long long *o_start, *o_end;
+  double *o_score;
+  uint64_t *o_name_off;
+  uint32_t *o_name_len;
+};
+
+struct BdgNameArgs {  // chromosome names -> ranks
+  const uint8_t *text;
+  const uint64_t *name_off;
+  const uint32_t *name_len;
+  uint64_t n;
+  uint8_t *flag;           // [n] 1: the name differs from the previous row's
+  uint64_t *tile_count;
+  uint32_t n_tiles;
+  uint64_t *seg_name_off;  // [n_segments]
+  uint32_t *seg_name_len;
+  const uint32_t *seg_rank;  // [n_segments] rank of the segment's name in byte-string order
+  uint32_t *chrom;           // [n]
+};
+
 constexpr int MULTI_MAX_BAMS = 64;
 struct MultiArgs {
   const uint32_t *counts[MULTI_MAX_BAMS];  // dense per-bin counts of each BAM (identical geometry)

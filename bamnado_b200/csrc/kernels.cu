@@ -11,6 +11,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #endif
 
+#include "bedgraph_parse.cuh"
 #include "bigwig.cuh"
 #include "collapse.cuh"
 #include "finalize.cuh"
@@ -225,6 +226,59 @@ cudaError_t launch_multi_emit(const MultiArgs &a, int sm_count, cudaStream_t s) 
 cudaError_t launch_multi_rows(const RunArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_runs == 0) return cudaSuccess;
   BND_LAUNCH(multi_rows_kernel, dim3(grid_for(a.n_runs, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+
+// ---- collapse-bedgraph reader (bedgraph_parse.cuh) ---------------------------------------------------------------------------
+cudaError_t launch_bdg_newline_count(const BdgParseArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_newline_count_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(BDG_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_line_starts(const BdgParseArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_line_starts_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(BDG_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_parse_lines(const BdgParseArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_lines == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_parse_lines_kernel, dim3(grid_for(a.n_lines, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_scatter_slow(const BdgSlow *slow, const double *vals, uint64_t n, double *score, int sm_count, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_scatter_slow_kernel, dim3(grid_for(n, 256, (uint64_t)sm_count * 8)), dim3(256), 0, s, slow, vals, n, score);
+  return launched();
+}
+cudaError_t launch_bdg_row_count(const BdgRowArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_row_count_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_compact_rows(const BdgRowArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_compact_rows_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_name_heads(const BdgNameArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_name_heads_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_name_segments(const BdgNameArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_name_segments_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_assign_chrom(const BdgNameArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_assign_chrom_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bdg_gather_rows(const uint32_t *perm, uint64_t n, const uint32_t *chrom, const long long *start, const long long *end, const double *score,
+                                   uint32_t *o_chrom, long long *o_start, long long *o_end, double *o_score, int sm_count, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  BND_LAUNCH(bdg_gather_rows_kernel, dim3(grid_for(n, 256, (uint64_t)sm_count * 8)), dim3(256), 0, s, perm, n, chrom, start, end, score, o_chrom, o_start, o_end, o_score);
   return launched();
 }
 

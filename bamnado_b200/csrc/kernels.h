@@ -33,6 +33,18 @@ cudaError_t launch_bdg_sorted_check(const BdgArgs &a, int sm_count, cudaStream_t
 cudaError_t launch_bdg_count(const BdgArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_bdg_emit(const BdgArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_u64_scan(uint64_t *v, uint32_t n, unsigned long long *total_out, cudaStream_t s);
+// collapse-bedgraph reader (bedgraph_parse.cuh)
+cudaError_t launch_bdg_newline_count(const BdgParseArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_line_starts(const BdgParseArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_parse_lines(const BdgParseArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_scatter_slow(const BdgSlow *slow, const double *vals, uint64_t n, double *score, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_row_count(const BdgRowArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_compact_rows(const BdgRowArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_name_heads(const BdgNameArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_name_segments(const BdgNameArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_assign_chrom(const BdgNameArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bdg_gather_rows(const uint32_t *perm, uint64_t n, const uint32_t *chrom, const long long *start, const long long *end, const double *score,
+                                   uint32_t *o_chrom, long long *o_start, long long *o_end, double *o_score, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_bits(const MultiArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_or(uint32_t *dst, const uint32_t *src, uint32_t n_src, uint64_t n_words, int sm_count, cudaStream_t s);
 cudaError_t launch_multi_text_len(const MultiTextArgs &a, int sm_count, cudaStream_t s);

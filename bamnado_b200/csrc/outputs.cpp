@@ -2,6 +2,11 @@
 // collapse-bedgraph file front end and the CLI mirror of src/cli.rs for the three coverage subcommands.
 #include "outputs.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -10,6 +15,7 @@
 #include <iostream>
 #include <map>
 #include <sstream>
+#include <thread>
 
 namespace bnd {
 
@@ -39,88 +45,102 @@ void multi_to_tsv(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int
 }
 
 // ---- collapse-bedgraph (src/cli.rs:1149-1205) -----------------------------------------------------------------------------------
+// The input's bytes are handed to the device as they are (Pileup engine: collapse_bedgraph_text); what comes back are the
+// collapsed groups.  Their text (name, start, end, shortest round-trip score like polars' CsvWriter) is formatted here by all
+// host cores at once and written with one positional write per thread.
 namespace {
-void collapse_stream(std::istream &in, std::ostream &out) {
-  std::vector<std::string> names;
-  std::map<std::string, uint32_t> id_of;
-  BdgRows rows;
-  std::vector<uint32_t> name_id;
-  std::string line;
-  while (std::getline(in, line)) {
-    size_t a = 0, b = line.size();
-    while (a < b && isspace((unsigned char)line[a])) a++;
-    while (b > a && isspace((unsigned char)line[b - 1])) b--;
-    if (a == b || line[a] == '#') continue;
-    std::vector<std::string> parts;
-    for (size_t i = a; i < b;) {
-      while (i < b && isspace((unsigned char)line[i])) i++;
-      size_t j = i;
-      while (j < b && !isspace((unsigned char)line[j])) j++;
-      if (j > i) parts.push_back(line.substr(i, j - i));
-      i = j;
+void write_collapsed(const std::vector<std::string> &names, const BdgRows &res, int fd, bool seekable) {
+  const size_t m = res.chrom.size();
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int threads = (int)std::max<size_t>(1, std::min<size_t>(hw, m / 65536 + 1));
+  std::vector<std::string> parts((size_t)threads);
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++)
+    th.emplace_back([&, t] {
+      const size_t lo = m * (size_t)t / (size_t)threads, hi = m * ((size_t)t + 1) / (size_t)threads;
+      std::string &text = parts[(size_t)t];
+      text.reserve((hi - lo) * 32);
+      char buf[48];
+      for (size_t i = lo; i < hi; i++) {
+        text += names[res.chrom[i]];
+        text.push_back('\t');
+        text.append(buf, (size_t)snprintf(buf, sizeof buf, "%lld", res.start[i]));
+        text.push_back('\t');
+        text.append(buf, (size_t)snprintf(buf, sizeof buf, "%lld", res.end[i]));
+        text.push_back('\t');
+        text += format_f64(res.score[i]);
+        text.push_back('\n');
+      }
+    });
+  for (auto &t : th) t.join();
+  auto write_all = [&](const std::string &text, off_t at) {
+    size_t done = 0;
+    while (done < text.size()) {
+      const ssize_t w = seekable ? pwrite(fd, text.data() + done, text.size() - done, at + (off_t)done) : write(fd, text.data() + done, text.size() - done);
+      if (w <= 0) fail("write error on the collapsed bedGraph");
+      done += (size_t)w;
     }
-    if (parts.size() < 4) continue;
-    char *e1 = nullptr, *e2 = nullptr, *e3 = nullptr;
-    errno = 0;
-    long long s = strtoll(parts[1].c_str(), &e1, 10), e = strtoll(parts[2].c_str(), &e2, 10);
-    double sc = strtod(parts[3].c_str(), &e3);
-    if (*e1 || *e2 || *e3 || e1 == parts[1].c_str() || e2 == parts[2].c_str() || e3 == parts[3].c_str())
-      fail("invalid bedGraph line: " + line);
-    auto it = id_of.find(parts[0]);
-    if (it == id_of.end()) {
-      it = id_of.emplace(parts[0], (uint32_t)names.size()).first;
-      names.push_back(parts[0]);
-    }
-    name_id.push_back(it->second);
-    rows.start.push_back(s);
-    rows.end.push_back(e);
-    rows.score.push_back(sc);
+  };
+  off_t at = 0;
+  for (auto &p : parts) {
+    write_all(p, at);
+    at += (off_t)p.size();
   }
-  // chromosome rank = position in byte-string order (polars sorts the string column bytewise)
-  std::vector<uint32_t> rank(names.size());
-  {
-    uint32_t r = 0;
-    for (auto &kv : id_of) rank[kv.second] = r++;
-  }
-  std::vector<std::string> by_rank(names.size());
-  for (auto &kv : id_of) by_rank[rank[kv.second]] = kv.first;
-  rows.chrom.resize(name_id.size());
-  for (size_t i = 0; i < name_id.size(); i++) rows.chrom[i] = rank[name_id[i]];
-  BdgRows res;
-  collapse_rows_device(rows, res, -1);
-  std::string text;
-  for (size_t i = 0; i < res.chrom.size(); i++) {
-    text += by_rank[res.chrom[i]];
-    text.push_back('\t');
-    text += std::to_string(res.start[i]);
-    text.push_back('\t');
-    text += std::to_string(res.end[i]);
-    text.push_back('\t');
-    text += format_f64(res.score[i]);
-    text.push_back('\n');
-    if (text.size() > (1u << 22)) {
-      out.write(text.data(), (std::streamsize)text.size());
-      text.clear();
-    }
-  }
-  out.write(text.data(), (std::streamsize)text.size());
-  out.flush();
-  if (!out) fail("write error on the collapsed bedGraph");
 }
 }  // namespace
 
 void collapse_bedgraph_file(const char *in_path, const char *out_path) {
-  std::ifstream fin;
-  std::ofstream fout;
+  std::vector<std::string> names;
+  BdgRows res;
   if (in_path) {
-    fin.open(in_path, std::ios::binary);
-    if (!fin) fail(std::string("cannot open ") + in_path);
+    const int fd = ::open(in_path, O_RDONLY);
+    if (fd < 0) fail(std::string("cannot open ") + in_path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+      close(fd);
+      fail(std::string("cannot stat ") + in_path);
+    }
+    const uint64_t n = (uint64_t)st.st_size;
+    void *m = n && S_ISREG(st.st_mode) ? mmap(nullptr, n, PROT_READ, MAP_SHARED, fd, 0) : MAP_FAILED;
+    try {
+      if (m != MAP_FAILED) {
+        collapse_bedgraph_text((const uint8_t *)m, n, names, res, -1);
+      } else {  // pipes, character devices, empty files
+        std::string all;
+        char buf[1 << 16];
+        ssize_t r;
+        while ((r = read(fd, buf, sizeof buf)) > 0) all.append(buf, (size_t)r);
+        if (r < 0) fail(std::string("read error on ") + in_path);
+        collapse_bedgraph_text((const uint8_t *)all.data(), all.size(), names, res, -1);
+      }
+    } catch (...) {
+      if (m != MAP_FAILED) munmap(m, n);
+      close(fd);
+      throw;
+    }
+    if (m != MAP_FAILED) munmap(m, n);
+    close(fd);
+  } else {
+    std::string all;
+    char buf[1 << 16];
+    size_t r;
+    while ((r = fread(buf, 1, sizeof buf, stdin)) > 0) all.append(buf, r);
+    collapse_bedgraph_text((const uint8_t *)all.data(), all.size(), names, res, -1);
   }
   if (out_path) {
-    fout.open(out_path, std::ios::binary | std::ios::trunc);
-    if (!fout) fail(std::string("cannot create ") + out_path);
+    const int fd = ::open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) fail(std::string("cannot create ") + out_path);
+    try {
+      write_collapsed(names, res, fd, true);
+    } catch (...) {
+      close(fd);
+      throw;
+    }
+    if (close(fd) != 0) fail(std::string("write error on ") + out_path);
+  } else {
+    fflush(stdout);
+    write_collapsed(names, res, 1, false);
   }
-  collapse_stream(in_path ? (std::istream &)fin : std::cin, out_path ? (std::ostream &)fout : std::cout);
 }
 
 // ---- run_cli (src/cli.rs:737-757) for bam-coverage / multi-bam-coverage / collapse-bedgraph -------------------------------------

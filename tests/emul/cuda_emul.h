@@ -208,6 +208,14 @@ inline unsigned __float_as_uint(float f) {
   memcpy(&u, &f, 4);
   return u;
 }
+inline double __ddiv_rn(double a, double b) {
+  volatile double r = a / b;
+  return r;
+}
+inline double __dmul_rn(double a, double b) {
+  volatile double r = a * b;
+  return r;
+}
 // round-to-nearest single operations (the emulator build uses -ffp-contract=off semantics: separate statements)
 inline float __fmul_rn(float a, float b) {
   volatile float r = a * b;

@@ -195,6 +195,37 @@ def test_collapse_bedgraph_matches_oracle(backend, oracle, tmp_path, make_bam):
         assert len(a.read_text().splitlines()) < len(sel)
 
 
+def test_collapse_bedgraph_reader_edge_cases(backend, oracle, tmp_path):
+    # the device-side reader (src/cli.rs:1160-1175: trim, skip blank / '#' / short lines, split_whitespace, str::parse): every way a
+    # number can be spelled - converted on the device (<= 19 digits, |exp| <= 22, mantissa < 2^53) or handed to the host - CRLF line
+    # ends, runs of blanks and tabs, a last line without '\n', names that repeat after another name
+    scores = ["0", "0.0", "-0.0", "1", "1.0", "+2.5", "3.", ".5", "1e3", "1E-3", "2.5e+2", "0.1", "0.30000000000000004", "1.2345678901234567",
+              "12345678901234567890", "9007199254740993", "1e23", "1e-23", "4.9e-324", "1.7976931348623157e308", "inf", "-inf", "Infinity", "1e400",
+              "0.000001", "000123.4500", "0.10000000000000001", "123456789012345678", "5e22", "5e-22", "0e999", "1e22", "9007199254740992", "0.3"]
+    lines = ["# header comment", "", "   ", "chrZ 1 2", "chrZ\t1"]
+    pos = 0
+    for k, sc in enumerate(scores):
+        name = ["chrB", "chrA", "chrB", "chr10"][k % 4]
+        sep = ["\t", " ", "  \t ", "\t\t"][k % 4]
+        lines.append(f"  {name}{sep}{pos}{sep}{pos + 10}{sep}{sc}  extra column" + ("\r" if k % 3 == 0 else ""))
+        if k % 5 != 4:
+            pos += 10
+    lines += ["chrA\t-20\t-10\t7", "chrA\t+5\t9223372036854775807\t7", "chrA\t-9223372036854775808\t0\t7"]
+    for tail in ("\n", ""):
+        src, a, b = tmp_path / "edge.bdg", tmp_path / "edge_a.bdg", tmp_path / "edge_b.bdg"
+        src.write_bytes(("\n".join(lines) + tail).encode())
+        backend.collapse_bedgraph(src, a)
+        oracle.collapse_bedgraph(src, b)
+        assert a.read_bytes() == b.read_bytes()
+        assert len(a.read_text().splitlines()) >= 20
+    for bad in ("chr1\t1.0\t2\t3", "chr1\t1\t2x\t3", "chr1\t1\t2\t3..0", "chr1\t1\t2\t0x10", "chr1\t1\t9223372036854775808\t1", "chr1\t-\t2\t3",
+                "chr1\t1\t2\t1e", "chr1\t1\t2\tnan(1)"):
+        src = tmp_path / "bad.bdg"
+        src.write_text("chr1\t0\t1\t1\n" + bad + "\n")
+        with pytest.raises(RuntimeError, match="invalid bedGraph line"):
+            backend.collapse_bedgraph(src, tmp_path / "bad_out.bdg")
+
+
 def test_collapse_bedgraph_random_rows_match_oracle(backend, oracle, tmp_path):
     # synthetic rows built to sit on every decision of collapse_adjacent_bins (bedgraph_utils.rs:5-45): touching and
     # gapped bins, scores equal, within and just beyond 1e-6 of the previous ROW (drift chains), repeated starts,
