@@ -357,6 +357,10 @@ struct ReaderPool {
         if (map) {
           stream_copy(slot.pin + j.off, map + s.begin + j.off, j.len);
           got = j.len;
+          // drop the page-table entries of the pages this piece covers completely (the page cache keeps the data): otherwise
+          // unmapping the whole file at the end costs ~10 ms per GB on the caller's critical path
+          const uintptr_t a0 = ((uintptr_t)(map + s.begin + j.off) + 4095) & ~(uintptr_t)4095, a1 = (uintptr_t)(map + s.begin + j.off + j.len) & ~(uintptr_t)4095;
+          if (a1 > a0) madvise((void *)a0, a1 - a0, MADV_DONTNEED);
         }
         while (got < j.len) {
           ssize_t r = pread(fd, slot.pin + j.off + got, j.len - got, (off_t)(s.begin + j.off + got));
@@ -1842,6 +1846,7 @@ void collapse_bedgraph_text(const uint8_t *text, uint64_t n, std::vector<std::st
   const double t0 = now_ms();
   try {
     d_text.ensure(n + 64);
+    const double t_alloc = now_ms();
     upload_bytes(ctx, text, n, d_text.as<uint8_t>(), st);
     const double t1 = now_ms();
     // ---- lines ----
@@ -2004,10 +2009,10 @@ void collapse_bedgraph_text(const uint8_t *text, uint64_t n, std::vector<std::st
     for (DevBuf *b : {&d_text, &d_line_off, &d_state, &d_slow, &d_vals, &d_flag, &d_seg_off, &d_seg_len}) b->release();
     collapse_device_columns(ctx, st, d_chrom, *c_start, *c_end, *c_score, n_rows, out);
     if (dbg)
-      fprintf(stderr, "[bnd] collapse-bedgraph: %llu bytes, %llu lines, %llu rows, %llu scores parsed on the host, %llu name segments; upload %.2f ms, lines + parse %.2f ms, "
+      fprintf(stderr, "[bnd] collapse-bedgraph: %llu bytes, %llu lines, %llu rows, %llu scores parsed on the host, %llu name segments; device buffer %.2f ms, upload %.2f ms, lines + parse %.2f ms, "
                       "rows + names %.2f ms, collapse %.2f ms -> %zu rows\n",
-              (unsigned long long)n, (unsigned long long)n_lines, (unsigned long long)n_rows, (unsigned long long)n_slow, (unsigned long long)n_seg, t1 - t0, t2 - t1,
-              t3 - t2, now_ms() - t3, out.chrom.size());
+              (unsigned long long)n, (unsigned long long)n_lines, (unsigned long long)n_rows, (unsigned long long)n_slow, (unsigned long long)n_seg, t_alloc - t0, t1 - t_alloc,
+              t2 - t1, t3 - t2, now_ms() - t3, out.chrom.size());
   } catch (...) {
     release();
     throw;
@@ -2260,9 +2265,12 @@ void Pileup::bedgraph_text(std::string &out) {
 // Fills this shard's pieces into the output file `fd` (size `total`; the first `prealloc` bytes already have pages) and
 // closes it.  Regular files: the writer threads memcpy into a shared mapping (parallel page-cache fills; pwrite would
 // serialise on the inode lock); anything unmappable falls back to positional writes.
-void Pileup::write_pieces(TextJob &job, int fd, const std::string &path, uint64_t total, uint64_t prealloc, bool truncate_at_end) {
+void Pileup::write_pieces(TextJob &job, int fd, const std::string &path, uint64_t total, uint64_t prealloc, bool truncate_at_end, char *premap,
+                          uint64_t premap_len) {
   DeviceCtx &ctx = *im_->ctx;
   char *map = nullptr;
+  uint64_t map_len = total;
+  const double t_w0 = now_ms();
   try {
     // every byte the writers will touch must be backed before it is mapped: a store into a hole of a sparse file raises
     // SIGBUS when the file system is full, which would take the host process down instead of returning an error
@@ -2271,17 +2279,28 @@ void Pileup::write_pieces(TextJob &job, int fd, const std::string &path, uint64_
       const uint64_t a0 = pc.out_off, a1 = pc.out_off + (pc.dev_end - pc.dev_begin);
       if (a1 > prealloc && posix_fallocate(fd, (off_t)std::max(a0, prealloc), (off_t)(a1 - std::max(a0, prealloc))) != 0) backed = false;
     }
-    if (backed && total) {
+    if (backed && total && premap && total <= premap_len) {
+      map = premap;  // the mapping whose pages were touched while the pile-up ran
+      map_len = premap_len;
+      premap = nullptr;
+    } else if (backed && total) {
       void *m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
       if (m != MAP_FAILED) map = (char *)m;
+    }
+    if (premap) {
+      munmap(premap, premap_len);
+      premap = nullptr;
     }
     // the writers spend most of their time in page faults, so more of them than cores pays: 8 -> 24 threads on the
     // 16-core B200 hosts takes the drain of 2.1 GB from 155 to 125 ms (profiles/r1_sweeps.md)
     const unsigned hw = host_cores_share();
     const int writers = (int)env_u64("BND_WRITERS", std::min(32u, std::max(4u, hw + hw / 2)));
+    const bool nt = env_u64("BND_WRITE_NT", 1) != 0;  // the text is not read again by this process: keep it out of the caches
     if (map)
-      drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, writers,
-                 [map](const uint8_t *src, uint64_t len, uint64_t off) { memcpy(map + off, src, len); });
+      drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, writers, [map, nt](const uint8_t *src, uint64_t len, uint64_t off) {
+        if (nt && len >= 4096) stream_copy((uint8_t *)map + off, src, len);
+        else memcpy(map + off, src, len);
+      });
     else
       drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, writers, [fd](const uint8_t *src, uint64_t len, uint64_t off) {
         uint64_t done = 0;
@@ -2292,22 +2311,24 @@ void Pileup::write_pieces(TextJob &job, int fd, const std::string &path, uint64_
         }
       });
   } catch (...) {
-    if (map) munmap(map, total);
+    if (map) munmap(map, map_len);
+    if (premap) munmap(premap, premap_len);
     close(fd);
     throw;
   }
   // The file's pages are complete; tearing down the page-table entries of the mapping (26 ms for 2 GB) only concerns this
   // process's address space, so it is left to a background thread and the file is closed right away.
-  if (map) g_unmapper.submit(map, total);
+  const double t_drained = now_ms();
+  if (map) g_unmapper.submit(map, map_len);
   if (truncate_at_end && ftruncate(fd, (off_t)total) != 0) {
     close(fd);
     fail("write error on " + path);
   }
   if (close(fd) != 0) fail("write error on " + path);
+  if (env_u64("BND_DEBUG_TIMING", 0)) fprintf(stderr, "[bnd] write_pieces: drain %.2f ms, truncate + close %.2f ms\n", t_drained - t_w0, now_ms() - t_drained);
 }
 
 void Pileup::to_bedgraph(const std::string &path) {
-  g_unmapper.reap();
   DeviceCtx &ctx = *im_->ctx;
   const double t00 = now_ms();
   int fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
@@ -2316,9 +2337,18 @@ void Pileup::to_bedgraph(const std::string &path) {
   // (one fallocate of an upper bound of the text size: rows <= min(bins, 2 reads + chunks), <= name + 46 bytes each).
   // Filling pre-allocated page-cache pages runs at memory speed (16 GB/s with 8 threads on the B200 hosts) instead of the
   // 6 GB/s of faulting them in one by one; the surplus is cut off by the final ftruncate.
-  std::atomic<uint64_t> prealloc_done{0};
+  std::atomic<uint64_t> prealloc_done{0}, touched{0};
   std::atomic<bool> prealloc_stop{false};
   std::thread prealloc_thread;
+  std::vector<std::thread> touchers;
+  char *premap = nullptr;
+  uint64_t premap_len = 0;
+  auto stop_background = [&] {
+    prealloc_stop.store(true);
+    if (prealloc_thread.joinable()) prealloc_thread.join();
+    for (auto &t : touchers) t.join();
+    touchers.clear();
+  };
   try {
     if (!accumulated_ && env_u64("BND_PREALLOC", 1)) {
       const uint64_t rows_cap = std::min<uint64_t>(shard_bins_upper(), 2 * (geo_.n_mapped + geo_.n_unmapped) + geo_.total_chunks() + 16);
@@ -2335,7 +2365,15 @@ void Pileup::to_bedgraph(const std::string &path) {
       uint64_t want = (uint64_t)((double)rows_cap * per_row * 0.72);
       want = std::min<uint64_t>(want, (shard_.byte_end - shard_.byte_begin) * 6 / 10);
       want &= ~(uint64_t)4095;
-      if (want > (8ull << 20)) {
+      if (want > env_u64("BND_PREALLOC_MIN", 8ull << 20)) {
+        // The same range is mapped now and its pages are touched behind the allocation (one store per page: the page-table entry
+        // exists and is writable when the text arrives), so that the writers later run at copy speed instead of taking one page
+        // fault per 4 KiB.  Plain stores take the per-VMA lock only; MADV_POPULATE_WRITE held the process's mmap lock for the
+        // whole range and stalled every CUDA driver call behind it (profiles/r1_sweeps.md).
+        if (env_u64("BND_PRETOUCH", 1)) {
+          void *m = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+          if (m != MAP_FAILED) premap = (char *)m, premap_len = want;
+        }
         prealloc_thread = std::thread([fd, want, &prealloc_done, &prealloc_stop] {
           const uint64_t step = 64ull << 20;
           uint64_t off = 0;
@@ -2343,20 +2381,38 @@ void Pileup::to_bedgraph(const std::string &path) {
             const uint64_t n = std::min(step, want - off);
             if (posix_fallocate(fd, (off_t)off, (off_t)n) != 0) break;
             off += n;
+            prealloc_done.store(off, std::memory_order_release);
           }
           prealloc_done.store(off);
         });
+        if (premap) {
+          const int n_touch = (int)env_u64("BND_TOUCHERS", std::max(1u, std::min(4u, host_cores_share() / 4)));  // 2 / 4 threads touch 1.4 / 2.1 GB of pages behind a 300 ms pile-up
+          for (int t = 0; t < n_touch; t++)
+            touchers.emplace_back([premap, want, t, n_touch, &prealloc_done, &prealloc_stop, &touched] {
+              const uint64_t step = 8ull << 20;  // touchers interleave 8 MiB blocks behind the allocation front
+              for (uint64_t blk = (uint64_t)t; blk * step < want; blk += (uint64_t)n_touch) {
+                const uint64_t b0 = blk * step, b1 = std::min(want, b0 + step);
+                while (prealloc_done.load(std::memory_order_acquire) < b1) {
+                  if (prealloc_stop.load(std::memory_order_relaxed)) return;
+                  std::this_thread::sleep_for(std::chrono::microseconds(200));
+                }
+                if (prealloc_stop.load(std::memory_order_relaxed)) return;
+                for (uint64_t p = b0; p < b1; p += 4096) ((volatile char *)premap)[p] = 0;
+                touched.fetch_add(b1 - b0, std::memory_order_relaxed);
+              }
+            });
+        }
       }
     }
     ensure_finalized();
   } catch (...) {
-    prealloc_stop.store(true);
-    if (prealloc_thread.joinable()) prealloc_thread.join();
+    stop_background();
+    if (premap) munmap(premap, premap_len);
     close(fd);
     throw;
   }
-  prealloc_stop.store(true);
-  if (prealloc_thread.joinable()) prealloc_thread.join();
+  stop_background();
+  g_unmapper.reap();  // the previous job's output mapping was torn down while this pile-up ran
   const uint64_t prealloc = prealloc_done.load();
   const double t0 = now_ms();
   std::lock_guard<std::mutex> lock(ctx.mu);
@@ -2370,14 +2426,15 @@ void Pileup::to_bedgraph(const std::string &path) {
     for (size_t r = 0; r < mine.size(); r++) mine[r] = job.span[r].second - job.span[r].first;
     out_bytes = place_pieces(job, mine.data(), 1, 0);
   } catch (...) {
+    if (premap) munmap(premap, premap_len);
     close(fd);
     throw;
   }
-  write_pieces(job, fd, path, out_bytes, prealloc, true);
+  write_pieces(job, fd, path, out_bytes, prealloc, true, premap, premap_len);
   tm_.text_ms = now_ms() - t0;
   if (env_u64("BND_DEBUG_TIMING", 0))
-    fprintf(stderr, "[bnd] to_bedgraph: pile-up %.2f ms (prealloc %llu MB), format %.2f ms, drain + close %.2f ms, %llu bytes\n", t0 - t00,
-            (unsigned long long)(prealloc >> 20), t1 - t0, now_ms() - t1, (unsigned long long)job.nbytes);
+    fprintf(stderr, "[bnd] to_bedgraph: pile-up %.2f ms (prealloc %llu MB, %llu MB touched), format %.2f ms, drain + close %.2f ms, %llu bytes\n", t0 - t00,
+            (unsigned long long)(prealloc >> 20), (unsigned long long)(touched.load() >> 20), t1 - t0, now_ms() - t1, (unsigned long long)job.nbytes);
 }
 
 // ---- to_bigwig (coverage_analysis.rs:642-759) ------------------------------------------------------------------------------------

@@ -101,7 +101,8 @@ class Pileup {
   std::unique_ptr<Impl> im_;
   void format_text(TextJob &job);
   uint64_t place_pieces(TextJob &job, const uint64_t *bytes_all, int world, int rank, uint64_t base = 0) const;
-  void write_pieces(TextJob &job, int fd, const std::string &path, uint64_t total, uint64_t prealloc, bool truncate_at_end);
+  void write_pieces(TextJob &job, int fd, const std::string &path, uint64_t total, uint64_t prealloc, bool truncate_at_end, char *premap = nullptr,
+                    uint64_t premap_len = 0);
 
   void open();
   Range range_for_chunks(uint64_t chunk_lo, uint64_t chunk_hi) const;

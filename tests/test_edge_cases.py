@@ -202,3 +202,21 @@ def test_chromosome_query_leaves_whole_object_outputs_alone(backend, oracle, tmp
         assert len(sig) > 0
         assert h.bedgraph_text() == whole == ref_out.read_bytes()
         assert h.stats() == ostats
+
+
+@pytest.mark.parametrize("touchers", ["0", "3"])
+def test_to_bedgraph_with_background_page_touching(backend, oracle, tmp_path, make_bam, monkeypatch, touchers):
+    # to_bedgraph allocates and touches the output's pages behind the pile-up (engine.cpp: prealloc thread + touchers) and hands
+    # that mapping to the writers; small outputs normally skip it, so the threshold is lowered here.  The surplus of the
+    # estimate must be cut off and the bytes must be the oracle's.
+    monkeypatch.setenv("BND_PREALLOC_MIN", "0")
+    monkeypatch.setenv("BND_TOUCHERS", touchers)
+    monkeypatch.setenv("BND_PRETOUCH", "1" if touchers != "0" else "0")
+    bam = make_bam("pe", "--pairs", 20000, "--odd")
+    pile, filt = dict(bam_path=bam, bin_size=50, norm="rpkm"), dict(min_mapq=30, proper_pair=True)
+    ref, out = tmp_path / "ref.bdg", tmp_path / "out.bdg"
+    oracle.pileup_to_bedgraph(pile, filt, ref)
+    for _ in range(2):
+        with backend.pileup(pile, filt) as h:
+            h.to_bedgraph(out)
+        assert out.read_bytes() == ref.read_bytes()
