@@ -29,7 +29,7 @@ EXPORTS = [
     "bnd_pileup_destroy", "bnd_pileup_to_bedgraph", "bnd_pileup_to_bigwig", "bnd_pileup_chromosome", "bnd_pileup_runs",
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
-    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_pileup_format_bedgraph", "bnd_pileup_write_bedgraph_pieces", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
+    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_pileup_preallocate_output", "bnd_pileup_format_bedgraph", "bnd_pileup_write_bedgraph_pieces", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
     "bnd_multi_prepare_resident", "bnd_multi_change_bits", "bnd_multi_or_bits", "bnd_multi_compact_columns", "bnd_multi_format_tsv", "bnd_multi_write_tsv_pieces", "bnd_pileup_refs", "bnd_collapse_bedgraph",
     "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
 ]
@@ -149,6 +149,7 @@ class Native:
         L.bnd_pileup_bedgraph_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.bnd_pileup_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.bnd_pileup_shape.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.bnd_pileup_preallocate_output.argtypes = [C.c_void_p, C.c_char_p]
         L.bnd_pileup_format_bedgraph.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64]
         L.bnd_pileup_write_bedgraph_pieces.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
         L.bnd_signal_for_chromosome.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg), C.c_char_p,
@@ -417,6 +418,10 @@ class PileupHandle:
         sizes = (C.c_uint64 * max(len(names), 1))()
         self.n.check(self.n.L.bnd_pileup_format_bedgraph(self.h, sizes, len(names)))
         return [int(sizes[i]) for i in range(len(names))]
+
+    def preallocate_output(self, path):
+        """One rank of a sharded job, before its pile-up: the merged file's estimated pages are allocated in the background."""
+        self.n.check(self.n.L.bnd_pileup_preallocate_output(self.h, _b(path)))
 
     def write_bedgraph_pieces(self, path, tables: list, rank: int):
         """tables[k] = format_bedgraph() of rank k; fills this rank's pieces of the one output file."""

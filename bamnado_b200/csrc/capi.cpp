@@ -136,6 +136,9 @@ int bnd_pileup_shape(bnd_pileup *p, uint64_t shape[16]) {
     shape[4] = s.bins, shape[5] = s.launches, shape[6] = s.chunk_len, shape[7] = s.n_chunks, shape[8] = s.segments;
   });
 }
+int bnd_pileup_preallocate_output(bnd_pileup *p, const char *out_path) {
+  return guarded([&] { P(p)->preallocate_output(out_path); });
+}
 int bnd_pileup_format_bedgraph(bnd_pileup *p, uint64_t *bytes_per_ref, uint64_t n_refs) {
   return guarded([&] {
     std::vector<uint64_t> v;

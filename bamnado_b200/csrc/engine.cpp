@@ -462,11 +462,16 @@ struct Pileup::Impl {
   uint64_t fin_bins = 0;
   // device text between format_bedgraph and write_bedgraph_pieces
   std::unique_ptr<Pileup::TextJob> text_job;
+  // merged output of a sharded job: pages allocated in the background by the one rank that was asked to (preallocate_output)
+  std::thread prealloc_thread;
+  std::atomic<bool> prealloc_stop{false};
   // resident copy of the shard's compressed bytes
   DevBuf d_resident;
   std::vector<Segment> res_segs;
   std::vector<BlockTable> res_tabs;
   ~Impl() {
+    prealloc_stop.store(true);
+    if (prealloc_thread.joinable()) prealloc_thread.join();
     if (map) munmap(const_cast<uint8_t *>(map), map_len);
     if (fd >= 0) close(fd);
     for (DevBuf *b : {&d_ref_len, &d_first_bin, &d_first_chunk, &d_rg, &d_tagv, &d_bl_off, &d_bl_starts, &d_bl_stops, &d_bc_table,
@@ -501,7 +506,7 @@ void device_inflate(const uint8_t *bgzf, uint64_t n_bytes, std::vector<uint8_t> 
   if (nblk == 0) return;
   DevBuf comp, coff, uoff, infl, st, err, work;
   try {
-    comp.ensure(tab.coff.back() + 64);
+    comp.ensure(tab.coff.back() + COMP_PAD);
     CU(cudaMemcpy(comp.p, bgzf, tab.coff.back(), cudaMemcpyHostToDevice));
     upload(coff, tab.coff.data(), tab.coff.size());
     upload(uoff, tab.uoff.data(), tab.uoff.size());
@@ -918,11 +923,11 @@ void Pileup::run_pass(const Range &range, bool resident) {
         CU(cudaStreamWaitEvent(S.stream, S.ev_carry, 0));
         S.carry_pending = false;
       }
-      const bool grow = (!resident && clen + 64 > S.comp.cap) || (nblk + 1) * 8 > S.coff.cap || data_end + 64 > S.infl.cap ||
+      const bool grow = (!resident && clen + COMP_PAD > S.comp.cap) || (nblk + 1) * 8 > S.coff.cap || data_end + 64 > S.infl.cap ||
                         (size_t)n_tiles * 8 > S.t_entry.cap || (ulen / 36 + 2) * 8 > S.rec_off.cap;
       if (grow) {
         for (auto &q : ctx.sets) CU(cudaStreamSynchronize(q.stream));  // rare: nothing may still use the old buffers
-        if (!resident) S.comp.ensure(clen + 64);
+        if (!resident) S.comp.ensure(clen + COMP_PAD);
         S.coff.ensure((nblk + 1) * 8);
         S.uoff.ensure((nblk + 1) * 8);
         S.infl.ensure(data_end + 64);
@@ -1092,7 +1097,7 @@ void Pileup::stage() {
     r.byte_end = it == cps.end() ? file_size_ : *it;
   }
   const uint64_t total = r.byte_end - r.byte_begin;
-  im.d_resident.ensure(total + 64);
+  im.d_resident.ensure(total + COMP_PAD);
   if (total == 0) return;
   // one pass over the file through a pinned bounce buffer; segment tables are kept on the host
   const std::vector<uint64_t> &cp = im.cut_points;
@@ -2351,18 +2356,10 @@ void Pileup::to_bedgraph(const std::string &path) {
   };
   try {
     if (!accumulated_ && env_u64("BND_PREALLOC", 1)) {
-      const uint64_t rows_cap = std::min<uint64_t>(shard_bins_upper(), 2 * (geo_.n_mapped + geo_.n_unmapped) + geo_.total_chunks() + 16);
-      double bytes = 0, bins_total = 0;
-      for (size_t r = 0; r < hdr_.names.size(); r++) {
-        const double nb = (double)(geo_.ref_first_bin[r + 1] - geo_.ref_first_bin[r]);
-        bytes += nb * (double)(hdr_.names[r].size() + 46);
-        bins_total += nb;
-      }
-      const double per_row = bins_total > 0 ? bytes / bins_total : 64.0;
       // 72 % of the upper bound (rows rarely reach it and are shorter than the longest possible: 2.1 GB of 2.9 GB at the
       // BASELINE size), and never more than the pile-up can hide: it moves ~30 GB/s of
       // BAM, fallocate ~14 GB/s of pages.  The thread allocates in 64 MiB steps and stops when the pile-up is done.
-      uint64_t want = (uint64_t)((double)rows_cap * per_row * 0.72);
+      uint64_t want = estimate_text_bytes(false);
       want = std::min<uint64_t>(want, (shard_.byte_end - shard_.byte_begin) * 6 / 10);
       want &= ~(uint64_t)4095;
       if (want > env_u64("BND_PREALLOC_MIN", 8ull << 20)) {
@@ -2768,6 +2765,42 @@ void Pileup::to_bigwig(const std::string &path) {
 // Sharded jobs write ONE bedGraph (write_bedgraph, coverage_analysis.rs:43-75): every rank formats its rows on the device and
 // reports the bytes it holds per reference; the caller gathers those tables from all ranks (n_ref x u64 each, the only
 // exchange besides the 13 filter counters) and every rank then fills its own pieces of the same file.
+// Upper estimate of the bedGraph text of the chunks [lo, hi): rows <= min(bins, 2 reads + chunks), <= name + 46 bytes each,
+// scaled by what real outputs reach (2.1 of 2.9 GB at the BASELINE size).
+uint64_t Pileup::estimate_text_bytes(bool whole_job) const {
+  const uint64_t bins = whole_job ? geo_.first_bin_of_chunk(geo_.total_chunks()) : shard_bins_upper();
+  const uint64_t rows_cap = std::min<uint64_t>(bins, 2 * (geo_.n_mapped + geo_.n_unmapped) + geo_.total_chunks() + 16);
+  double bytes = 0, bins_total = 0;
+  for (size_t r = 0; r < hdr_.names.size(); r++) {
+    const double nb = (double)(geo_.ref_first_bin[r + 1] - geo_.ref_first_bin[r]);
+    bytes += nb * (double)(hdr_.names[r].size() + 46);
+    bins_total += nb;
+  }
+  const double per_row = bins_total > 0 ? bytes / bins_total : 64.0;
+  return (uint64_t)((double)rows_cap * per_row * 0.72) & ~(uint64_t)4095;
+}
+
+// Sharded jobs: ONE rank calls this before its pile-up.  The merged file is created and its estimated pages are allocated by a
+// background thread while the pile-ups run; without it every rank allocates its own pieces when it writes them, and those
+// posix_fallocate calls queue up on the file's inode lock (2.1 GB at 14 GB/s: 150 ms that no rank can hide).
+void Pileup::preallocate_output(const std::string &path) {
+  Impl &im = *im_;
+  if (im.prealloc_thread.joinable()) {
+    im.prealloc_stop.store(true);
+    im.prealloc_thread.join();
+  }
+  im.prealloc_stop.store(false);
+  const uint64_t want = estimate_text_bytes(true);
+  const int fd = ::open(path.c_str(), O_RDWR | O_CREAT, 0644);
+  if (fd < 0) fail("cannot create " + path);
+  im.prealloc_thread = std::thread([fd, want, stop = &im.prealloc_stop] {
+    const uint64_t step = 64ull << 20;
+    for (uint64_t off = 0; off < want && !stop->load(std::memory_order_relaxed); off += step)
+      if (posix_fallocate(fd, (off_t)off, (off_t)std::min(step, want - off)) != 0) break;
+    close(fd);
+  });
+}
+
 void Pileup::format_bedgraph(std::vector<uint64_t> &bytes_per_ref) {
   ensure_finalized();
   Impl &im = *im_;
@@ -2794,6 +2827,10 @@ void Pileup::write_bedgraph_pieces(const std::string &path, const uint64_t *byte
   const uint64_t total = place_pieces(*job, bytes_all, world, rank);
   // every rank opens (or creates) the same file and sets the same size; pieces never overlap, so no rank has to wait for
   // another one before it fills its own
+  if (im.prealloc_thread.joinable()) {  // this rank allocated the file's pages behind its pile-up: stop where it is
+    im.prealloc_stop.store(true);
+    im.prealloc_thread.join();
+  }
   int fd = ::open(path.c_str(), O_RDWR | O_CREAT, 0644);
   if (fd < 0) fail("cannot create " + path);
   struct stat st;

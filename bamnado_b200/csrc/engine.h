@@ -51,6 +51,7 @@ class Pileup {
   void bedgraph_text(std::string &out);
   // sharded jobs, one output file: text on the device + bytes per reference, then this shard's pieces at the offsets that
   // follow from every rank's table (bytes_all[rank][ref])
+  void preallocate_output(const std::string &path);  // one rank, before its pile-up: pages of the merged file allocated meanwhile
   void format_bedgraph(std::vector<uint64_t> &bytes_per_ref);
   void write_bedgraph_pieces(const std::string &path, const uint64_t *bytes_all, int world, int rank);
   const Timings &timings() const { return tm_; }
@@ -111,6 +112,7 @@ class Pileup {
   uint64_t finalize_range(bool dense_counts, bool emit_runs = true);
   void fetch_rows(std::vector<RunRow> &out);
   void ensure_finalized();
+  uint64_t estimate_text_bytes(bool whole_job) const;
   uint64_t shard_bins_upper() const { return geo_.first_bin_of_chunk(shard_.chunk_hi) - geo_.first_bin_of_chunk(shard_.chunk_lo); }
 
   bnd_pileup_cfg cfg_;

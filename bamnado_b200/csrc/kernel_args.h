@@ -31,8 +31,12 @@ struct CrcTables {
   uint32_t z[4][256];     // "advance by 32*G zero bits" operator, sliced by byte
 };
 
+// K1 stages its input with bulk copies of one round (1.3 KB) that may start up to a round before the end of the last block:
+// every buffer of compressed bytes is allocated with this many readable bytes behind the data
+constexpr size_t COMP_PAD = 2048;
+
 struct InflateArgs {
-  const uint8_t *comp;        // compressed bytes of the segment (padded by >= 16 readable bytes)
+  const uint8_t *comp;        // compressed bytes of the segment (padded by COMP_PAD readable bytes)
   const uint64_t *blk_coff;   // [n+1] offset of each BGZF block (gzip header) within comp
   const uint64_t *blk_uoff;   // [n+1] offset of each block's output within out
   uint8_t *out;               // inflated bytes

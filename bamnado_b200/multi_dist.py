@@ -146,7 +146,7 @@ def _wrap_u32(ptr: int, n: int, device: torch.device) -> torch.Tensor:
         return torch.zeros(0, dtype=torch.int32, device=device)
     if device.type == "cuda":
         class _Arr:  # __cuda_array_interface__: zero-copy view of library-owned device memory
-            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, True), "version": 3}
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
 
         return torch.as_tensor(_Arr(), device=device)
     import ctypes

@@ -511,28 +511,50 @@ def main():
             h.set_total_stats([int(x) for x in t.tolist()])
 
     # ---- e2e leg: host file -> ONE output file through the C ABI ----
+    trace = bool(os.environ.get("BND_BENCH_TRACE"))
+
     def e2e_step():
         out_path = outdir() / f"out_cfg{W.config}_{len(out_paths)}.{ext}"  # a fresh output file per job, shared by all ranks
         out_paths.append(out_path)
+        stamps = [("start", time.perf_counter())]
+        mark = lambda name: stamps.append((name, time.perf_counter()))  # noqa: E731
         with N.pileup(pile, W.filt) as h:
+            mark("create")
             if world > 1:  # sharded: the ranks meet once to sum the 13 filter counters before normalising, once to place their pieces
+                if W.out_kind == "bedgraph" and rank == 0:
+                    h.preallocate_output(out_path)  # one rank allocates the merged file's pages behind its pile-up
                 h.accumulate()
+                mark("accumulate")
                 allreduce_stats(h)
+                mark("allreduce")
                 h.finalize()
+                mark("finalize")
                 if W.out_kind == "bedgraph":
                     sizes = h.format_bedgraph()  # text on the device; bytes per reference of this shard
+                    mark("format")
                     t = torch.tensor(sizes, dtype=torch.int64, device="cuda")
                     allv = [torch.empty_like(t) for _ in range(world)]
                     dist.all_gather(allv, t)  # n_ref x u64 per rank: where every rank's pieces go in the one sorted file
-                    h.write_bedgraph_pieces(out_path, [[int(x) for x in v.tolist()] for v in allv], rank)
+                    tables = [[int(x) for x in v.tolist()] for v in allv]
+                    mark("all_gather")
+                    h.write_bedgraph_pieces(out_path, tables, rank)
+                    mark("write_pieces")
                     dist.barrier()
+                    mark("barrier")
                 else:
                     h.to_bigwig(str(out_path) + f".rank{rank}")  # BigWig sections of a shard: one file per rank
+                    mark("to_bigwig")
             elif W.out_kind == "bedgraph":
                 h.to_bedgraph(out_path)  # single GPU: one call = BamPileup::to_bedgraph (pile-up, normalise, write)
+                mark("to_bedgraph")
             else:
                 h.to_bigwig(out_path)
-            return h.shape(), h.timings(), h.norm_factor()
+                mark("to_bigwig")
+            res = h.shape(), h.timings(), h.norm_factor()
+        mark("close")
+        if trace:
+            sys.stderr.write(f"[trace rank {rank}] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.1f}" for a, b in zip(stamps, stamps[1:])) + " ms\n")
+        return res
 
     def clean_outputs(keep_last=False):
         for p in out_paths[:-1] if keep_last else out_paths:

@@ -132,7 +132,11 @@ int bnd_pileup_shape(bnd_pileup *p, uint64_t shape[16]);
  * 2. the caller gathers those tables from all ranks (all-gather of n_refs x u64 - the only exchange besides the counters);
  * 3. every rank fills its own pieces of the same file: references in byte-string order, inside a reference the shards in rank
  *    order.  bytes_all is [world][n_refs], row `rank` must be what step 1 returned.  No rank waits for another one; the file is
- *    complete once every rank has returned (the caller's barrier). */
+ *    complete once every rank has returned (the caller's barrier).
+ * 0. optional, ONE rank, before its pile-up: bnd_pileup_preallocate_output creates the file and allocates its estimated pages in
+ *    the background while the pile-ups run (otherwise every rank allocates its own pieces when it writes them, and those
+ *    allocations queue up on the file's lock). */
+int bnd_pileup_preallocate_output(bnd_pileup *p, const char *out_path);
 int bnd_pileup_format_bedgraph(bnd_pileup *p, uint64_t *bytes_per_ref, uint64_t n_refs);
 int bnd_pileup_write_bedgraph_pieces(bnd_pileup *p, const char *out_path, const uint64_t *bytes_all, int32_t world, int32_t rank);
 

@@ -24,6 +24,8 @@ WORKER = textwrap.dedent("""
     pile = dict(bam_path={bam!r}, bin_size=50, norm="rpkm", shard_rank=rank, shard_world=world)
     filt = dict(min_mapq=30, proper_pair=True)
     with N.pileup(pile, filt) as h:
+        if rank == 0:
+            h.preallocate_output({out!r} + ".merged.bdg")  # one rank allocates the merged file's pages behind its pile-up
         h.accumulate()
         t = torch.tensor(list(h.stats().values()), dtype=torch.int64)
         dist.all_reduce(t)
