@@ -32,8 +32,7 @@ template <int LB, int DB, int NT, int SPAN_BITS>
 struct alignas(16) SpecSmemT {
   static constexpr int LIT_BITS = LB, DIST_BITS = DB, MAX_MATCHES = NT, SPAN = SPAN_BITS;
   static constexpr int LIT_SUB = 344;              // second-level entries: zlib's bound for 286 symbols is 308 (root 10) / 340 (root 9), + 2 reserved
-  static constexpr int STAGE_WORDS = SPAN_BITS + 8 + 4;  // one round of input: 32 spans + the longest token + the reader's look-ahead + the 16-byte alignment of the bulk copy
-  static_assert(STAGE_WORDS % 4 == 0, "the bulk copy moves multiples of 16 bytes");
+  static constexpr int STAGE_WORDS = SPAN_BITS + 8;  // one round of input: 32 spans + the longest token + the reader's look-ahead
   // literal/length code: root table of 2^LB entries, then the second-level tables of the codes longer than LB bits.
   // entry: bits 0-4 = bits to consume (code + extra bits), symbol from bit 7; bits 0-4 == 0: second-level pointer with
   // bits 5-7 = index width, bits 8-15 = (offset / 2) into the second level (0 = the reserved all-zero entry = no code)
@@ -41,15 +40,12 @@ struct alignas(16) SpecSmemT {
   uint16_t dist_lut[1 << DB];
   HuffCanon dist_canon;
   uint16_t dist_sorted[32];
-  alignas(16) uint32_t stage[STAGE_WORDS];  // this round's compressed words (filled by one cp.async.bulk per round)
-  alignas(8) uint64_t mbar;                 // completion barrier of that copy
-  uint32_t phase;                           // its parity: one completed copy per round (kept here, not in a register)
+  uint32_t stage[STAGE_WORDS];  // this round's compressed words
   // the round's matches in stream order: {output position | (length - 3) << 16, distance}
   uint2 matches[NT];
   __device__ __forceinline__ uint16_t *codes() { return reinterpret_cast<uint16_t *>(matches); }     // 320 x u16
   __device__ __forceinline__ uint8_t *lens() { return reinterpret_cast<uint8_t *>(matches) + 640; }  // 320 x u8
   static_assert(NT * 8 >= 960, "match list must hold the table-building scratch");
-  // the kernel addresses mbar and phase relative to stage: stage + 4 * STAGE_WORDS and + 8
 };
 
 enum : uint32_t { SPAN_OK = 0, SPAN_EOB = 1, SPAN_BAD_SYMBOL = 2, SPAN_BAD_DISTANCE = 3, SPAN_PAST_END = 4 };
@@ -295,16 +291,25 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
   if (isize != isize_expected) return INF_SIZE_MISMATCH;
   if (isize > 65536u) return INF_BAD_HEADER;  // BGZF blocks hold at most 64 KiB (SAM spec 4.1); match positions are 16-bit here
 
-  // the payload as a bit-addressed array of words that starts on a 16-byte line (the unit of the bulk copies below)
-  const uint32_t *base = (const uint32_t *)((uintptr_t)payload & ~(uintptr_t)15);
-  uint32_t p0 = (uint32_t)((uintptr_t)payload & 15) * 8;
+  // the payload as a bit-addressed array of aligned words
+  const uint32_t *base = (const uint32_t *)((uintptr_t)payload & ~(uintptr_t)3);
+  uint32_t p0 = (uint32_t)((uintptr_t)payload & 3) * 8;
   const uint32_t end_bit = p0 + (uint32_t)(pend - payload) * 8;
   const saddr_t ml0 = smem_addr(S.matches), stage0 = smem_addr(S.stage);
-  // One round of input, starting at the 16-byte line holding bit p: ONE bulk copy issued by lane 0 (the TMA engine moves the
-  // 1.3 KB; it replaces eleven 4-byte cp.async per lane and round).  The copy may read up to a stage past the block's end:
-  // every compressed buffer is padded by COMP_PAD readable bytes, and bits past `end_bit` never reach the output.
+  const uint32_t word_limit = ((end_bit + 31u) >> 5) + 2u;  // words holding payload bits, + 2 inside the block's 8-byte trailer
+  // asynchronous copy of one round of input, starting at the word holding bit p: global -> shared, zeros past the payload.
+  // (One cp.async.bulk per round with an mbarrier - UBLKCP / SYNCS.PHASECHK in the SASS - was built and measured in round 2:
+  // bit-exact, but the pass went 115.5 -> 123.1 ms at 40 M pairs: the engine's operands live in uniform registers and the round
+  // loop, which is at the 56-register cap, picked up 43 spill instructions inside the match resolution.  Eleven 4-byte LDGSTS per
+  // lane are 0.2 % of a round's instructions, so there was nothing to win on the other side; profiles/r2_sweeps.md.)
   auto stage_issue = [&](uint32_t p) {
-    if (lane == 0) bulk_copy_g2s(stage0, (const void *)(base + ((p >> 7) << 2)), (uint32_t)STAGE_WORDS * 4u, stage0 + (saddr_t)(STAGE_WORDS * 4));
+    const uint32_t w0 = p >> 5;
+    for (uint32_t k = (uint32_t)lane; k < (uint32_t)STAGE_WORDS; k += 32) {
+      if (w0 + k < word_limit)
+        cp_async_u32(stage0 + 4 * k, base + w0 + k);
+      else
+        sts_u32(stage0 + 4 * k, 0u);
+    }
   };
   uint32_t outpos = 0;
   int status = INF_OK;
@@ -379,17 +384,10 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
         status = INF_INPUT_OVERRUN;
         break;
       }
-      if (!staged) {
-        tile.sync();  // nobody still reads the staged words of an earlier DEFLATE block
-        stage_issue(p0);
-      }
-      {
-        const uint32_t ph = lds_u32(stage0 + (saddr_t)(STAGE_WORDS * 4 + 8));
-        mbar_wait(stage0 + (saddr_t)(STAGE_WORDS * 4), ph);  // the copy engine has delivered the round's bytes
-        tile.sync();
-        if (lane == 0) sts_u32(stage0 + (saddr_t)(STAGE_WORDS * 4 + 8), ph ^ 1u);
-      }
-      const uint32_t sbit0 = p0 & ~127u;  // bit address of the first staged bit: the 16-byte line holding bit p0
+      if (!staged) stage_issue(p0);
+      cp_async_wait_all();
+      tile.sync();
+      const uint32_t sbit0 = p0 & ~31u;  // bit address of the first staged word
       // ---- pass 1: every lane decodes its span from the span's first bit ----
       uint32_t start = p0 + (uint32_t)lane * SPAN;
       const uint32_t limit = tmin(p0 + (uint32_t)(lane + 1) * SPAN, end_bit);
@@ -602,10 +600,6 @@ __global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs 
     const uint32_t *src = reinterpret_cast<const uint32_t *>(a.crc);
     uint32_t *dst = reinterpret_cast<uint32_t *>(crc_s);
     for (int i = threadIdx.x; i < (int)(sizeof(CrcTables) / 4); i += THREADS) dst[i] = src[i];
-  }
-  if ((threadIdx.x & 31u) == 0) {
-    warps[threadIdx.x / 32].phase = 0;
-    mbar_init(smem_addr(&warps[threadIdx.x / 32].mbar), 1);
   }
   __syncthreads();
   const CrcTables *crcT = CRC_SMEM ? crc_s : a.crc;
