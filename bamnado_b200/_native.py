@@ -29,7 +29,7 @@ EXPORTS = [
     "bnd_pileup_destroy", "bnd_pileup_to_bedgraph", "bnd_pileup_to_bigwig", "bnd_pileup_chromosome", "bnd_pileup_runs",
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
-    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_pileup_preallocate_output", "bnd_pileup_format_bedgraph", "bnd_pileup_write_bedgraph_pieces", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
+    "bnd_pileup_timings", "bnd_pileup_shape", "bnd_pileup_preallocate_output", "bnd_pileup_preallocated_bytes", "bnd_pileup_format_bedgraph", "bnd_pileup_write_bedgraph_pieces", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
     "bnd_multi_prepare_resident", "bnd_multi_change_bits", "bnd_multi_or_bits", "bnd_multi_compact_columns", "bnd_multi_format_tsv", "bnd_multi_write_tsv_pieces", "bnd_pileup_refs", "bnd_collapse_bedgraph",
     "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
 ]
@@ -151,7 +151,8 @@ class Native:
         L.bnd_pileup_shape.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.bnd_pileup_preallocate_output.argtypes = [C.c_void_p, C.c_char_p]
         L.bnd_pileup_format_bedgraph.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64]
-        L.bnd_pileup_write_bedgraph_pieces.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
+        L.bnd_pileup_preallocated_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.bnd_pileup_write_bedgraph_pieces.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_uint64]
         L.bnd_signal_for_chromosome.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg), C.c_char_p,
                                                 C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_uint64)]
         L.bnd_multi_to_tsv.argtypes = [C.POINTER(PileupCfg), C.POINTER(FilterCfg), C.c_int32, C.c_char_p]
@@ -423,11 +424,18 @@ class PileupHandle:
         """One rank of a sharded job, before its pile-up: the merged file's estimated pages are allocated in the background."""
         self.n.check(self.n.L.bnd_pileup_preallocate_output(self.h, _b(path)))
 
-    def write_bedgraph_pieces(self, path, tables: list, rank: int):
-        """tables[k] = format_bedgraph() of rank k; fills this rank's pieces of the one output file."""
+    def preallocated_bytes(self) -> int:
+        """Stops this rank's background allocation of the merged output (if any) -> leading bytes of the file that have pages."""
+        n = C.c_uint64()
+        self.n.check(self.n.L.bnd_pileup_preallocated_bytes(self.h, C.byref(n)))
+        return n.value
+
+    def write_bedgraph_pieces(self, path, tables: list, rank: int, preallocated: int = 0):
+        """tables[k] = format_bedgraph() of rank k; fills this rank's pieces of the one output file.  `preallocated`: leading
+        bytes of the file that already have pages (max over ranks of preallocated_bytes())."""
         world, n_ref = len(tables), len(tables[0])
         flat = (C.c_uint64 * max(world * n_ref, 1))(*[v for t in tables for v in t])
-        self.n.check(self.n.L.bnd_pileup_write_bedgraph_pieces(self.h, _b(path), flat, world, rank))
+        self.n.check(self.n.L.bnd_pileup_write_bedgraph_pieces(self.h, _b(path), flat, world, rank, preallocated))
 
 
 _native = None

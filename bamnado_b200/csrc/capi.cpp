@@ -147,8 +147,11 @@ int bnd_pileup_format_bedgraph(bnd_pileup *p, uint64_t *bytes_per_ref, uint64_t 
     for (size_t i = 0; i < v.size(); i++) bytes_per_ref[i] = v[i];
   });
 }
-int bnd_pileup_write_bedgraph_pieces(bnd_pileup *p, const char *out_path, const uint64_t *bytes_all, int32_t world, int32_t rank) {
-  return guarded([&] { P(p)->write_bedgraph_pieces(out_path, bytes_all, world, rank); });
+int bnd_pileup_preallocated_bytes(bnd_pileup *p, uint64_t *n_bytes) {
+  return guarded([&] { *n_bytes = P(p)->preallocated_bytes(); });
+}
+int bnd_pileup_write_bedgraph_pieces(bnd_pileup *p, const char *out_path, const uint64_t *bytes_all, int32_t world, int32_t rank, uint64_t preallocated) {
+  return guarded([&] { P(p)->write_bedgraph_pieces(out_path, bytes_all, world, rank, preallocated); });
 }
 
 int bnd_signal_for_chromosome(const bnd_pileup_cfg *cfg, const bnd_filter_cfg *filter, const char *chrom, float **signal,

@@ -4,6 +4,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -465,6 +466,7 @@ struct Pileup::Impl {
   // merged output of a sharded job: pages allocated in the background by the one rank that was asked to (preallocate_output)
   std::thread prealloc_thread;
   std::atomic<bool> prealloc_stop{false};
+  std::atomic<uint64_t> prealloc_done{0};
   // resident copy of the shard's compressed bytes
   DevBuf d_resident;
   std::vector<Segment> res_segs;
@@ -1707,7 +1709,7 @@ void Pileup::multi_write_tsv_pieces(const std::string &path, const char *header,
       done += (uint64_t)w;
     }
   }
-  write_pieces(*job, fd, path, total, 0, false);
+  write_pieces(*job, fd, path, total, 0, false, nullptr, 0, world > 1);
 }
 
 // ---- collapse-bedgraph ------------------------------------------------------------------------------------------------------
@@ -2271,19 +2273,31 @@ void Pileup::bedgraph_text(std::string &out) {
 // closes it.  Regular files: the writer threads memcpy into a shared mapping (parallel page-cache fills; pwrite would
 // serialise on the inode lock); anything unmappable falls back to positional writes.
 void Pileup::write_pieces(TextJob &job, int fd, const std::string &path, uint64_t total, uint64_t prealloc, bool truncate_at_end, char *premap,
-                          uint64_t premap_len) {
+                          uint64_t premap_len, bool sparse_ok) {
   DeviceCtx &ctx = *im_->ctx;
   char *map = nullptr;
   uint64_t map_len = total;
   const double t_w0 = now_ms();
+  double t_backed = t_w0, t_mapped = t_w0;
   try {
     // every byte the writers will touch must be backed before it is mapped: a store into a hole of a sparse file raises
     // SIGBUS when the file system is full, which would take the host process down instead of returning an error
     bool backed = !job.pieces.empty();
+    // Sharded jobs: every rank allocating its own pieces queues on the file's inode lock (tmpfs: 10-14 GB/s for all ranks
+    // together, ~1 us per page even where pages exist), while pages allocated by the writers' own page faults scale with the
+    // ranks (27 GB/s over eight ranks).  When the file system has room for twice the file, the holes are left to the faults;
+    // a file system that is nearly full takes the slow, checked path.
+    bool roomy = false;
+    if (sparse_ok) {
+      struct statvfs vfs;
+      if (fstatvfs(fd, &vfs) == 0) roomy = (double)vfs.f_bavail * (double)vfs.f_frsize >= 2.0 * (double)total;
+    }
     for (const TextPiece &pc : job.pieces) {
+      if (roomy) break;
       const uint64_t a0 = pc.out_off, a1 = pc.out_off + (pc.dev_end - pc.dev_begin);
       if (a1 > prealloc && posix_fallocate(fd, (off_t)std::max(a0, prealloc), (off_t)(a1 - std::max(a0, prealloc))) != 0) backed = false;
     }
+    t_backed = now_ms();
     if (backed && total && premap && total <= premap_len) {
       map = premap;  // the mapping whose pages were touched while the pile-up ran
       map_len = premap_len;
@@ -2300,6 +2314,7 @@ void Pileup::write_pieces(TextJob &job, int fd, const std::string &path, uint64_
     // 16-core B200 hosts takes the drain of 2.1 GB from 155 to 125 ms (profiles/r1_sweeps.md)
     const unsigned hw = host_cores_share();
     const int writers = (int)env_u64("BND_WRITERS", std::min(32u, std::max(4u, hw + hw / 2)));
+    t_mapped = now_ms();
     const bool nt = env_u64("BND_WRITE_NT", 1) != 0;  // the text is not read again by this process: keep it out of the caches
     if (map)
       drain_text(ctx, job.d_text.as<uint8_t>(), job.nbytes, job.pieces, writers, [map, nt](const uint8_t *src, uint64_t len, uint64_t off) {
@@ -2330,7 +2345,8 @@ void Pileup::write_pieces(TextJob &job, int fd, const std::string &path, uint64_
     fail("write error on " + path);
   }
   if (close(fd) != 0) fail("write error on " + path);
-  if (env_u64("BND_DEBUG_TIMING", 0)) fprintf(stderr, "[bnd] write_pieces: drain %.2f ms, truncate + close %.2f ms\n", t_drained - t_w0, now_ms() - t_drained);
+  if (env_u64("BND_DEBUG_TIMING", 0)) fprintf(stderr, "[bnd] write_pieces: %zu pieces, backing %.2f ms, map %.2f ms, drain %.2f ms, truncate + close %.2f ms\n", job.pieces.size(), t_backed - t_w0,
+                                             t_mapped - t_backed, t_drained - t_mapped, now_ms() - t_drained);
 }
 
 void Pileup::to_bedgraph(const std::string &path) {
@@ -2793,12 +2809,26 @@ void Pileup::preallocate_output(const std::string &path) {
   const uint64_t want = estimate_text_bytes(true);
   const int fd = ::open(path.c_str(), O_RDWR | O_CREAT, 0644);
   if (fd < 0) fail("cannot create " + path);
-  im.prealloc_thread = std::thread([fd, want, stop = &im.prealloc_stop] {
+  im.prealloc_done.store(0);
+  im.prealloc_thread = std::thread([fd, want, stop = &im.prealloc_stop, done = &im.prealloc_done] {
     const uint64_t step = 64ull << 20;
-    for (uint64_t off = 0; off < want && !stop->load(std::memory_order_relaxed); off += step)
+    for (uint64_t off = 0; off < want && !stop->load(std::memory_order_relaxed); off += step) {
       if (posix_fallocate(fd, (off_t)off, (off_t)std::min(step, want - off)) != 0) break;
+      done->store(std::min(want, off + step));
+    }
     close(fd);
   });
+}
+
+// Bytes of the merged output this rank has allocated so far; stops the background allocation (called after the pile-up, before
+// the ranks exchange their tables, so that every rank learns how much of the file needs no allocation when it writes).
+uint64_t Pileup::preallocated_bytes() {
+  Impl &im = *im_;
+  if (im.prealloc_thread.joinable()) {
+    im.prealloc_stop.store(true);
+    im.prealloc_thread.join();
+  }
+  return im.prealloc_done.load();
 }
 
 void Pileup::format_bedgraph(std::vector<uint64_t> &bytes_per_ref) {
@@ -2816,7 +2846,7 @@ void Pileup::format_bedgraph(std::vector<uint64_t> &bytes_per_ref) {
   for (size_t r = 0; r < bytes_per_ref.size(); r++) bytes_per_ref[r] = im.text_job->span[r].second - im.text_job->span[r].first;
 }
 
-void Pileup::write_bedgraph_pieces(const std::string &path, const uint64_t *bytes_all, int world, int rank) {
+void Pileup::write_bedgraph_pieces(const std::string &path, const uint64_t *bytes_all, int world, int rank, uint64_t preallocated) {
   Impl &im = *im_;
   if (!im.text_job) fail("write_bedgraph_pieces called before format_bedgraph", ERR_INVALID);
   if (world < 1 || rank < 0 || rank >= world || !bytes_all) fail("bad shard table", ERR_INVALID);
@@ -2827,10 +2857,7 @@ void Pileup::write_bedgraph_pieces(const std::string &path, const uint64_t *byte
   const uint64_t total = place_pieces(*job, bytes_all, world, rank);
   // every rank opens (or creates) the same file and sets the same size; pieces never overlap, so no rank has to wait for
   // another one before it fills its own
-  if (im.prealloc_thread.joinable()) {  // this rank allocated the file's pages behind its pile-up: stop where it is
-    im.prealloc_stop.store(true);
-    im.prealloc_thread.join();
-  }
+  preallocated_bytes();  // a rank that still allocates in the background stops here (callers normally did that before the exchange)
   int fd = ::open(path.c_str(), O_RDWR | O_CREAT, 0644);
   if (fd < 0) fail("cannot create " + path);
   struct stat st;
@@ -2838,8 +2865,12 @@ void Pileup::write_bedgraph_pieces(const std::string &path, const uint64_t *byte
     close(fd);
     fail("cannot size " + path);
   }
-  write_pieces(*job, fd, path, total, 0, false);
+  const double t_open = now_ms();
+  // [0, preallocated) already has pages (allocated behind the pile-ups by the rank that was asked to): only what lies beyond is
+  // allocated here, piece by piece - on tmpfs such calls cost ~1 us per page even for existing pages and queue on the inode lock
+  write_pieces(*job, fd, path, total, std::min(preallocated, total), false, nullptr, 0, true);
   tm_.text_ms = now_ms() - t0;
+  if (env_u64("BND_DEBUG_TIMING", 0)) fprintf(stderr, "[bnd] write_bedgraph_pieces: reap + place + open + size %.2f ms, pieces %.2f ms\n", t_open - t0, now_ms() - t_open);
 }
 
 }  // namespace bnd

@@ -53,7 +53,8 @@ class Pileup {
   // follow from every rank's table (bytes_all[rank][ref])
   void preallocate_output(const std::string &path);  // one rank, before its pile-up: pages of the merged file allocated meanwhile
   void format_bedgraph(std::vector<uint64_t> &bytes_per_ref);
-  void write_bedgraph_pieces(const std::string &path, const uint64_t *bytes_all, int world, int rank);
+  uint64_t preallocated_bytes();                      // stops that allocation; bytes of the file that have pages
+  void write_bedgraph_pieces(const std::string &path, const uint64_t *bytes_all, int world, int rank, uint64_t preallocated = 0);
   const Timings &timings() const { return tm_; }
   const Shape &shape() const { return shape_; }
 
@@ -103,7 +104,7 @@ class Pileup {
   void format_text(TextJob &job);
   uint64_t place_pieces(TextJob &job, const uint64_t *bytes_all, int world, int rank, uint64_t base = 0) const;
   void write_pieces(TextJob &job, int fd, const std::string &path, uint64_t total, uint64_t prealloc, bool truncate_at_end, char *premap = nullptr,
-                    uint64_t premap_len = 0);
+                    uint64_t premap_len = 0, bool sparse_ok = false);
 
   void open();
   Range range_for_chunks(uint64_t chunk_lo, uint64_t chunk_hi) const;

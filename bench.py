@@ -532,12 +532,12 @@ def main():
                 if W.out_kind == "bedgraph":
                     sizes = h.format_bedgraph()  # text on the device; bytes per reference of this shard
                     mark("format")
-                    t = torch.tensor(sizes, dtype=torch.int64, device="cuda")
+                    t = torch.tensor(sizes + [h.preallocated_bytes()], dtype=torch.int64, device="cuda")
                     allv = [torch.empty_like(t) for _ in range(world)]
-                    dist.all_gather(allv, t)  # n_ref x u64 per rank: where every rank's pieces go in the one sorted file
+                    dist.all_gather(allv, t)  # n_ref x u64 per rank: where every rank's pieces go in the one sorted file (+ the bytes already allocated)
                     tables = [[int(x) for x in v.tolist()] for v in allv]
                     mark("all_gather")
-                    h.write_bedgraph_pieces(out_path, tables, rank)
+                    h.write_bedgraph_pieces(out_path, [tb[:-1] for tb in tables], rank, max(tb[-1] for tb in tables))
                     mark("write_pieces")
                     dist.barrier()
                     mark("barrier")

@@ -38,10 +38,11 @@ WORKER = textwrap.dedent("""
         text = h.bedgraph_text()
         open({out!r} + f".text{{rank}}", "wb").write(text)
         # ONE sorted bedGraph written by all ranks: all-gather of the per-reference byte counts, then every rank fills its pieces
-        sizes = torch.tensor(h.format_bedgraph(), dtype=torch.int64)
+        sizes = torch.tensor(h.format_bedgraph() + [h.preallocated_bytes()], dtype=torch.int64)
         tables = [torch.empty_like(sizes) for _ in range(world)]
         dist.all_gather(tables, sizes)
-        h.write_bedgraph_pieces({out!r} + ".merged.bdg", [t.tolist() for t in tables], rank)
+        tables = [t.tolist() for t in tables]
+        h.write_bedgraph_pieces({out!r} + ".merged.bdg", [t[:-1] for t in tables], rank, max(t[-1] for t in tables))
         dist.barrier()
     dist.destroy_process_group()
 """)
