@@ -2463,43 +2463,19 @@ struct BwLevel {  // compressed sections of the data level or of one zoom level,
   std::vector<bwl::Section> secs;  // chrom, start, end, offset (inside the blob), size
   ~BwLevel() { blob.release(); }
 };
-}  // namespace
-
-void Pileup::to_bigwig(const std::string &path) {
-  ensure_finalized();
-  g_unmapper.reap();
-  Impl &im = *im_;
-  DeviceCtx &ctx = *im.ctx;
-  const double t0 = now_ms();
-  const double factor = norm_factor();
-  std::lock_guard<std::mutex> lock(ctx.mu);
-  CU(cudaSetDevice(ctx.device));
-  cudaStream_t st = ctx.sets[0].stream;
-  const size_t n_ref = hdr_.names.size();
-  const bool compress = env_u64("BND_BIGWIG_COMPRESS", 1) != 0;
-
-  // chromosome ids are dense (0 .. kept - 1, header order): readers such as libBigWig index arrays of `itemCount`
-  // entries by id, so the BAM reference index cannot be used once references are dropped
-  std::vector<uint8_t> skip(n_ref, 0);
-  std::vector<uint32_t> dense(n_ref, 0);
-  std::vector<std::tuple<std::string, uint32_t, uint32_t>> chroms;
-  std::vector<int> ref_of_dense;
-  for (size_t r = 0; r < n_ref; r++) {
-    skip[r] = cfg_.ignore_scaffold && is_scaffold(hdr_.names[r]);
-    if (hdr_.lens[r] > 0xffffffffull) fail("chromosome too long for BigWig");
-    if (!skip[r]) {
-      dense[r] = (uint32_t)chroms.size();
-      chroms.emplace_back(hdr_.names[r], dense[r], (uint32_t)hdr_.lens[r]);
-      ref_of_dense.push_back((int)r);
-    }
-  }
+// Everything behind the items: 1 024-item sections, one zlib stream per section, summary statistics, zoom levels, file layout
+// and the drain of the section blobs into the file.  Shared by BamPileup::to_bigwig and the BigWig-to-BigWig tools
+// (bigwig_compare.cpp).  `chroms`: (name, dense id, length) in id order; chrom_item_first[c] = first item of chromosome c.
+void encode_bigwig_file(DeviceCtx &ctx, cudaStream_t st, const std::string &path, const std::vector<std::tuple<std::string, uint32_t, uint32_t>> &chroms,
+                        const std::vector<uint64_t> &chrom_item_first, DevBuf &d_items, double t0) {
   const uint32_t n_chrom = (uint32_t)chroms.size();
-
-  DevBuf d_row_first, d_item_first, d_skip, d_items, d_flag, d_secs, d_staging, d_sizes, d_bounds, d_stats, d_offsets;
+  const uint64_t n_items = chrom_item_first[n_chrom];
+  const bool compress = env_u64("BND_BIGWIG_COMPRESS", 1) != 0;
+  DevBuf d_secs, d_staging, d_sizes, d_bounds, d_stats, d_offsets;
   DevBuf z_item_first, z_win_first, z_win_first2, z_recs, z_recs2, z_flags, z_flags2, z_tiles, z_total, z_out, z_chrom_first;
   auto release = [&] {
-    for (DevBuf *b : {&d_row_first, &d_item_first, &d_skip, &d_items, &d_flag, &d_secs, &d_staging, &d_sizes, &d_bounds, &d_stats, &d_offsets, &z_item_first,
-                      &z_win_first, &z_win_first2, &z_recs, &z_recs2, &z_flags, &z_flags2, &z_tiles, &z_total, &z_out, &z_chrom_first})
+    for (DevBuf *b : {&d_secs, &d_staging, &d_sizes, &d_bounds, &d_stats, &d_offsets, &z_item_first, &z_win_first, &z_win_first2, &z_recs, &z_recs2, &z_flags,
+                      &z_flags2, &z_tiles, &z_total, &z_out, &z_chrom_first})
       b->release();
   };
   BwLevel data;
@@ -2510,43 +2486,8 @@ void Pileup::to_bigwig(const std::string &path) {
   int fd = -1;
   char *map = nullptr;
   uint64_t file_bytes = 0;
+  const double t_items = now_ms();
   try {
-    // ---- items of the kept references ----
-    std::vector<uint64_t> row_first(n_ref + 1, 0), item_first(n_ref + 1, 0);
-    d_row_first.ensure((n_ref + 1) * 8);
-    if (im.n_runs) {
-      CU(launch_bw_row_first(im.d_run_bin.as<uint64_t>(), im.n_runs, im.gdev, d_row_first.as<uint64_t>(), st));
-      CU(cudaMemcpyAsync(row_first.data(), d_row_first.p, (n_ref + 1) * 8, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-    }
-    for (size_t r = 0; r < n_ref; r++) item_first[r + 1] = item_first[r] + (skip[r] ? 0 : row_first[r + 1] - row_first[r]);
-    const uint64_t n_items = item_first[n_ref];
-    std::vector<uint64_t> chrom_item_first(n_chrom + 1, 0);  // per dense chromosome
-    for (uint32_t c = 0; c < n_chrom; c++) chrom_item_first[c] = item_first[ref_of_dense[c]];
-    chrom_item_first[n_chrom] = n_items;
-    upload(d_item_first, item_first.data(), item_first.size());
-    upload(d_skip, skip.data(), skip.size());
-    d_items.ensure(std::max<uint64_t>(n_items, 1) * sizeof(BwItem));
-    d_flag.ensure(16);
-    CU(cudaMemsetAsync(d_flag.p, 0, 16, st));
-    if (im.n_runs) {
-      BwItemArgs ia{};
-      ia.run_bin = im.d_run_bin.as<uint64_t>();
-      ia.run_val = im.d_run_val.as<uint32_t>();
-      ia.n_runs = im.n_runs;
-      ia.g = im.gdev;
-      ia.row_first = d_row_first.as<uint64_t>();
-      ia.item_first = d_item_first.as<uint64_t>();
-      ia.ref_skip = d_skip.as<uint8_t>();
-      ia.factor = factor;
-      ia.items = d_items.as<BwItem>();
-      ia.range_error = d_flag.as<unsigned int>();
-      CU(launch_bw_items(ia, ctx.sm_count, st));
-      unsigned int bad = 0;
-      CU(cudaMemcpyAsync(&bad, d_flag.p, 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      if (bad) fail("interval out of range for BigWig");
-    }
     // ---- one level = section table -> zlib streams -> packed blob ----
     auto encode = [&](BwLevel &lv, const uint8_t *units, const std::vector<uint64_t> &first_unit_of_chrom, uint32_t unit_bytes, uint32_t header_bytes,
                       const uint32_t lags[4], bool want_stats) {
@@ -2618,7 +2559,6 @@ void Pileup::to_bigwig(const std::string &path) {
       CU(cudaStreamSynchronize(st));  // d_secs / d_staging are reused by the next level
     };
     const uint32_t item_lags[4] = {4, 8, 12, 24};  // start = previous end (lag 8), fields of the previous items (12, 24), zero / equal halves (4)
-    const double t_items = now_ms();
     encode(data, d_items.as<uint8_t>(), chrom_item_first, BW_ITEM_BYTES, BW_SEC_HEADER, item_lags, true);
     const double t_data = now_ms();
 
@@ -2772,10 +2712,91 @@ void Pileup::to_bigwig(const std::string &path) {
   release();
   g_unmapper.submit(map, file_bytes);
   if (close(fd) != 0) fail("write error on " + path);
-  tm_.text_ms = now_ms() - t0;
   if (env_u64("BND_DEBUG_TIMING", 0))
     fprintf(stderr, "[bnd] to_bigwig: %llu sections, %llu bytes of data sections, %zu zoom levels, %.2f ms after the pile-up\n",
             (unsigned long long)data.secs.size(), (unsigned long long)data.bytes, zooms.size(), now_ms() - t0);
+}
+
+
+}  // namespace
+
+void Pileup::to_bigwig(const std::string &path) {
+  ensure_finalized();
+  g_unmapper.reap();
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  const double t0 = now_ms();
+  const double factor = norm_factor();
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  CU(cudaSetDevice(ctx.device));
+  cudaStream_t st = ctx.sets[0].stream;
+  const size_t n_ref = hdr_.names.size();
+
+  // chromosome ids are dense (0 .. kept - 1, header order): readers such as libBigWig index arrays of `itemCount`
+  // entries by id, so the BAM reference index cannot be used once references are dropped
+  std::vector<uint8_t> skip(n_ref, 0);
+  std::vector<uint32_t> dense(n_ref, 0);
+  std::vector<std::tuple<std::string, uint32_t, uint32_t>> chroms;
+  std::vector<int> ref_of_dense;
+  for (size_t r = 0; r < n_ref; r++) {
+    skip[r] = cfg_.ignore_scaffold && is_scaffold(hdr_.names[r]);
+    if (hdr_.lens[r] > 0xffffffffull) fail("chromosome too long for BigWig");
+    if (!skip[r]) {
+      dense[r] = (uint32_t)chroms.size();
+      chroms.emplace_back(hdr_.names[r], dense[r], (uint32_t)hdr_.lens[r]);
+      ref_of_dense.push_back((int)r);
+    }
+  }
+  const uint32_t n_chrom = (uint32_t)chroms.size();
+
+  DevBuf d_row_first, d_item_first, d_skip, d_items, d_flag;
+  auto release = [&] {
+    for (DevBuf *b : {&d_row_first, &d_item_first, &d_skip, &d_items, &d_flag}) b->release();
+  };
+  try {
+    // ---- items of the kept references ----
+    std::vector<uint64_t> row_first(n_ref + 1, 0), item_first(n_ref + 1, 0);
+    d_row_first.ensure((n_ref + 1) * 8);
+    if (im.n_runs) {
+      CU(launch_bw_row_first(im.d_run_bin.as<uint64_t>(), im.n_runs, im.gdev, d_row_first.as<uint64_t>(), st));
+      CU(cudaMemcpyAsync(row_first.data(), d_row_first.p, (n_ref + 1) * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
+    for (size_t r = 0; r < n_ref; r++) item_first[r + 1] = item_first[r] + (skip[r] ? 0 : row_first[r + 1] - row_first[r]);
+    const uint64_t n_items = item_first[n_ref];
+    std::vector<uint64_t> chrom_item_first(n_chrom + 1, 0);  // per dense chromosome
+    for (uint32_t c = 0; c < n_chrom; c++) chrom_item_first[c] = item_first[ref_of_dense[c]];
+    chrom_item_first[n_chrom] = n_items;
+    upload(d_item_first, item_first.data(), item_first.size());
+    upload(d_skip, skip.data(), skip.size());
+    d_items.ensure(std::max<uint64_t>(n_items, 1) * sizeof(BwItem));
+    d_flag.ensure(16);
+    CU(cudaMemsetAsync(d_flag.p, 0, 16, st));
+    if (im.n_runs) {
+      BwItemArgs ia{};
+      ia.run_bin = im.d_run_bin.as<uint64_t>();
+      ia.run_val = im.d_run_val.as<uint32_t>();
+      ia.n_runs = im.n_runs;
+      ia.g = im.gdev;
+      ia.row_first = d_row_first.as<uint64_t>();
+      ia.item_first = d_item_first.as<uint64_t>();
+      ia.ref_skip = d_skip.as<uint8_t>();
+      ia.factor = factor;
+      ia.items = d_items.as<BwItem>();
+      ia.range_error = d_flag.as<unsigned int>();
+      CU(launch_bw_items(ia, ctx.sm_count, st));
+      unsigned int bad = 0;
+      CU(cudaMemcpyAsync(&bad, d_flag.p, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (bad) fail("interval out of range for BigWig");
+    }
+    encode_bigwig_file(ctx, st, path, chroms, chrom_item_first, d_items, t0);
+  } catch (...) {
+    release();
+    throw;
+  }
+  release();
+  tm_.text_ms = now_ms() - t0;
 }
 
 // Sharded jobs write ONE bedGraph (write_bedgraph, coverage_analysis.rs:43-75): every rank formats its rows on the device and

@@ -275,20 +275,35 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
 
 
 // Inflate one BGZF block with one warp.  Returns a status code (same on every lane).
-template <class Smem>
+// ZLIB: the same walk over a zlib stream (RFC 1950: 2-byte header, DEFLATE, big-endian Adler-32) as BigWig sections are stored
+// (bigwig_io.cuh); `isize_expected` is then the capacity of `out`, the inflated size is returned through `out_len` and the
+// Adler-32 is checked instead of the CRC-32.
+template <class Smem, bool ZLIB = false>
 __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables &T, const uint8_t *blk, uint32_t blk_size, uint8_t *out,
-                                  uint32_t isize_expected, const CrcTables *crcT, int verify_crc) {
+                                  uint32_t isize_expected, const CrcTables *crcT, int verify_crc, uint32_t *out_len = nullptr) {
   constexpr int NM = Smem::MAX_MATCHES, SPAN = Smem::SPAN, STAGE_WORDS = Smem::STAGE_WORDS;
   static_assert(SPAN >= 64 && (SPAN + 64) / 2 <= NM, "a span's matches (>= 2 bits each) must fit the match list");
   const int lane = tile.lane;
-  if (blk_size < 26) return INF_BAD_HEADER;
-  const uint32_t xlen = blk[10] | ((uint32_t)blk[11] << 8);
-  if (12 + xlen + 8 > blk_size) return INF_BAD_HEADER;
-  const uint8_t *payload = blk + 12 + xlen;
-  const uint8_t *pend = blk + blk_size - 8;
-  const uint32_t crc_expected = pend[0] | ((uint32_t)pend[1] << 8) | ((uint32_t)pend[2] << 16) | ((uint32_t)pend[3] << 24);
-  const uint32_t isize = pend[4] | ((uint32_t)pend[5] << 8) | ((uint32_t)pend[6] << 16) | ((uint32_t)pend[7] << 24);
-  if (isize != isize_expected) return INF_SIZE_MISMATCH;
+  const uint8_t *payload, *pend;
+  uint32_t crc_expected, isize;
+  if (ZLIB) {
+    if (blk_size < 6) return INF_BAD_HEADER;
+    const uint32_t cmf = blk[0], flg = blk[1];
+    if ((cmf & 0x0fu) != 8u || ((cmf << 8) | flg) % 31u != 0u || (flg & 0x20u)) return INF_BAD_HEADER;  // deflate, valid check bits, no preset dictionary
+    payload = blk + 2;
+    pend = blk + blk_size - 4;
+    crc_expected = ((uint32_t)pend[0] << 24) | ((uint32_t)pend[1] << 16) | ((uint32_t)pend[2] << 8) | pend[3];  // Adler-32, big-endian
+    isize = isize_expected;  // capacity
+  } else {
+    if (blk_size < 26) return INF_BAD_HEADER;
+    const uint32_t xlen = blk[10] | ((uint32_t)blk[11] << 8);
+    if (12 + xlen + 8 > blk_size) return INF_BAD_HEADER;
+    payload = blk + 12 + xlen;
+    pend = blk + blk_size - 8;
+    crc_expected = pend[0] | ((uint32_t)pend[1] << 8) | ((uint32_t)pend[2] << 16) | ((uint32_t)pend[3] << 24);
+    isize = pend[4] | ((uint32_t)pend[5] << 8) | ((uint32_t)pend[6] << 16) | ((uint32_t)pend[7] << 24);
+    if (isize != isize_expected) return INF_SIZE_MISMATCH;
+  }
   if (isize > 65536u) return INF_BAD_HEADER;  // BGZF blocks hold at most 64 KiB (SAM spec 4.1); match positions are 16-bit here
 
   // the payload as a bit-addressed array of aligned words
@@ -364,7 +379,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
       outpos += stored_len;
       p0 += stored_len * 8;
       tile.sync();
-      if (verify_crc) crc.advance(lane, out, outpos, crcT);
+      if (!ZLIB && verify_crc) crc.advance(lane, out, outpos, crcT);
       continue;
     }
     if (btype == 1) {
@@ -563,8 +578,29 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
         }
       }
       outpos += total;
-      if (verify_crc) crc.advance(lane, out, outpos, crcT);  // the round's bytes are final and still cached
+      if (!ZLIB && verify_crc) crc.advance(lane, out, outpos, crcT);  // the round's bytes are final and still cached
     }
+  }
+  if (ZLIB) {
+    tile.sync();
+    if (status == INF_OK) {
+      // Adler-32 of the inflated bytes: a = 1 + sum b_i, b = n + sum (n - i) b_i, both mod 65521
+      uint64_t sa = 0, sb = 0;
+      for (uint32_t i = (uint32_t)lane; i < outpos; i += 32) {
+        const uint64_t x = out[i];
+        sa += x;
+        sb += (uint64_t)(outpos - i) * x;
+      }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        sa += tile.shfl_xor(sa, d);
+        sb += tile.shfl_xor(sb, d);
+      }
+      const uint32_t adler = ((uint32_t)((outpos + sb) % 65521u) << 16) | (uint32_t)((1 + sa) % 65521u);
+      if (verify_crc && adler != crc_expected) status = INF_CRC_MISMATCH;
+      if (out_len && lane == 0) *out_len = outpos;
+    }
+    return status;
   }
   if (status == INF_OK && outpos != isize) status = INF_SIZE_MISMATCH;
   tile.sync();
@@ -579,7 +615,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
 // read them through L1 from global memory instead.  That shape was tried to let a finished warp hand its slot to the next
 // segment's launch without waiting for its nine CTA neighbours: measured 8 % slower at 40 M pairs (124.5 vs 115.5 ms per pass;
 // two-warp CTAs 121.7 ms), so blocks are not waiting for slots - the ten-warp shape stays (profiles/r2_sweeps.md).
-template <int THREADS, int MIN_CTAS, int LB, int DB, int SPAN, int NT, bool CRC_SMEM>
+template <int THREADS, int MIN_CTAS, int LB, int DB, int SPAN, int NT, bool CRC_SMEM, bool ZLIB = false>
 __global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs a) {
   using Smem = SpecSmemT<LB, DB, NT, SPAN>;
   BND_DYN_SMEM(smem_raw);
@@ -596,7 +632,7 @@ __global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs 
     const uint32_t dbase = s < 4 ? s + 1 : ((2 + (s & 1)) << deb) + 1;
     sym_s->dist_tab[s] = s < 30 ? (dbase | (deb << 16)) : 0u;
   }
-  if (CRC_SMEM) {
+  if (CRC_SMEM && !ZLIB) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(a.crc);
     uint32_t *dst = reinterpret_cast<uint32_t *>(crc_s);
     for (int i = threadIdx.x; i < (int)(sizeof(CrcTables) / 4); i += THREADS) dst[i] = src[i];
@@ -612,7 +648,8 @@ __global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs 
     if (b >= a.n_blocks) break;
     const uint64_t c0 = a.blk_coff[b], c1 = a.blk_coff[b + 1];
     const uint64_t u0 = a.blk_uoff[b], u1 = a.blk_uoff[b + 1];
-    const int st = inflate_block_spec<Smem>(tile, S, *sym_s, a.comp + c0, (uint32_t)(c1 - c0), a.out + u0, (uint32_t)(u1 - u0), crcT, a.verify_crc);
+    const int st = inflate_block_spec<Smem, ZLIB>(tile, S, *sym_s, a.comp + c0, (uint32_t)(c1 - c0), a.out + u0, (uint32_t)(u1 - u0), crcT, a.verify_crc,
+                                                  ZLIB && a.out_len ? a.out_len + b : nullptr);
     if (tile.lane == 0) {
       if (a.status) a.status[b] = st;
       if (st != INF_OK) atomicCAS(a.error_flag, 0, st | ((int)(b & 0xffffff) << 8));

@@ -43,6 +43,7 @@ struct InflateArgs {
   int32_t *status;            // [n] per-block status, or nullptr
   int32_t *error_flag;        // sticky: first non-zero status (atomicCAS)
   uint32_t *work_counter;     // dynamic block scheduler (zeroed before launch)
+  uint32_t *out_len;          // zlib streams only: [n] inflated size of each stream (blk_uoff then holds capacities)
   const CrcTables *crc;       // device-resident tables for this G
   uint32_t n_blocks;
   int verify_crc;

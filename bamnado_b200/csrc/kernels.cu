@@ -53,9 +53,9 @@ int shape_index() {
   }
   return v;
 }
-template <int T, int MINB, int LB, int DB, int SPAN, int NT, bool CRC_SMEM>
+template <int T, int MINB, int LB, int DB, int SPAN, int NT, bool CRC_SMEM, bool ZLIB = false>
 cudaError_t launch_inflate_spec_t(const InflateArgs &a, int sm_count, int ctas_per_sm, cudaStream_t s) {
-  auto kern = bgzf_inflate_spec_kernel<T, MINB, LB, DB, SPAN, NT, CRC_SMEM>;
+  auto kern = bgzf_inflate_spec_kernel<T, MINB, LB, DB, SPAN, NT, CRC_SMEM, ZLIB>;
   constexpr int warps = T / 32;
   const size_t smem = inflate_spec_smem_bytes<LB, DB, NT, SPAN>(warps, CRC_SMEM);
   static bool attr_done = false;
@@ -96,6 +96,12 @@ cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
     case 3: return launch_inflate_spec_t<32, 30, 9, 8, 320, 384, false>(a, sm_count, v.ctas_per_sm, s);  // 30 one-warp CTAs / SM, CRC tables through L1 (A/B: 8 % slower)
     default: return launch_inflate_spec_t<320, 3, 9, 8, 320, 384, true>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM in three CTAs, 320-bit spans
   }
+}
+
+// zlib streams (BigWig sections): the same walk, Adler-32 instead of CRC-32, sizes reported per stream
+cudaError_t launch_inflate_zlib(const InflateArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_blocks == 0) return cudaSuccess;
+  return launch_inflate_spec_t<320, 3, 9, 8, 320, 384, true, true>(a, sm_count, 3, s);
 }
 
 cudaError_t launch_record_index(const RecArgs &a, cudaStream_t s) {

@@ -11,6 +11,7 @@ int inflate_ctas_per_sm();
 cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s);
 
 // K2 — record index (records.cuh): guess+walk, fix+scan, compact
+cudaError_t launch_inflate_zlib(const InflateArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_record_index(const RecArgs &a, cudaStream_t s);
 cudaError_t launch_carry_copy(const uint8_t *src_buf, uint8_t *dst_buf, const SegState *prev, SegState *cur,
                               uint64_t carry_cap, cudaStream_t s);
