@@ -30,7 +30,7 @@ EXPORTS = [
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
     "bnd_pileup_timings", "bnd_pileup_shape", "bnd_pileup_preallocate_output", "bnd_pileup_preallocated_bytes", "bnd_pileup_format_bedgraph", "bnd_pileup_write_bedgraph_pieces", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
-    "bnd_multi_prepare_resident", "bnd_multi_change_bits", "bnd_multi_or_bits", "bnd_multi_compact_columns", "bnd_multi_format_tsv", "bnd_multi_write_tsv_pieces", "bnd_pileup_refs", "bnd_collapse_bedgraph",
+    "bnd_multi_prepare_resident", "bnd_multi_change_bits", "bnd_multi_or_bits", "bnd_multi_compact_columns", "bnd_multi_format_tsv", "bnd_multi_write_tsv_pieces", "bnd_pileup_refs", "bnd_collapse_bedgraph", "bnd_bigwig_compare", "bnd_bigwig_aggregate", "bnd_bigwig_from_intervals",
     "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
 ]
 
@@ -165,6 +165,10 @@ class Native:
         L.bnd_multi_write_tsv_pieces.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
         L.bnd_pileup_refs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
         L.bnd_collapse_bedgraph.argtypes = [C.c_char_p, C.c_char_p]
+        dp = C.POINTER(C.c_double)
+        L.bnd_bigwig_compare.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_uint32, dp, dp, dp]
+        L.bnd_bigwig_aggregate.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_char_p, C.c_int32, C.c_uint32, dp, dp]
+        L.bnd_bigwig_from_intervals.argtypes = [C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p]
         L.bnd_scale_factor.restype = C.c_double
         L.bnd_scale_factor.argtypes = [C.c_int32, C.c_float, C.c_uint64, C.c_uint64]
         L.bnd_bam_stats.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -276,6 +280,28 @@ class Native:
 
     def collapse_bedgraph(self, in_path, out_path):
         self.check(self.L.bnd_collapse_bedgraph(_b(in_path), _b(out_path)))
+
+    COMPARISONS = {"subtraction": 0, "ratio": 1, "log-ratio": 2}
+    AGGREGATIONS = {"sum": 0, "mean": 1, "max": 2, "min": 3, "median": 4}
+
+    def bigwig_compare(self, bw1, bw2, out_path, comparison: str, bin_size: int = 50, pseudocount=None, scale_factor_bw1=None, scale_factor_bw2=None):
+        opt = lambda v: None if v is None else C.byref(C.c_double(v))  # noqa: E731
+        self.check(self.L.bnd_bigwig_compare(_b(bw1), _b(bw2), _b(out_path), self.COMPARISONS[comparison], bin_size, opt(pseudocount), opt(scale_factor_bw1),
+                                             opt(scale_factor_bw2)))
+
+    def bigwig_aggregate(self, bigwigs: list, out_path, method: str, bin_size: int = 50, pseudocount=None, scale_factors=None):
+        paths = (C.c_char_p * len(bigwigs))(*[_b(p) for p in bigwigs])
+        sf = (C.c_double * len(scale_factors))(*scale_factors) if scale_factors is not None else None
+        pc = None if pseudocount is None else C.byref(C.c_double(pseudocount))
+        self.check(self.L.bnd_bigwig_aggregate(paths, len(bigwigs), _b(out_path), self.AGGREGATIONS[method], bin_size, pc, sf))
+
+    def bigwig_from_intervals(self, chroms: list, chrom_idx, start, end, value, out_path):
+        """chroms: [(name, length)]; the four arrays describe intervals sorted by (chromosome index, start)."""
+        names = (C.c_char_p * len(chroms))(*[c[0].encode() for c in chroms])
+        lens = np.ascontiguousarray([c[1] for c in chroms], dtype=np.uint32)
+        ci, st, en = (np.ascontiguousarray(x, dtype=np.uint32) for x in (chrom_idx, start, end))
+        va = np.ascontiguousarray(value, dtype=np.float32)
+        self.check(self.L.bnd_bigwig_from_intervals(names, lens.ctypes.data, len(chroms), ci.ctypes.data, st.ctypes.data, en.ctypes.data, va.ctypes.data, len(ci), _b(out_path)))
 
     def cli_main(self, argv: list) -> int:
         arr = (C.c_char_p * len(argv))(*[_b(a) for a in argv])

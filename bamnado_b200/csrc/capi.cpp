@@ -242,6 +242,18 @@ int bnd_multi_write_tsv_pieces(bnd_pileup *p, const char *out_path, const char *
   return guarded([&] { P(p)->multi_write_tsv_pieces(out_path, header, bytes_all, world, rank); });
 }
 
+int bnd_bigwig_compare(const char *bw1, const char *bw2, const char *out_path, int32_t comparison, uint32_t bin_size, const double *pseudocount,
+                       const double *scale_factor_bw1, const double *scale_factor_bw2) {
+  return guarded([&] { bnd::bigwig_compare(bw1, bw2, out_path, comparison, bin_size, pseudocount, scale_factor_bw1, scale_factor_bw2, -1); });
+}
+int bnd_bigwig_aggregate(const char *const *bw_paths, int32_t n, const char *out_path, int32_t method, uint32_t bin_size, const double *pseudocount,
+                         const double *scale_factors) {
+  return guarded([&] { bnd::bigwig_aggregate(bw_paths, n, out_path, 10 + method, bin_size, pseudocount, scale_factors, -1); });
+}
+int bnd_bigwig_from_intervals(const char *const *chrom_names, const uint32_t *chrom_lens, uint32_t n_chrom, const uint32_t *chrom_idx, const uint32_t *start,
+                              const uint32_t *end, const float *value, uint64_t n, const char *out_path) {
+  return guarded([&] { bnd::bigwig_from_intervals(chrom_names, chrom_lens, n_chrom, chrom_idx, start, end, value, n, out_path, -1); });
+}
 int bnd_collapse_bedgraph(const char *in_path, const char *out_path) {
   return guarded([&] { bnd::collapse_bedgraph_file(in_path, out_path); });
 }

@@ -2894,4 +2894,6 @@ void Pileup::write_bedgraph_pieces(const std::string &path, const uint64_t *byte
   if (env_u64("BND_DEBUG_TIMING", 0)) fprintf(stderr, "[bnd] write_bedgraph_pieces: reap + place + open + size %.2f ms, pieces %.2f ms\n", t_open - t0, now_ms() - t_open);
 }
 
+#include "bigwig_tools.inl"
+
 }  // namespace bnd

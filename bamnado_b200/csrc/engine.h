@@ -144,4 +144,14 @@ struct BdgRows {
 };
 void collapse_bedgraph_text(const uint8_t *text, uint64_t n, std::vector<std::string> &names, BdgRows &out, int device);
 
+// bigwig-compare / bigwig-aggregate (bamnado/src/bigwig_compare.rs:616-790) on the device.  comparison: 0 subtraction, 1 ratio,
+// 2 log-ratio; mode: 10 sum, 11 mean, 12 max, 13 min, 14 median (kernel_args.h BWT_*).  Null pointers = the reference's defaults.
+void bigwig_compare(const char *bw1, const char *bw2, const char *out, int comparison, uint32_t bin_size, const double *pseudocount, const double *scale1,
+                    const double *scale2, int device);
+void bigwig_aggregate(const char *const *paths, int n, const char *out, int mode, uint32_t bin_size, const double *pseudocount, const double *scale_factors,
+                      int device);
+
+void bigwig_from_intervals(const char *const *chrom_names, const uint32_t *chrom_lens, uint32_t n_chrom, const uint32_t *chrom_idx, const uint32_t *start,
+                           const uint32_t *end, const float *value, uint64_t n, const char *out_path, int device);
+
 }  // namespace bnd

@@ -646,7 +646,8 @@ __global__ void __maxnreg__(BND_K1_MAXREG) bgzf_inflate_spec_kernel(InflateArgs 
     if (tile.lane == 0) b = atomicAdd(a.work_counter, 1u);
     b = tile.shfl(b, 0);
     if (b >= a.n_blocks) break;
-    const uint64_t c0 = a.blk_coff[b], c1 = a.blk_coff[b + 1];
+    const uint32_t cs = ZLIB && a.coff_stride == 2 ? 2u : 1u;
+    const uint64_t c0 = a.blk_coff[(uint64_t)b * cs], c1 = a.blk_coff[(uint64_t)b * cs + 1];
     const uint64_t u0 = a.blk_uoff[b], u1 = a.blk_uoff[b + 1];
     const int st = inflate_block_spec<Smem, ZLIB>(tile, S, *sym_s, a.comp + c0, (uint32_t)(c1 - c0), a.out + u0, (uint32_t)(u1 - u0), crcT, a.verify_crc,
                                                   ZLIB && a.out_len ? a.out_len + b : nullptr);

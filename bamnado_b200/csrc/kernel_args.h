@@ -44,6 +44,7 @@ struct InflateArgs {
   int32_t *error_flag;        // sticky: first non-zero status (atomicCAS)
   uint32_t *work_counter;     // dynamic block scheduler (zeroed before launch)
   uint32_t *out_len;          // zlib streams only: [n] inflated size of each stream (blk_uoff then holds capacities)
+  uint32_t coff_stride;       // zlib streams only: 2 = blk_coff holds (begin, end) pairs instead of consecutive offsets
   const CrcTables *crc;       // device-resident tables for this G
   uint32_t n_blocks;
   int verify_crc;
@@ -423,6 +424,41 @@ struct BwZoomArgs {
   const uint8_t *prev_recs;    // level below (dense slots, reduction / 4), or null: build this level from the items
   const uint8_t *prev_flags;
   const uint64_t *prev_win_first;
+};
+
+// ---- bigwig-compare / bigwig-aggregate (bigwig_tools.cuh) --------------------------------------------------------------------
+struct BwrEmitArgs {  // inflated sections -> items
+  const uint8_t *data;
+  const uint64_t *sec_off;   // [n_secs] byte offset of every section in `data`
+  const uint64_t *item_off;  // [n_secs] first item of every section
+  uint32_t n_secs;
+  BwItem *items;
+  unsigned int *bad;         // bit 0: empty interval, bit 1: overlapping / unsorted intervals
+};
+
+constexpr int BWT_MAX_FILES = 64;
+enum : int { BWT_SUBTRACTION = 0, BWT_RATIO = 1, BWT_LOGRATIO = 2, BWT_SUM = 10, BWT_MEAN = 11, BWT_MAX = 12, BWT_MIN = 13, BWT_MEDIAN = 14 };
+
+struct BwtArgs {
+  int n_files, mode;
+  const BwItem *items[BWT_MAX_FILES];
+  const uint64_t *range[BWT_MAX_FILES];  // [n_chrom][2]: items of output chromosome c in file f
+  double scale[BWT_MAX_FILES];
+  double pseudocount;
+  uint32_t n_chrom, bin_size;
+  const uint64_t *bin_first;   // [n_chrom + 1] first output bin of every chromosome
+  const uint32_t *chrom_len;   // [n_chrom]
+  uint64_t n_bins;
+  float *bins;                 // [n_bins]
+  // weighted median: pairs per bin (counts -> exclusive offsets after the scan) and their storage
+  uint64_t *pair_off;
+  float *pair_val;
+  uint32_t *pair_w;
+  // bins -> items
+  uint64_t *tile_count;
+  uint32_t n_tiles;
+  BwItem *out_items;
+  uint64_t *chrom_item_first;  // [n_chrom]
 };
 
 }  // namespace bnd

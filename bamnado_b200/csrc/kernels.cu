@@ -13,6 +13,7 @@
 
 #include "bedgraph_parse.cuh"
 #include "bigwig.cuh"
+#include "bigwig_tools.cuh"
 #include "collapse.cuh"
 #include "finalize.cuh"
 #include "inflate_spec.cuh"
@@ -330,6 +331,48 @@ cudaError_t launch_bw_zoom_compact(const BwZoomArgs &a, unsigned long long total
   cudaError_t e = launched();
   if (e != cudaSuccess) return e;
   BND_LAUNCH(bw_zoom_chrom_first_kernel, dim3((a.n_chrom + 1 + 127) / 128), dim3(128), 0, s, a, total);
+  return launched();
+}
+
+// ---- bigwig-compare / bigwig-aggregate (bigwig_tools.cuh) --------------------------------------------------------------------
+cudaError_t launch_bwr_headers(const uint8_t *data, const uint64_t *sec_off, uint32_t n_secs, uint32_t *headers, int sm_count, cudaStream_t s) {
+  if (n_secs == 0) return cudaSuccess;
+  BND_LAUNCH(bwr_headers_kernel, dim3(grid_for(n_secs, 256, (uint64_t)sm_count * 8)), dim3(256), 0, s, data, sec_off, n_secs, headers);
+  return launched();
+}
+cudaError_t launch_bwr_emit_items(const BwrEmitArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_secs == 0) return cudaSuccess;
+  BND_LAUNCH(bwr_emit_items_kernel, dim3(grid_for(a.n_secs, 8, (uint64_t)sm_count * 8)), dim3(256), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bwr_check_sorted(const BwItem *items, const uint64_t *range, uint32_t n_chrom, unsigned int *bad, int sm_count, cudaStream_t s) {
+  if (n_chrom == 0) return cudaSuccess;
+  BND_LAUNCH(bwr_check_sorted_kernel, dim3((unsigned)sm_count, std::min<uint32_t>(n_chrom, 1024u)), dim3(256), 0, s, items, range, n_chrom, bad);
+  return launched();
+}
+cudaError_t launch_bwt_bins(const BwtArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_bins == 0) return cudaSuccess;
+  BND_LAUNCH(bwt_bins_kernel, dim3(grid_for(a.n_bins, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bwt_median_count(const BwtArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_bins == 0) return cudaSuccess;
+  BND_LAUNCH(bwt_median_count_kernel, dim3(grid_for(a.n_bins, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bwt_median_fill(const BwtArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_bins == 0) return cudaSuccess;
+  BND_LAUNCH(bwt_median_fill_kernel, dim3(grid_for(a.n_bins, 256, (uint64_t)sm_count * 16)), dim3(256), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bwt_heads(const BwtArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bwt_heads_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bwt_emit(const BwtArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_tiles == 0) return cudaSuccess;
+  BND_LAUNCH(bwt_emit_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
   return launched();
 }
 

@@ -67,4 +67,14 @@ cudaError_t sort_rows_by_chrom_start(const uint32_t *d_chrom, const long long *d
 // number of kernel launches issued through this file since process start (bench's gpu_launches)
 unsigned long long launch_count();
 
+// bigwig-compare / bigwig-aggregate (bigwig_tools.cuh)
+cudaError_t launch_bwr_headers(const uint8_t *data, const uint64_t *sec_off, uint32_t n_secs, uint32_t *headers, int sm_count, cudaStream_t s);
+cudaError_t launch_bwr_emit_items(const BwrEmitArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bwr_check_sorted(const BwItem *items, const uint64_t *range, uint32_t n_chrom, unsigned int *bad, int sm_count, cudaStream_t s);
+cudaError_t launch_bwt_bins(const BwtArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bwt_median_count(const BwtArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bwt_median_fill(const BwtArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bwt_heads(const BwtArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bwt_emit(const BwtArgs &a, int sm_count, cudaStream_t s);
+
 }  // namespace bnd

@@ -160,6 +160,8 @@ const char *TOP_HELP =
     "Commands (B200 coverage path):\n"
     "  bam-coverage        Generate a coverage track from one BAM file [aliases: coverage]\n"
     "  multi-bam-coverage  Merge coverage from multiple BAM files into one track [aliases: multi-coverage]\n"
+    "  bigwig-compare      Compare two BigWig files bin by bin [aliases: compare-bigwigs]\n"
+    "  bigwig-aggregate    Aggregate multiple BigWig files into one track [aliases: aggregate-bigwigs]\n"
     "  collapse-bedgraph   Collapse adjacent bins with equal scores in a bedGraph file [aliases: collapse]\n\n"
     "Options:\n"
     "  -v, --verbose <LEVEL>  Log verbosity from 0 (quiet) to 4 (debug) [default: 2]\n"
@@ -546,6 +548,79 @@ int run(const std::vector<std::string> &argv) {
       else usage_error("unexpected argument '" + a + "' found");
     }
     collapse_bedgraph_file(has_in ? in.c_str() : nullptr, has_out ? out.c_str() : nullptr);
+    return 0;
+  }
+  if (cmd == "bigwig-compare" || cmd == "compare-bigwigs" || cmd == "bigwig-aggregate" || cmd == "aggregate-bigwigs") {
+    // src/cli.rs:259-330 (flags) and :1081-1147 (dispatch)
+    const bool compare = cmd == "bigwig-compare" || cmd == "compare-bigwigs";
+    std::string bw1, bw2, out, method;
+    std::vector<std::string> inputs;
+    std::vector<double> sfs;
+    uint32_t bin_size = 50;
+    bool has_pc = false, has_sf1 = false, has_sf2 = false;
+    double pc = 0, sf1 = 1, sf2 = 1;
+    auto parse_f64 = [&](const std::string &v, const std::string &opt) {
+      char *e = nullptr;
+      const double x = strtod(v.c_str(), &e);
+      if (v.empty() || *e) usage_error("invalid value '" + v + "' for '" + opt + " <FLOAT>': invalid float literal");
+      return x;
+    };
+    for (size_t k = 0; k < rest.size(); k++) {
+      const std::string &a = rest[k];
+      auto val = [&]() -> std::string {
+        if (k + 1 >= rest.size()) usage_error("a value is required for '" + a + "' but none was supplied");
+        return rest[++k];
+      };
+      auto more = [&]() { return k + 1 < rest.size() && (rest[k + 1].empty() || rest[k + 1][0] != '-' || (rest[k + 1].size() > 1 && (isdigit((unsigned char)rest[k + 1][1]) || rest[k + 1][1] == '.'))); };
+      if (a == "-h" || a == "--help") {
+        if (compare)
+          printf("Compare two BigWig files bin by bin\n\nUsage: bamnado bigwig-compare [OPTIONS] --bw1 <BW> --bw2 <BW> --output <BW> --comparison <METHOD>\n\nOptions:\n"
+                 "      --bw1 <BW>                  First BigWig input\n      --bw2 <BW>                  Second BigWig input\n  -o, --output <BW>               Output BigWig path\n"
+                 "  -c, --comparison <METHOD>       Comparison method [possible values: subtraction, ratio, log-ratio]\n  -s, --bin-size <BP>             Bin size for comparison [default: 50]\n"
+                 "      --pseudocount <FLOAT>       Value added to both tracks before comparison\n      --scale-factor-bw1 <FLOAT>  Scale factor applied to bw1 before comparison\n"
+                 "      --scale-factor-bw2 <FLOAT>  Scale factor applied to bw2 before comparison\n      --threads <THREADS>         Number of threads to use for BigWig writing [default: 6]\n  -h, --help                      Print help\n");
+        else
+          printf("Aggregate multiple BigWig files into one track\n\nUsage: bamnado bigwig-aggregate [OPTIONS] --output <BW> --method <METHOD>\n\nOptions:\n"
+                 "      --bigwigs <BW>...           BigWig files to aggregate\n  -o, --output <BW>               Output BigWig path\n"
+                 "  -m, --method <METHOD>           Aggregation method [possible values: sum, mean, median, max, min]\n  -s, --bin-size <BP>             Bin size for aggregation [default: 50]\n"
+                 "      --pseudocount <FLOAT>       Value added to all inputs before aggregation\n      --scale-factors [<FLOAT>...]  Per-file scale factors (one per --bigwigs input, in order)\n"
+                 "      --threads <THREADS>         Number of threads to use for BigWig writing [default: 6]\n  -h, --help                      Print help\n");
+        return 0;
+      } else if (compare && a == "--bw1") bw1 = val();
+      else if (compare && a == "--bw2") bw2 = val();
+      else if (!compare && a == "--bigwigs") {
+        inputs.push_back(val());
+        while (more()) inputs.push_back(rest[++k]);
+      } else if (a == "-o" || a == "--output") out = val();
+      else if ((compare && (a == "-c" || a == "--comparison")) || (!compare && (a == "-m" || a == "--method"))) method = lower(val());
+      else if (a == "-s" || a == "--bin-size") bin_size = (uint32_t)parse_uint("--bin-size <BP>", val(), 0xffffffffull);
+      else if (a == "--pseudocount") pc = parse_f64(val(), "--pseudocount"), has_pc = true;
+      else if (compare && a == "--scale-factor-bw1") sf1 = parse_f64(val(), "--scale-factor-bw1"), has_sf1 = true;
+      else if (compare && a == "--scale-factor-bw2") sf2 = parse_f64(val(), "--scale-factor-bw2"), has_sf2 = true;
+      else if (!compare && a == "--scale-factors") {
+        while (more()) sfs.push_back(parse_f64(rest[++k], "--scale-factors"));
+      } else if (a == "--threads") val();  // sizes the reference's tokio writer; the device encoder has no use for it
+      else if (a == "-v" || a == "--verbose") val();
+      else usage_error("unexpected argument '" + a + "' found");
+    }
+    if (out.empty()) usage_error("the following required arguments were not provided:\n  --output <BW>");
+    if (compare) {
+      if (bw1.empty() || bw2.empty()) usage_error("the following required arguments were not provided:\n  --bw1 <BW>\n  --bw2 <BW>");
+      int m = method == "subtraction" ? 0 : method == "ratio" ? 1 : method == "log-ratio" ? 2 : -1;
+      if (m < 0) usage_error("invalid value '" + method + "' for '--comparison <METHOD>'\n  [possible values: subtraction, ratio, log-ratio]");
+      bigwig_compare(bw1.c_str(), bw2.c_str(), out.c_str(), m, bin_size, has_pc ? &pc : nullptr, has_sf1 ? &sf1 : nullptr, has_sf2 ? &sf2 : nullptr, -1);
+      fprintf(stderr, "Successfully compared BigWig files and wrote output to %s\n", out.c_str());
+    } else {
+      int m = method == "sum" ? 0 : method == "mean" ? 1 : method == "max" ? 2 : method == "min" ? 3 : method == "median" ? 4 : -1;
+      if (m < 0) usage_error("invalid value '" + method + "' for '--method <METHOD>'\n  [possible values: sum, mean, median, max, min]");
+      if (inputs.empty()) fail("At least one BigWig file must be provided");
+      if (!sfs.empty() && sfs.size() != inputs.size())
+        fail("--scale-factors count (" + std::to_string(sfs.size()) + ") must match input BigWig count (" + std::to_string(inputs.size()) + ")");
+      std::vector<const char *> ps;
+      for (auto &x : inputs) ps.push_back(x.c_str());
+      bigwig_aggregate(ps.data(), (int)ps.size(), out.c_str(), 10 + m, bin_size, has_pc ? &pc : nullptr, sfs.empty() ? nullptr : sfs.data(), -1);
+      fprintf(stderr, "Successfully aggregated %zu BigWig files and wrote output to %s\n", inputs.size(), out.c_str());
+    }
     return 0;
   }
   usage_error("unrecognized subcommand '" + cmd + "'");

@@ -200,6 +200,22 @@ int bnd_multi_write_tsv_pieces(bnd_pileup *p, const char *out_path, const char *
 /* ---- collapse-bedgraph (src/cli.rs:1149-1205 + bedgraph_utils.rs:5-45) ------------------------------------ */
 int bnd_collapse_bedgraph(const char *in_path, const char *out_path);
 
+/* ---- bigwig-compare / bigwig-aggregate (bamnado/src/bigwig_compare.rs:616-790; src/cli.rs:259-297, 299-330, 1081-1147) -------
+ * The sections of every input are inflated on the device, every output bin is computed by its own thread replaying the
+ * reference's sweep for that bin (f64, same order of additions: subtraction / ratio / sum / mean / max / min / median are
+ * bit-identical, log-ratio within 1e-6), equal neighbouring bins merge, and the result is written by the device BigWig encoder.
+ * Chromosomes and their order are those of the first input.  NULL pseudocount / scale factors = the reference's defaults
+ * (compare: 1e-12 and 1.0; aggregate: 0.0 and 1.0).
+ *   comparison: 0 subtraction (bw1 - bw2), 1 ratio (bw1 / (bw2 + pc)), 2 log-ratio (ln((bw1 + pc) / (bw2 + pc)))
+ *   method:     0 sum, 1 mean, 2 max, 3 min, 4 median (weighted lower median over the bases of a bin) */
+int bnd_bigwig_compare(const char *bw1, const char *bw2, const char *out_path, int32_t comparison, uint32_t bin_size, const double *pseudocount,
+                       const double *scale_factor_bw1, const double *scale_factor_bw2);
+int bnd_bigwig_aggregate(const char *const *bw_paths, int32_t n, const char *out_path, int32_t method, uint32_t bin_size, const double *pseudocount,
+                         const double *scale_factors);
+/* A BigWig from explicit intervals (sorted by (chromosome index, start), disjoint): the device encoder on caller-provided rows. */
+int bnd_bigwig_from_intervals(const char *const *chrom_names, const uint32_t *chrom_lens, uint32_t n_chrom, const uint32_t *chrom_idx, const uint32_t *start,
+                              const uint32_t *end, const float *value, uint64_t n, const char *out_path);
+
 /* ---- NormalizationMethod::scale_factor (signal_normalization.rs:50-74) ------------------------------------ */
 double bnd_scale_factor(int32_t method, float base_scale, uint64_t bin_size, uint64_t n_reads);
 

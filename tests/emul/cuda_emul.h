@@ -216,6 +216,14 @@ inline double __dmul_rn(double a, double b) {
   volatile double r = a * b;
   return r;
 }
+inline double __dadd_rn(double a, double b) {
+  volatile double r = a + b;
+  return r;
+}
+inline double __dsub_rn(double a, double b) {
+  volatile double r = a - b;
+  return r;
+}
 // round-to-nearest single operations (the emulator build uses -ffp-contract=off semantics: separate statements)
 inline float __fmul_rn(float a, float b) {
   volatile float r = a * b;
