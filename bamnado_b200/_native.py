@@ -30,8 +30,8 @@ EXPORTS = [
     "bnd_pileup_norm_factor", "bnd_pileup_stats", "bnd_pileup_accumulate", "bnd_pileup_stage",
     "bnd_pileup_accumulate_resident", "bnd_pileup_set_total_stats", "bnd_pileup_finalize", "bnd_pileup_bedgraph_text",
     "bnd_pileup_timings", "bnd_pileup_shape", "bnd_pileup_preallocate_output", "bnd_pileup_preallocated_bytes", "bnd_pileup_format_bedgraph", "bnd_pileup_write_bedgraph_pieces", "bnd_signal_for_chromosome", "bnd_multi_to_tsv", "bnd_bin_counts", "bnd_multi_prepare",
-    "bnd_multi_prepare_resident", "bnd_multi_change_bits", "bnd_multi_or_bits", "bnd_multi_compact_columns", "bnd_multi_format_tsv", "bnd_multi_write_tsv_pieces", "bnd_pileup_refs", "bnd_collapse_bedgraph", "bnd_bigwig_compare", "bnd_bigwig_aggregate", "bnd_bigwig_from_intervals",
-    "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate",
+    "bnd_multi_prepare_resident", "bnd_multi_change_bits", "bnd_multi_or_bits", "bnd_multi_compact_columns", "bnd_multi_format_tsv", "bnd_multi_write_tsv_pieces", "bnd_pileup_refs", "bnd_collapse_bedgraph", "bnd_bigwig_compare", "bnd_bigwig_aggregate", "bnd_bigwig_from_intervals", "bnd_bam_split", "bnd_bam_modify", "bnd_bam_split_exogenous",
+    "bnd_scale_factor", "bnd_bam_stats", "bnd_cli_main", "bnd_bgzf_inflate", "bnd_bgzf_compress",
 ]
 
 
@@ -169,6 +169,11 @@ class Native:
         L.bnd_bigwig_compare.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_uint32, dp, dp, dp]
         L.bnd_bigwig_aggregate.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_char_p, C.c_int32, C.c_uint32, dp, dp]
         L.bnd_bigwig_from_intervals.argtypes = [C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p]
+        u64p = C.POINTER(C.c_uint64)
+        L.bnd_bgzf_compress.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p), u64p]
+        L.bnd_bam_split.argtypes = [C.c_char_p, C.POINTER(FilterCfg), C.c_char_p, C.c_char_p, C.c_int32, u64p]
+        L.bnd_bam_modify.argtypes = [C.c_char_p, C.POINTER(FilterCfg), C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, u64p]
+        L.bnd_bam_split_exogenous.argtypes = [C.c_char_p, C.POINTER(FilterCfg), C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, u64p]
         L.bnd_scale_factor.restype = C.c_double
         L.bnd_scale_factor.argtypes = [C.c_int32, C.c_float, C.c_uint64, C.c_uint64]
         L.bnd_bam_stats.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -202,6 +207,15 @@ class Native:
         out = (C.c_uint64 * 6)()
         self.check(self.L.bnd_bam_stats(_b(bam_path), bin_size, out))
         return dict(zip(["n_mapped", "n_unmapped", "genome_len", "chunk_len", "n_chunks", "n_refs"], [int(v) for v in out]))
+
+    def bgzf_compress(self, data: bytes) -> bytes:
+        """The device BGZF compressor on its own: BGZF blocks + EOF marker."""
+        out, n = C.c_void_p(), C.c_uint64()
+        self.check(self.L.bnd_bgzf_compress(data, len(data), C.byref(out), C.byref(n)))
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            self.L.bnd_free(out)
 
     def bgzf_inflate(self, data: bytes):
         """K1 on its own: returns (inflated bytes, per-block status array)."""
@@ -302,6 +316,30 @@ class Native:
         ci, st, en = (np.ascontiguousarray(x, dtype=np.uint32) for x in (chrom_idx, start, end))
         va = np.ascontiguousarray(value, dtype=np.float32)
         self.check(self.L.bnd_bigwig_from_intervals(names, lens.ctypes.data, len(chroms), ci.ctypes.data, st.ctypes.data, en.ctypes.data, va.ctypes.data, len(ci), _b(out_path)))
+
+    BAM_WRITE_COUNTERS = ["n_total_reads", "n_unmapped_reads", "n_qcfail_reads", "n_duplicate_reads", "n_secondary_reads", "n_filtered_reads", "n_low_maq",
+                          "n_both_genomes", "n_exogenous", "n_endogenous", "n_written", "n_dropped_by_shift", "n_errors"]
+
+    def _bam_counters(self, arr):
+        return {k: int(arr[i]) for i, k in enumerate(self.BAM_WRITE_COUNTERS)}
+
+    def bam_split(self, bam, out_path, filt: dict | None = None, command_line: str = "", device: int = -1):
+        """`bamnado split` (BamFilterer): the records the filter keeps, written as one BAM."""
+        f, cnt = make_filter_cfg(**(filt or {})), (C.c_uint64 * 16)()
+        self.check(self.L.bnd_bam_split(_b(bam), C.byref(f), _b(out_path), _b(command_line), device, cnt))
+        return self._bam_counters(cnt)
+
+    def bam_modify(self, bam, out_path, filt: dict | None = None, tn5_shift: bool = False, command_line: str = "", device: int = -1):
+        """`bamnado modify` (BamModifier): filter, optionally the Tn5 shift of every properly paired record."""
+        f, cnt = make_filter_cfg(**(filt or {})), (C.c_uint64 * 16)()
+        self.check(self.L.bnd_bam_modify(_b(bam), C.byref(f), int(bool(tn5_shift)), _b(out_path), _b(command_line), device, cnt))
+        return self._bam_counters(cnt)
+
+    def bam_split_exogenous(self, bam, out_prefix, exogenous_prefix: str, filt: dict | None = None, command_line: str = "", device: int = -1):
+        """`bamnado split-exogenous` (BamSplitter): <prefix>.{endogenous,exogenous,both,unmapped}.bam + SplitStats counters."""
+        f, cnt = make_filter_cfg(**(filt or {})), (C.c_uint64 * 16)()
+        self.check(self.L.bnd_bam_split_exogenous(_b(bam), C.byref(f), _b(exogenous_prefix), _b(out_prefix), _b(command_line), device, cnt))
+        return self._bam_counters(cnt)
 
     def cli_main(self, argv: list) -> int:
         arr = (C.c_char_p * len(argv))(*[_b(a) for a in argv])

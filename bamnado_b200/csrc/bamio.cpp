@@ -130,6 +130,7 @@ bool parse_bam_header(const uint8_t *d, uint64_t n, BamHeader &out, uint64_t &co
   const uint32_t n_ref = rd32(d + p);
   p += 4;
   BamHeader h;
+  h.text.assign((const char *)d + 8, l_text);
   h.names.reserve(n_ref);
   h.lens.reserve(n_ref);
   for (uint32_t i = 0; i < n_ref; i++) {

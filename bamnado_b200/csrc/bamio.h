@@ -25,6 +25,7 @@ struct BamHeader {
   std::vector<uint64_t> lens;
   std::unordered_map<std::string, int> name_to_id;  // last occurrence wins, like a HashMap insert
   uint64_t first_record_voff = 0;                   // virtual offset of the first alignment record
+  std::string text;                                 // SAM header text (the BAM writers copy it and append their @PG line)
 };
 
 struct BaiChunk {

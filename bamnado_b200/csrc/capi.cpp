@@ -254,6 +254,28 @@ int bnd_bigwig_from_intervals(const char *const *chrom_names, const uint32_t *ch
                               const uint32_t *end, const float *value, uint64_t n, const char *out_path) {
   return guarded([&] { bnd::bigwig_from_intervals(chrom_names, chrom_lens, n_chrom, chrom_idx, start, end, value, n, out_path, -1); });
 }
+int bnd_bam_split(const char *bam_path, const bnd_filter_cfg *filter, const char *out_path, const char *command_line, int32_t device, uint64_t *counters) {
+  return guarded([&] {
+    if (!out_path) bnd::fail("missing output path", bnd::ERR_INVALID);
+    bnd::bam_write_tool(bam_path, filter, bnd::BAMW_SPLIT, 0, nullptr, {out_path}, command_line, device, counters, nullptr);
+  });
+}
+int bnd_bam_modify(const char *bam_path, const bnd_filter_cfg *filter, int32_t tn5_shift, const char *out_path, const char *command_line, int32_t device,
+                   uint64_t *counters) {
+  return guarded([&] {
+    if (!out_path) bnd::fail("missing output path", bnd::ERR_INVALID);
+    bnd::bam_write_tool(bam_path, filter, bnd::BAMW_MODIFY, tn5_shift ? 1 : 0, nullptr, {out_path}, command_line, device, counters, nullptr);
+  });
+}
+int bnd_bam_split_exogenous(const char *bam_path, const bnd_filter_cfg *filter, const char *exogenous_prefix, const char *out_prefix, const char *command_line,
+                            int32_t device, uint64_t *counters) {
+  return guarded([&] {
+    if (!out_prefix || !exogenous_prefix) bnd::fail("missing output prefix or exogenous prefix", bnd::ERR_INVALID);
+    std::vector<std::string> paths;
+    for (const char *ext : {"endogenous.bam", "exogenous.bam", "both.bam", "unmapped.bam"}) paths.push_back(bnd::path_with_extension(out_prefix, ext));
+    bnd::bam_write_tool(bam_path, filter, bnd::BAMW_SPLIT_EXOGENOUS, 0, exogenous_prefix, paths, command_line, device, counters, nullptr);
+  });
+}
 int bnd_collapse_bedgraph(const char *in_path, const char *out_path) {
   return guarded([&] { bnd::collapse_bedgraph_file(in_path, out_path); });
 }
@@ -314,6 +336,19 @@ int bnd_bgzf_inflate(const uint8_t *bgzf, uint64_t n_bytes, uint8_t *out, uint64
     if (!st.empty()) memcpy(status, st.data(), st.size() * sizeof(int32_t));
     *out_len = o.size();
     *n_blocks = st.size();
+  });
+}
+
+int bnd_bgzf_compress(const uint8_t *data, uint64_t n_bytes, uint8_t **out, uint64_t *out_len) {
+  return guarded([&] {
+    if (!out || !out_len || (n_bytes && !data)) bnd::fail("missing argument", bnd::ERR_INVALID);
+    std::vector<uint8_t> o;
+    bnd::device_bgzf_compress(data, n_bytes, o, -1);
+    uint8_t *p = (uint8_t *)malloc(o.size() ? o.size() : 1);
+    if (!p) bnd::fail("out of memory");
+    memcpy(p, o.data(), o.size());
+    *out = p;
+    *out_len = o.size();
   });
 }
 

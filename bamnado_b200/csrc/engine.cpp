@@ -442,8 +442,11 @@ struct Unmapper {
 }  // namespace
 
 // ---- Pileup::Impl: device state of one pileup ------------------------------------------------------------------------
+struct BamWriteJob;  // bam_write.inl: attached to a pass by Pileup::write_bam
+
 struct Pileup::Impl {
   DeviceCtx *ctx = nullptr;
+  BamWriteJob *wjob = nullptr;
   int fd = -1;
   const uint8_t *map = nullptr;      // read-only mapping of the BAM (the readers copy out of the page cache through it)
   uint64_t map_len = 0;
@@ -827,6 +830,9 @@ void Pileup::reset_accumulators(const Range &r) {
 }
 
 // ---- the hot path: segments of compressed bytes -> inflate -> record index -> filter/scatter ----------------------------
+#define BND_BAMNADO_VERSION "0.9.0"  // CARGO_PKG_VERSION of the reference crate this path stands in for (bamnado/Cargo.toml:3)
+#include "bam_write.inl"
+
 void Pileup::run_pass(const Range &range, bool resident) {
   Impl &im = *im_;
   DeviceCtx &ctx = *im.ctx;
@@ -920,6 +926,7 @@ void Pileup::run_pass(const Range &range, bool resident) {
       const uint64_t ulen = tab->uoff.back();
       const uint64_t data_end = ctx.carry_cap + ulen;
       const uint32_t n_tiles = (uint32_t)((data_end + REC_TILE - 1) / REC_TILE);
+      if (im.wjob) im.wjob->before_segment(ulen + ctx.carry_cap);  // room in every output stream, else compress + write first
       // the segment that followed this set's previous use must have taken its carry before the buffers are reused
       if (S.carry_pending) {
         CU(cudaStreamWaitEvent(S.stream, S.ev_carry, 0));
@@ -1016,7 +1023,8 @@ void Pileup::run_pass(const Range &range, bool resident) {
       pa.p = im.pdev;
       pa.g = im.gdev;
       pa.use_window = use_window;
-      if (!dbg_k1_only) CU(launch_pileup(pa, ctx.sm_count, st));
+      if (im.wjob) im.wjob->segment(S, (int)(i % ctx.n_sets), ulen + ctx.carry_cap);
+      else if (!dbg_k1_only) CU(launch_pileup(pa, ctx.sm_count, st));
       CU(cudaEventRecord(E.e[4], st));
       shape_.comp_bytes += clen;
       shape_.inflated_bytes += ulen;
@@ -2892,6 +2900,106 @@ void Pileup::write_bedgraph_pieces(const std::string &path, const uint64_t *byte
   write_pieces(*job, fd, path, total, std::min(preallocated, total), false, nullptr, 0, true);
   tm_.text_ms = now_ms() - t0;
   if (env_u64("BND_DEBUG_TIMING", 0)) fprintf(stderr, "[bnd] write_bedgraph_pieces: reap + place + open + size %.2f ms, pieces %.2f ms\n", t_open - t0, now_ms() - t_open);
+}
+
+// K-deflate exposed on its own (bnd_bgzf_compress): bytes in host memory -> BGZF blocks + EOF marker, compressed on the device
+void device_bgzf_compress(const uint8_t *data, uint64_t n, std::vector<uint8_t> &out, int device) {
+  DeviceCtx &ctx = ctx_for(device);
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  cudaStream_t st = ctx.sets[0].stream;
+  BamWriteJob job;
+  job.ctx = &ctx;
+  job.store_only = env_u64("BND_BAM_STORE_ONLY", 0) != 0;
+  ClassStream s;
+  s.mem = &out;
+  out.clear();
+  DevBuf d;
+  try {
+    if (n) {
+      d.ensure(n + 64);
+      upload_bytes(ctx, data, n, d.as<uint8_t>(), st);
+      job.compress_and_write(s, d.as<uint8_t>(), n, nullptr, st);
+    }
+  } catch (...) {
+    d.release();
+    throw;
+  }
+  d.release();
+  out.insert(out.end(), BGZF_EOF, BGZF_EOF + sizeof BGZF_EOF);
+}
+
+// ---- split / modify / split-exogenous ----------------------------------------------------------------------------------------
+void Pileup::write_bam(int mode, int tn5_shift, const std::string &exogenous_prefix, const std::vector<std::string> &paths, const std::string &command_line,
+                       uint64_t *counters, uint64_t *file_bytes) {
+  Impl &im = *im_;
+  DeviceCtx &ctx = *im.ctx;
+  if (cfg_.shard_world > 1) fail("BAM writers run unsharded", ERR_INVALID);
+  if (mode != BAMW_SPLIT && mode != BAMW_MODIFY && mode != BAMW_SPLIT_EXOGENOUS) fail("unknown BAM writer mode", ERR_INVALID);
+  const double t0 = now_ms();
+  BamWriteJob job;
+  {
+    std::lock_guard<std::mutex> lock(ctx.mu);
+    CU(cudaSetDevice(ctx.device));
+    job.begin(ctx, hdr_, im.fdev, nullptr, mode, tn5_shift, exogenous_prefix, paths, command_line);
+  }
+  im.wjob = &job;
+  try {
+    run_pass(shard_, false);
+  } catch (...) {
+    im.wjob = nullptr;
+    accumulated_ = false;
+    throw;
+  }
+  im.wjob = nullptr;
+  accumulated_ = false;  // the pass fed the writers, not the bins
+  unsigned long long cnt[BW_N_COUNTERS];
+  {
+    std::lock_guard<std::mutex> lock(ctx.mu);
+    CU(cudaSetDevice(ctx.device));
+    CU(cudaMemcpy(cnt, job.d_counts.p, sizeof cnt, cudaMemcpyDeviceToHost));
+    if (cnt[BW_N_ERRORS]) {
+      // the reference propagates these with `?` and stops (read_filter.rs: missing reference id / malformed aux data;
+      // bam_modifier.rs:186 "Missing mate alignment start")
+      for (auto &c : job.cls)
+        if (c.fd >= 0) close(c.fd), c.fd = -1;
+      fail(std::to_string(cnt[BW_N_ERRORS]) + " record(s) made the read filter or the Tn5 shift fail (no reference id, malformed aux data or no mate start)");
+    }
+    job.flush(true);
+  }
+  for (int k = 0; k < BW_N_COUNTERS; k++)
+    if (counters) counters[k] = cnt[k];
+  for (int k = 0; k < BAMW_MAX_CLASSES; k++)
+    if (file_bytes) file_bytes[k] = job.cls[k].file_off;
+  if (env_u64("BND_DEBUG_TIMING", 0)) {
+    uint64_t raw = 0, out = 0, blocks = 0;
+    for (auto &c : job.cls) raw += c.raw_bytes, out += c.file_off, blocks += c.blocks;
+    fprintf(stderr, "[bnd] write_bam (mode %d): %.2f ms; %llu records kept of %llu, %llu raw bytes -> %llu bytes in %llu BGZF blocks; %llu flushes, compress %.2f ms, D2H + write %.2f ms\n",
+            mode, now_ms() - t0, (unsigned long long)(cnt[BW_N_WRITTEN] + cnt[BW_N_ENDOGENOUS] + cnt[BW_N_EXOGENOUS] + cnt[BW_N_UNMAPPED] + cnt[BW_N_QCFAIL] + cnt[BW_N_DUPLICATE] + cnt[BW_N_SECONDARY]),
+            cnt[BW_N_TOTAL], (unsigned long long)raw, (unsigned long long)out, (unsigned long long)blocks, (unsigned long long)job.flushes, job.compress_ms, job.write_ms);
+  }
+}
+
+std::string path_with_extension(const std::string &prefix, const std::string &ext) {
+  const size_t slash = prefix.find_last_of('/');
+  const size_t name0 = slash == std::string::npos ? 0 : slash + 1;
+  const size_t dot = prefix.find_last_of('.');
+  std::string stem = prefix;
+  if (dot != std::string::npos && dot > name0) stem = prefix.substr(0, dot);  // a leading dot is part of the name
+  return stem + "." + ext;
+}
+
+void bam_write_tool(const char *bam_path, const bnd_filter_cfg *filter, int mode, int tn5_shift, const char *exogenous_prefix,
+                    const std::vector<std::string> &paths, const char *command_line, int device, uint64_t *counters, uint64_t *file_bytes) {
+  if (!bam_path) fail("missing BAM path", ERR_INVALID);
+  bnd_pileup_cfg cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.bam_path = bam_path;
+  cfg.bin_size = 1000;  // the bins are not used; a coarse grid keeps the idle accumulators small
+  cfg.scale_factor = 1.0f;
+  cfg.collapse = 1;
+  cfg.device = device;
+  Pileup p(&cfg, filter);
+  p.write_bam(mode, tn5_shift, exogenous_prefix ? exogenous_prefix : "", paths, command_line ? command_line : "", counters, file_bytes);
 }
 
 #include "bigwig_tools.inl"

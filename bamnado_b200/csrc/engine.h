@@ -88,6 +88,11 @@ class Pileup {
     std::vector<uint64_t> library_sizes;    // reads kept by each sample's filter (per read and chunk, like the pile-up)
   };
   static void count_bins(const bnd_pileup_cfg *cfgs, const bnd_filter_cfg *filters, int n_samples, BinCounts &out);
+  // split / modify / split-exogenous (bam_splitter.rs:54-120, bam_modifier.rs:55-230, spike_in_analysis.rs:233-400): one pass over
+  // the file, kept records gathered per output on the device, BGZF-compressed there and written.  mode = BAMW_*; paths: one
+  // output (split, modify) or four (endogenous, exogenous, both, unmapped).  counters[BW_N_COUNTERS], file_bytes[4].
+  void write_bam(int mode, int tn5_shift, const std::string &exogenous_prefix, const std::vector<std::string> &paths, const std::string &command_line,
+                 uint64_t *counters, uint64_t *file_bytes);
 
  private:
   struct Range {  // what part of the file / genome a pass covers
@@ -133,6 +138,9 @@ class Pileup {
 // K1 exposed on its own (bnd_bgzf_inflate): inflate BGZF blocks held in host memory on the device.
 void device_inflate(const uint8_t *bgzf, uint64_t n_bytes, std::vector<uint8_t> &out, std::vector<int32_t> &status, int device);
 
+// the BGZF compressor of the BAM writers on its own (bnd_bgzf_compress)
+void device_bgzf_compress(const uint8_t *data, uint64_t n, std::vector<uint8_t> &out, int device);
+
 int device_count();
 
 // collapse-bedgraph (src/cli.rs:1149-1205 + bedgraph_utils.rs:5-45): the raw bytes of the bedGraph are parsed and collapsed on
@@ -150,6 +158,12 @@ void bigwig_compare(const char *bw1, const char *bw2, const char *out, int compa
                     const double *scale2, int device);
 void bigwig_aggregate(const char *const *paths, int n, const char *out, int mode, uint32_t bin_size, const double *pseudocount, const double *scale_factors,
                       int device);
+
+// the three BAM-writing tools behind one call (a Pileup is opened on `bam_path` for the pass)
+void bam_write_tool(const char *bam_path, const bnd_filter_cfg *filter, int mode, int tn5_shift, const char *exogenous_prefix,
+                    const std::vector<std::string> &paths, const char *command_line, int device, uint64_t *counters, uint64_t *file_bytes);
+// Path::with_extension as BamSplitter::new uses it (spike_in_analysis.rs:171-174): "<prefix minus its extension>.<ext>"
+std::string path_with_extension(const std::string &prefix, const std::string &ext);
 
 void bigwig_from_intervals(const char *const *chrom_names, const uint32_t *chrom_lens, uint32_t n_chrom, const uint32_t *chrom_idx, const uint32_t *start,
                            const uint32_t *end, const float *value, uint64_t n, const char *out_path, int device);

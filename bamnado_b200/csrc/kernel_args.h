@@ -461,4 +461,45 @@ struct BwtArgs {
   uint64_t *chrom_item_first;  // [n_chrom]
 };
 
+// ---- BAM writers: split / split-exogenous / modify (bam_write.cuh) -------------------------------------------------------------
+constexpr uint32_t BGZF_RAW = 0xff00;    // payload bytes per BGZF block (htslib's block size)
+constexpr uint32_t BGZF_SLOT = 65536;    // bytes reserved per compressed block (a BGZF block holds at most 64 KiB)
+constexpr int BAMW_MAX_CLASSES = 4;
+constexpr int BAMW_TILE = 256;           // records per tile of the class scans
+enum : int { BAMW_SPLIT = 0, BAMW_MODIFY = 1, BAMW_SPLIT_EXOGENOUS = 2 };
+// counters of a writer job (SplitStats of spike_in_analysis.rs:28-58 come first, in its order)
+enum : int {
+  BW_N_TOTAL = 0, BW_N_UNMAPPED, BW_N_QCFAIL, BW_N_DUPLICATE, BW_N_SECONDARY, BW_N_FILTERED, BW_N_LOW_MAPQ, BW_N_BOTH, BW_N_EXOGENOUS, BW_N_ENDOGENOUS,
+  BW_N_WRITTEN, BW_N_DROPPED_BY_SHIFT, BW_N_ERRORS, BW_N_COUNTERS = 16
+};
+
+struct BamwArgs {
+  const uint8_t *buf;         // segment buffer (records of the segment through rec_off)
+  const uint64_t *rec_off;
+  const SegState *st;
+  FilterDev f;
+  int32_t mode, tn5_shift, n_classes;
+  int32_t n_ref;
+  const uint64_t *ref_len;    // [n_ref]
+  const uint8_t *ref_is_exo;  // [n_ref] split-exogenous: reference name starts with the exogenous prefix
+  uint8_t *rec_cls;           // [records] class of every record of the segment (0xff = not written)
+  uint64_t *tile_sum;         // [tiles][BAMW_MAX_CLASSES] bytes of every class per tile -> exclusive stream offsets after the scan
+  uint64_t *class_len;        // [BAMW_MAX_CLASSES] bytes appended to every class stream so far (chained from segment to segment)
+  unsigned long long *counts; // [BW_N_COUNTERS]
+  uint8_t *stream[BAMW_MAX_CLASSES];      // class streams
+  uint32_t *first_rec[BAMW_MAX_CLASSES];  // per BGZF_RAW block of a stream: offset of the first record starting in it
+};
+
+struct BamwDeflateArgs {
+  const uint8_t *raw;         // stream to cut into blocks of BGZF_RAW bytes (16-byte aligned)
+  uint64_t raw_len;
+  uint32_t n_blocks;          // ceil(raw_len / BGZF_RAW)
+  const uint32_t *first_rec;  // [n_blocks] or nullptr (no record structure: header text)
+  uint8_t *out;               // [n_blocks][BGZF_SLOT]
+  uint32_t *out_size;         // [n_blocks]
+  uint32_t *tokens;           // scratch [gridDim.x][BGZF_RAW]
+  const CrcTables *crc;
+  int32_t store_only;         // 1 = stored blocks (no compression)
+};
+
 }  // namespace bnd

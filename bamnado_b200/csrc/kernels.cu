@@ -11,6 +11,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #endif
 
+#include "bam_write.cuh"
 #include "bedgraph_parse.cuh"
 #include "bigwig.cuh"
 #include "bigwig_tools.cuh"
@@ -373,6 +374,31 @@ cudaError_t launch_bwt_heads(const BwtArgs &a, int sm_count, cudaStream_t s) {
 cudaError_t launch_bwt_emit(const BwtArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_tiles == 0) return cudaSuccess;
   BND_LAUNCH(bwt_emit_kernel, dim3(grid_for(a.n_tiles, 1, (uint64_t)sm_count * 8)), dim3(COL_THREADS), 0, s, a);
+  return launched();
+}
+
+// ---- BAM writers (bam_write.cuh) ---------------------------------------------------------------------------------------------
+cudaError_t launch_bamw_segment(const BamwArgs &a, int sm_count, cudaStream_t s) {
+  BND_LAUNCH(bamw_classify_kernel, dim3((unsigned)sm_count * 8), dim3(BAMW_TILE), 0, s, a);
+  if (cudaError_t e = launched()) return e;
+  BND_LAUNCH(bamw_scan_kernel, dim3(1), dim3(BAMW_THREADS), 0, s, a);
+  return launched();
+}
+cudaError_t launch_bamw_gather(const BamwArgs &a, int sm_count, cudaStream_t s) {
+  BND_LAUNCH(bamw_gather_kernel, dim3((unsigned)sm_count * 8), dim3(BAMW_TILE), 0, s, a);
+  return launched();
+}
+unsigned bamw_deflate_grid(uint32_t n_blocks, int sm_count) { return grid_for(n_blocks, 1, (uint64_t)sm_count * 2); }
+cudaError_t launch_bamw_deflate(const BamwDeflateArgs &a, int sm_count, cudaStream_t s) {
+  if (a.n_blocks == 0) return cudaSuccess;
+  const size_t smem = BGZF_RAW + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(bamw_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  BND_LAUNCH(bamw_deflate_kernel, dim3(bamw_deflate_grid(a.n_blocks, sm_count)), dim3(BAMW_THREADS), smem, s, a);
   return launched();
 }
 

@@ -77,4 +77,10 @@ cudaError_t launch_bwt_median_fill(const BwtArgs &a, int sm_count, cudaStream_t 
 cudaError_t launch_bwt_heads(const BwtArgs &a, int sm_count, cudaStream_t s);
 cudaError_t launch_bwt_emit(const BwtArgs &a, int sm_count, cudaStream_t s);
 
+// BAM writers (bam_write.cuh): classify + scan of one segment; gather into the class streams; BGZF compression of a stream
+cudaError_t launch_bamw_segment(const BamwArgs &a, int sm_count, cudaStream_t s);
+cudaError_t launch_bamw_gather(const BamwArgs &a, int sm_count, cudaStream_t s);
+unsigned bamw_deflate_grid(uint32_t n_blocks, int sm_count);  // CTAs the next call launches (token scratch is per CTA)
+cudaError_t launch_bamw_deflate(const BamwDeflateArgs &a, int sm_count, cudaStream_t s);
+
 }  // namespace bnd

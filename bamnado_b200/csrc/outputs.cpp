@@ -160,6 +160,9 @@ const char *TOP_HELP =
     "Commands (B200 coverage path):\n"
     "  bam-coverage        Generate a coverage track from one BAM file [aliases: coverage]\n"
     "  multi-bam-coverage  Merge coverage from multiple BAM files into one track [aliases: multi-coverage]\n"
+    "  split               Split a BAM file using the supplied filters\n"
+    "  split-exogenous     Split a BAM file into endogenous and exogenous reads [aliases: split-spikein]\n"
+    "  modify              Filter and/or adjust reads in a BAM file\n"
     "  bigwig-compare      Compare two BigWig files bin by bin [aliases: compare-bigwigs]\n"
     "  bigwig-aggregate    Aggregate multiple BigWig files into one track [aliases: aggregate-bigwigs]\n"
     "  collapse-bedgraph   Collapse adjacent bins with equal scores in a bedGraph file [aliases: collapse]\n\n"
@@ -548,6 +551,89 @@ int run(const std::vector<std::string> &argv) {
       else usage_error("unexpected argument '" + a + "' found");
     }
     collapse_bedgraph_file(has_in ? in.c_str() : nullptr, has_out ? out.c_str() : nullptr);
+    return 0;
+  }
+  if (cmd == "split" || cmd == "modify" || cmd == "split-exogenous" || cmd == "split-spikein") {
+    // src/cli.rs:343-395 (flags) and :962-1079 (dispatch): --input / --output plus the read filters; the pass and the BAM writer
+    // run on the device (engine: Pileup::write_bam)
+    const bool exo = cmd == "split-exogenous" || cmd == "split-spikein", modify = cmd == "modify";
+    std::vector<std::string> pass;
+    std::string input, prefix, stats;
+    bool has_input = false, has_prefix = false, has_stats = false, tn5 = false;
+    for (size_t k = 0; k < rest.size(); k++) {
+      std::string a = rest[k], inl;
+      bool has_inl = false;
+      if (a.rfind("--", 0) == 0 && a.find('=') != std::string::npos) inl = a.substr(a.find('=') + 1), a = a.substr(0, a.find('=')), has_inl = true;
+      else if (a.size() > 2 && a[0] == '-' && a[1] != '-') inl = a.substr(a[2] == '=' ? 3 : 2), a = a.substr(0, 2), has_inl = true;
+      auto val = [&]() -> std::string {
+        if (has_inl) return inl;
+        if (k + 1 >= rest.size()) usage_error("a value is required for '" + a + "' but none was supplied");
+        return rest[++k];
+      };
+      if (a == "-i" || a == "--input") input = val(), has_input = true;
+      else if (exo && (a == "-e" || a == "--exogenous-prefix")) prefix = val(), has_prefix = true;
+      else if (exo && (a == "-s" || a == "--stats")) stats = val(), has_stats = true;
+      else if (modify && a == "--tn5-shift") tn5 = true;
+      else pass.push_back(rest[k]);
+    }
+    Opts o;
+    bool help = false;
+    parse_coverage_args(pass, false, o, help);
+    if (help) {
+      printf("%s\n\nUsage: bamnado %s [OPTIONS] --input <BAM> --output <PREFIX>%s\n\nOptions:\n  -i, --input <BAM>                   Input BAM file\n"
+             "  -o, --output <PREFIX>               Output prefix\n%s%s\nRead Filters: the same flags as bam-coverage (--strand, --proper-pairs, --min-mapq, --min-length, --max-length,\n"
+             "  --blacklist, --barcode-allowlist, --read-group, --tag, --tag-value, --min-fragment-len, --max-fragment-len,\n  --ignore-duplicates, --ignore-secondary, --ignore-supplementary)\n",
+             exo ? "Split a BAM file into endogenous and exogenous reads" : modify ? "Filter and/or adjust reads in a BAM file" : "Split a BAM file using the supplied filters",
+             cmd.c_str(), exo ? " --exogenous-prefix <PREFIX>" : "",
+             exo ? "  -e, --exogenous-prefix <PREFIX>     Reference-name prefix used to identify exogenous sequences\n  -s, --stats <FILE>                  Optional path for summary statistics output\n" : "",
+             modify ? "      --tn5-shift                     Apply the standard Tn5 offset\n" : "");
+      return 0;
+    }
+    if (o.has_bin || !o.bams.empty()) usage_error("unexpected argument found");
+    std::string missing;
+    if (!has_input) missing += "\n  --input <BAM>";
+    if (!o.has_output) missing += "\n  --output <PREFIX>";
+    if (exo && !has_prefix) missing += "\n  --exogenous-prefix <PREFIX>";
+    if (!missing.empty()) usage_error("the following required arguments were not provided:" + missing);
+    validate_bam_file(input);
+    bnd_pileup_cfg pc;
+    bnd_filter_cfg fc;
+    fill_cfgs(o, input, true, true, -1, pc, fc);
+    std::string cl;  // bamnado_command_line (bam_utils.rs:782-788): the process arguments joined by spaces
+    for (size_t k = 0; k < argv.size(); k++) cl += (k ? " " : "") + argv[k];
+    uint64_t cnt[BW_N_COUNTERS] = {0};
+    if (exo) {
+      std::vector<std::string> paths;
+      for (const char *ext : {"endogenous.bam", "exogenous.bam", "both.bam", "unmapped.bam"}) paths.push_back(path_with_extension(o.output, ext));
+      bam_write_tool(input.c_str(), &fc, BAMW_SPLIT_EXOGENOUS, 0, prefix.c_str(), paths, cl.c_str(), -1, cnt, nullptr);
+      fprintf(stderr, "Successfully split BAM file\n");
+      if (has_stats) {  // serde_json of SplitStats (spike_in_analysis.rs:101-125); non-finite floats are null
+        const size_t slash = input.find_last_of('/');
+        const std::string fname = slash == std::string::npos ? input : input.substr(slash + 1);
+        auto f64 = [](double v) { return std::isfinite(v) ? format_f64(v) : std::string("null"); };
+        double factor = 1.0 / ((double)cnt[BW_N_EXOGENOUS] / 1e6);
+        if (std::isinf(factor)) factor = 1.0;
+        const double pct = (double)cnt[BW_N_EXOGENOUS] / (double)cnt[BW_N_ENDOGENOUS] * 100.0;
+        std::string js = "{\"filename\":\"";
+        for (char c : fname) {
+          if (c == '"' || c == '\\') js += '\\';
+          js += c;
+        }
+        js += "\"";
+        const char *keys[10] = {"n_total_reads", "n_unmapped_reads", "n_qcfail_reads", "n_duplicate_reads", "n_secondary_reads", "n_filtered_reads", "n_low_maq",
+                                "n_both_genomes", "n_exogenous", "n_endogenous"};
+        for (int k = 0; k < 10; k++) js += std::string(",\"") + keys[k] + "\":" + std::to_string(cnt[k]);
+        js += ",\"spike_in_factor\":" + f64(factor) + ",\"spike_in_percentage\":" + f64(pct) + "}";
+        std::ofstream f(stats, std::ios::binary);
+        if (!f) fail("Failed to create stats file");
+        f << js;
+        if (!f.flush()) fail("Failed to write stats file");
+        fprintf(stderr, "Successfully wrote stats file to %s\n", stats.c_str());
+      }
+    } else {
+      bam_write_tool(input.c_str(), &fc, modify ? BAMW_MODIFY : BAMW_SPLIT, tn5 ? 1 : 0, nullptr, {o.output}, cl.c_str(), -1, cnt, nullptr);
+      fprintf(stderr, modify ? "Successfully modified BAM file\n" : "Successfully split BAM file\n");
+    }
     return 0;
   }
   if (cmd == "bigwig-compare" || cmd == "compare-bigwigs" || cmd == "bigwig-aggregate" || cmd == "aggregate-bigwigs") {

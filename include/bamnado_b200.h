@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define BND_ABI_VERSION 3
+#define BND_ABI_VERSION 4
 
 /* error classes */
 enum { BND_OK = 0, BND_ERR_RUNTIME = 1, BND_ERR_NOT_FOUND = 2, BND_ERR_INVALID = 3 };
@@ -216,6 +216,28 @@ int bnd_bigwig_aggregate(const char *const *bw_paths, int32_t n, const char *out
 int bnd_bigwig_from_intervals(const char *const *chrom_names, const uint32_t *chrom_lens, uint32_t n_chrom, const uint32_t *chrom_idx, const uint32_t *start,
                               const uint32_t *end, const float *value, uint64_t n, const char *out_path);
 
+/* ---- split / modify / split-exogenous (the BAM-writing consumers of the read filter) -----------------------
+ * One pass over the BAM: records inflated and indexed by the coverage kernels, BamReadFilter::is_valid on the device, the kept
+ * records gathered per output file, BGZF-compressed on the device (dynamic-Huffman DEFLATE, record-parallel LZ77) and written.
+ * The output header is the input's plus the reference's `@PG ID:bamnado PN:bamnado VN:<version> CL:<command_line>` record
+ * (bam_utils.rs:757-780).  The input needs its .bai.  `counters` (may be NULL) receives BND_BW_N_COUNTERS values.
+ *   bnd_bam_split            BamFilterer::split_async (bam_splitter.rs:54-120): every placed record the per-contig queries return
+ *                            and the filter accepts, contigs in header order (the reference walks a HashMap: any order)
+ *   bnd_bam_modify           BamModifier::run (bam_modifier.rs:55-230): the same, and with tn5_shift every properly paired record is
+ *                            rewritten (+4 / -5 shift, tlen, mate start, bin), the others are dropped like the reference drops them
+ *   bnd_bam_split_exogenous  BamSplitter::split (spike_in_analysis.rs:233-400): <prefix>.endogenous.bam, .exogenous.bam (reference
+ *                            name starts with exogenous_prefix), .both.bam (always empty), .unmapped.bam (unmapped, QC-fail,
+ *                            duplicate, secondary); counters[0..10) are SplitStats in its field order */
+enum {
+  BND_BW_N_TOTAL = 0, BND_BW_N_UNMAPPED, BND_BW_N_QCFAIL, BND_BW_N_DUPLICATE, BND_BW_N_SECONDARY, BND_BW_N_FILTERED, BND_BW_N_LOW_MAPQ,
+  BND_BW_N_BOTH, BND_BW_N_EXOGENOUS, BND_BW_N_ENDOGENOUS, BND_BW_N_WRITTEN, BND_BW_N_DROPPED_BY_SHIFT, BND_BW_N_ERRORS, BND_BW_N_COUNTERS = 16
+};
+int bnd_bam_split(const char *bam_path, const bnd_filter_cfg *filter, const char *out_path, const char *command_line, int32_t device, uint64_t *counters);
+int bnd_bam_modify(const char *bam_path, const bnd_filter_cfg *filter, int32_t tn5_shift, const char *out_path, const char *command_line, int32_t device,
+                   uint64_t *counters);
+int bnd_bam_split_exogenous(const char *bam_path, const bnd_filter_cfg *filter, const char *exogenous_prefix, const char *out_prefix, const char *command_line,
+                            int32_t device, uint64_t *counters);
+
 /* ---- NormalizationMethod::scale_factor (signal_normalization.rs:50-74) ------------------------------------ */
 double bnd_scale_factor(int32_t method, float base_scale, uint64_t bin_size, uint64_t n_reads);
 
@@ -234,6 +256,10 @@ int bnd_cli_main(int argc, const char *const *argv);
  * (capacity out_cap) and per-block status (0 ok) into `status`.  CRC32 and ISIZE are verified on the device. */
 int bnd_bgzf_inflate(const uint8_t *bgzf, uint64_t n_bytes, uint8_t *out, uint64_t out_cap, uint64_t *out_len,
                      int32_t *status, uint64_t status_cap, uint64_t *n_blocks);
+
+/* The BGZF compressor of the BAM writers on its own: `data` cut into 65 280-byte blocks, each a gzip member with a dynamic-Huffman
+ * DEFLATE stream built on the device, followed by the EOF marker.  *out is released with bnd_free. */
+int bnd_bgzf_compress(const uint8_t *data, uint64_t n_bytes, uint8_t **out, uint64_t *out_len);
 
 #ifdef __cplusplus
 }

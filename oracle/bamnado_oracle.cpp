@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <sstream>
 #include <atomic>
 #include <charconv>
 #include <cmath>
@@ -1448,3 +1449,5 @@ int orc_count_records(const char *bam_path, uint64_t *n_records, uint64_t *infla
 }
 
 }  // extern "C"
+
+#include "bam_writers.inl"

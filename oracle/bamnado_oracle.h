@@ -110,6 +110,13 @@ uint64_t orc_collapse_equal_bins(int32_t *chrom, uint64_t *start, uint64_t *end,
 /* count records by a full sequential scan (bench bookkeeping) */
 int orc_count_records(const char *bam_path, uint64_t *n_records, uint64_t *inflated_bytes, uint64_t *n_blocks);
 
+/* BAM-writing tools (bam_writers.inl): split (bam_splitter.rs:54-120), modify (bam_modifier.rs:55-230), split-exogenous
+   (spike_in_analysis.rs:233-400; paths[4] = endogenous, exogenous, both, unmapped; stats[10] in the order of SplitStats) */
+int orc_bam_split(const char *bam, const orc_filter_cfg *fc, const char *out_path, const char *command_line, uint64_t *n_written);
+int orc_bam_modify(const char *bam, const orc_filter_cfg *fc, int32_t tn5_shift, const char *out_path, const char *command_line, uint64_t *n_written);
+int orc_bam_split_exogenous(const char *bam, const orc_filter_cfg *fc, const char *exogenous_prefix, const char *const *paths, const char *command_line,
+                            uint64_t stats[10]);
+
 #ifdef __cplusplus
 }
 #endif

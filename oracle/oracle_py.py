@@ -59,7 +59,7 @@ RUN_DTYPE = np.dtype([("ref_id", "<i4"), ("val", "<u4"), ("start", "<u8"), ("sto
 def build(force: bool = False) -> Path:
     """Compile the oracle with its Makefile (gcc + zlib)."""
     src = HERE / "bamnado_oracle.cpp"
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < max(src.stat().st_mtime, (HERE / "bamnado_oracle.h").stat().st_mtime):
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < max(p.stat().st_mtime for p in (src, HERE / "bamnado_oracle.h", HERE / "bam_writers.inl")):
         subprocess.run(["make", "-C", str(HERE)], check=True, capture_output=True)
     return LIB_PATH
 
@@ -319,3 +319,31 @@ def count_bins(bam_paths, bin_size, filters, use_fragment=False, ignore_scaffold
                 counts[idx, s] = runs["val"]
         libs.append(int(lib))
     return counts, grid, libs
+
+
+# ---- BAM-writing tools (bam_writers.inl) -----------------------------------------------------------------------------------
+SPLIT_STATS = ["n_total_reads", "n_unmapped_reads", "n_qcfail_reads", "n_duplicate_reads", "n_secondary_reads", "n_filtered_reads", "n_low_maq",
+               "n_both_genomes", "n_exogenous", "n_endogenous"]
+
+
+def bam_split(bam, out_path, filt=None, command_line=""):
+    n = C.c_uint64(0)
+    f = make_filter_cfg(**(filt or {}))
+    _check(lib().orc_bam_split(_b(bam), C.byref(f), _b(out_path), _b(command_line), C.byref(n)))
+    return int(n.value)
+
+
+def bam_modify(bam, out_path, filt=None, tn5_shift=False, command_line=""):
+    n = C.c_uint64(0)
+    f = make_filter_cfg(**(filt or {}))
+    _check(lib().orc_bam_modify(_b(bam), C.byref(f), int(bool(tn5_shift)), _b(out_path), _b(command_line), C.byref(n)))
+    return int(n.value)
+
+
+def bam_split_exogenous(bam, paths, exogenous_prefix, filt=None, command_line=""):
+    """paths: [endogenous, exogenous, both, unmapped] -> SplitStats counters"""
+    f = make_filter_cfg(**(filt or {}))
+    arr = (C.c_char_p * 4)(*[_b(p) for p in paths])
+    st = (C.c_uint64 * 10)()
+    _check(lib().orc_bam_split_exogenous(_b(bam), C.byref(f), _b(exogenous_prefix), arr, _b(command_line), st))
+    return {k: int(st[i]) for i, k in enumerate(SPLIT_STATS)}

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(product_lib):
     from bamnado_b200 import _native
 
     assert sorted(_native.EXPORTS) == names
-    assert lib.bnd_abi_version() == 3
+    assert lib.bnd_abi_version() == 4
 
 
 def test_library_is_sm100a_and_self_contained(product_lib):
