@@ -81,7 +81,8 @@ def build_emul(force: bool = False) -> Path:
     if not force and EMUL_LIB.exists() and EMUL_LIB.stat().st_mtime >= _newest(srcs):
         return EMUL_LIB
     EMUL_LIB.parent.mkdir(parents=True, exist_ok=True)
-    common = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-pthread", "-DBND_EMUL", "-I", str(EMUL_DIR), "-I", str(CSRC), "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function"]
+    asan = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("BND_EMUL_ASAN") else []  # debugging aid: LD_PRELOAD libasan.so
+    common = ["g++", "-O1", "-g", *asan, "-std=c++17", "-fPIC", "-pthread", "-DBND_EMUL", "-I", str(EMUL_DIR), "-I", str(CSRC), "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function"]
     objs, procs = [], []
     for src in DEVICE_SOURCES + HOST_SOURCES:
         o = EMUL_LIB.parent / (src + ".o")
@@ -94,7 +95,7 @@ def build_emul(force: bool = False) -> Path:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"emulator build failed for {src}:\n{out}")
-    r = subprocess.run(["g++", "-shared", "-pthread", "-o", str(EMUL_LIB), *objs], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-pthread", *asan, "-o", str(EMUL_LIB), *objs], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulator link failed:\n" + r.stdout + r.stderr)
     return EMUL_LIB

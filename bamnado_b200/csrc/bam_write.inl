@@ -122,6 +122,33 @@ struct BamWriteJob {
       c.file_off += n;
       return;
     }
+    // One pwrite stream fills page-cache pages at ~4 GB/s on the B200 hosts, and parallel pwrites to one file serialise on the
+    // inode lock (profiles/r1_sweeps.md).  Large pieces therefore go through a shared mapping of the file's new tail, filled by
+    // several threads with non-temporal copies; the pages are backed first unless the file system has ample room (a store into
+    // a hole of a full file system would raise SIGBUS instead of an error).
+    const unsigned nt = n >= (8u << 20) && env_u64("BND_BAM_WRITE_MMAP", 1) ? std::min<unsigned>(24u, std::max(2u, host_cores_share() * 3 / 2)) : 1u;
+    if (nt > 1 && ftruncate(c.fd, (off_t)(c.file_off + n)) == 0) {
+      bool backed = true;
+      struct statvfs vfs;
+      const bool roomy = fstatvfs(c.fd, &vfs) == 0 && (double)vfs.f_bavail * (double)vfs.f_frsize >= 2.0 * (double)n + 1e9;
+      if (!roomy && posix_fallocate(c.fd, (off_t)c.file_off, (off_t)n) != 0) backed = false;
+      const uint64_t a0 = c.file_off & ~4095ull, delta = c.file_off - a0;
+      void *m = backed ? mmap(nullptr, n + delta, PROT_READ | PROT_WRITE, MAP_SHARED, c.fd, (off_t)a0) : MAP_FAILED;
+      if (m != MAP_FAILED) {
+        uint8_t *dst = (uint8_t *)m + delta;
+        std::vector<std::thread> th;
+        auto piece = [&](unsigned k) {
+          const uint64_t a = (n * k / nt) & ~63ull, b = k + 1 == nt ? n : (n * (k + 1) / nt) & ~63ull;
+          stream_copy(dst + a, p + a, b - a);
+        };
+        for (unsigned k = 1; k < nt; k++) th.emplace_back(piece, k);
+        piece(0);
+        for (auto &t : th) t.join();
+        g_unmapper.submit((char *)m, n + delta);
+        c.file_off += n;
+        return;
+      }
+    }
     while (n) {
       ssize_t w = pwrite(c.fd, p, n, (off_t)c.file_off);
       if (w <= 0) fail("write error on " + c.path);
