@@ -289,7 +289,10 @@ struct DflShared {
   uint16_t lit_code[288], dist_code[32];
   uint8_t lit_len[288], dist_len[32];
   uint16_t unit_start[BAMW_MAX_UNITS + 1];
-  uint16_t unit_lag[BAMW_MAX_UNITS];
+  uint16_t unit_lag[BAMW_MAX_UNITS];       // distance to the previous record's start: fixed fields and read name
+  uint16_t unit_lag_mid[BAMW_MAX_UNITS];   // ... to its CIGAR start: CIGAR, sequence, qualities (from unit_mid on)
+  uint16_t unit_lag_aux[BAMW_MAX_UNITS];   // ... to its aux start: the tags (from unit_aux on)
+  uint16_t unit_mid[BAMW_MAX_UNITS], unit_aux[BAMW_MAX_UNITS];
   uint8_t rle_sym[320], rle_ext[320];
   uint16_t cl_code[19];
   uint8_t cl_len[19];
@@ -432,27 +435,42 @@ __global__ void __launch_bounds__(BAMW_THREADS) bamw_deflate_kernel(BamwDeflateA
     // ---- 2. units (thread 0 follows the record chain of the block) and the CRC-32 (warp 1) ----
     if (tid == 0) {
       uint32_t k = 0;
-      auto add = [&](uint32_t s, uint32_t e, uint32_t lag) {  // [s, e) in pieces
-        if (lag > 32768u) lag = 0;  // beyond the DEFLATE window
+      // [s, e) in pieces; lags beyond the DEFLATE window are dropped
+      auto add = [&](uint32_t s, uint32_t e, uint32_t lag, uint32_t lag_mid, uint32_t lag_aux, uint32_t mid, uint32_t aux) {
+        if (lag > 32768u) lag = 0;
+        if (lag_mid > 32768u) lag_mid = 0;
+        if (lag_aux > 32768u) lag_aux = 0;
         while (s < e && k < BAMW_MAX_UNITS - 1) {
           const uint32_t q = k == BAMW_MAX_UNITS - 2 ? e : tmin<uint32_t>(e, s + BAMW_PIECE);
-          S.unit_start[k] = (uint16_t)s, S.unit_lag[k] = (uint16_t)lag;
+          S.unit_start[k] = (uint16_t)s, S.unit_lag[k] = (uint16_t)lag, S.unit_lag_mid[k] = (uint16_t)lag_mid, S.unit_lag_aux[k] = (uint16_t)lag_aux;
+          S.unit_mid[k] = (uint16_t)mid, S.unit_aux[k] = (uint16_t)aux;
           k++;
           s = q;
         }
       };
       uint32_t first = a.first_rec ? a.first_rec[b] : BAMW_NONE;
       if (first >= n) first = n;
-      add(0, first, 0);
-      uint32_t p = first, prev = BAMW_NONE;
+      add(0, first, 0, 0, 0, n, n);
+      // Records differ in name, CIGAR and read length, so one lag does not line every field up with the previous record: the
+      // fixed fields and the name repeat at the distance of the record starts, CIGAR / sequence / qualities at the distance of
+      // the CIGAR starts, the tags at the distance of the aux starts.
+      uint32_t p = first, prev = BAMW_NONE, prev_mid = BAMW_NONE, prev_aux = BAMW_NONE;
       while (p < n) {
-        uint32_t q = n;
+        uint32_t q = n, mid = n, aux = n;
         if (p + 4 <= n) {
           const uint32_t bs = (uint32_t)raw[p] | ((uint32_t)raw[p + 1] << 8) | ((uint32_t)raw[p + 2] << 16) | ((uint32_t)raw[p + 3] << 24);
           if (bs >= 32 && bs < REC_MAX_SIZE && (uint64_t)p + 4 + bs < (uint64_t)n) q = p + 4 + bs;
+          if (bs >= 32 && p + 24 <= n) {
+            const uint32_t lrn = raw[p + 12], nc = (uint32_t)raw[p + 16] | ((uint32_t)raw[p + 17] << 8);
+            const uint32_t ls = (uint32_t)raw[p + 20] | ((uint32_t)raw[p + 21] << 8) | ((uint32_t)raw[p + 22] << 16) | ((uint32_t)raw[p + 23] << 24);
+            const uint64_t m64 = (uint64_t)p + 36 + lrn, a64 = m64 + 4ull * nc + ((uint64_t)ls + 1) / 2 + ls;
+            if (a64 <= (uint64_t)p + 4 + bs) mid = (uint32_t)tmin<uint64_t>(m64, n), aux = (uint32_t)tmin<uint64_t>(a64, n);
+          }
         }
-        add(p, q, prev == BAMW_NONE ? 0u : p - prev);
-        prev = p;
+        const bool have = prev != BAMW_NONE;
+        add(p, q, have ? p - prev : 0u, have && mid < n && prev_mid != BAMW_NONE ? mid - prev_mid : 0u,
+            have && aux < n && prev_aux != BAMW_NONE ? aux - prev_aux : 0u, mid, aux);
+        prev = p, prev_mid = mid < n ? mid : BAMW_NONE, prev_aux = aux < n ? aux : BAMW_NONE;
         p = q;
       }
       S.unit_start[k] = (uint16_t)n;
@@ -470,10 +488,12 @@ __global__ void __launch_bounds__(BAMW_THREADS) bamw_deflate_kernel(BamwDeflateA
     // ---- 3. greedy parse of every unit against its two lags; tokens to scratch; frequencies ----
     if (!S.stored) {
       for (uint32_t u = u0; u < u1; u++) {
-        const uint32_t s = S.unit_start[u], e = S.unit_start[u + 1], lag = S.unit_lag[u];
+        const uint32_t s = S.unit_start[u], e = S.unit_start[u + 1];
+        const uint32_t lag_a = S.unit_lag[u], lag_m = S.unit_lag_mid[u], lag_x = S.unit_lag_aux[u], mid = S.unit_mid[u], aux = S.unit_aux[u];
         uint32_t p = s, k = 0;
         while (p < e) {
           const uint32_t maxm = tmin<uint32_t>(258u, e - p);
+          const uint32_t lag = p < mid ? lag_a : p < aux ? lag_m : lag_x;
           uint32_t best = 0, bestd = 0;
           if (lag && p >= lag) {
             uint32_t m = 0;

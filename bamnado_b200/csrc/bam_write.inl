@@ -95,7 +95,8 @@ struct BamWriteJob {
   DevBuf rec_cls[MAX_SETS], tile_sum[MAX_SETS];
   cudaEvent_t ev_scan[MAX_SETS] = {};
   int prev_set = -1;
-  DevBuf d_slots, d_sizes, d_offsets, d_tokens, d_blob;
+  DevBuf d_slots, d_sizes, d_offsets, d_tokens, d_blob[2];
+  cudaStream_t wstream = nullptr;  // D2H of a packed batch, issued by the writer thread while the next batch is compressed
   FilterDev fdev{};
   int32_t n_ref = 0;
   double compress_ms = 0, write_ms = 0;
@@ -108,7 +109,8 @@ struct BamWriteJob {
       c.buf.release();
       c.first_rec.release();
     }
-    for (DevBuf *b : {&d_class_len, &d_counts, &d_ref_exo, &d_ref_len, &d_slots, &d_sizes, &d_offsets, &d_tokens, &d_blob}) b->release();
+    for (DevBuf *b : {&d_class_len, &d_counts, &d_ref_exo, &d_ref_len, &d_slots, &d_sizes, &d_offsets, &d_tokens, &d_blob[0], &d_blob[1]}) b->release();
+    if (wstream) cudaStreamDestroy(wstream);
     for (int i = 0; i < MAX_SETS; i++) {
       rec_cls[i].release();
       tile_sum[i].release();
@@ -156,76 +158,114 @@ struct BamWriteJob {
     }
   }
 
-  // blocks [0, n_blocks) of a device stream -> compressed, packed, written behind the file's current end
-  void compress_and_write(ClassStream &c, const uint8_t *d_raw, uint64_t raw_len, const uint32_t *d_first_rec, cudaStream_t st) {
-    const uint64_t n_blocks = (raw_len + BGZF_RAW - 1) / BGZF_RAW;
-    d_slots.ensure((size_t)BATCH * BGZF_SLOT);
-    d_blob.ensure((size_t)BATCH * BGZF_SLOT);
-    d_sizes.ensure((size_t)BATCH * 4);
-    d_offsets.ensure((size_t)BATCH * 8);
-    std::vector<uint32_t> sizes(BATCH);
-    std::vector<uint64_t> offs(BATCH);
+  // a packed batch on the device -> pinned bounce buffers -> file; runs on the writer thread with its own stream
+  void drain_blob(ClassStream &c, const uint8_t *d_src, uint64_t total, uint64_t CH) {
+    CU(cudaSetDevice(ctx->device));
     PinnedBounce &pb = ctx->bounce;
-    const uint64_t CH = std::max<uint64_t>(env_u64("BND_TEXT_CHUNK_BYTES", 64ull << 20), 1u << 20);
-    pb.ensure(CH);
-    for (uint64_t b0 = 0; b0 < n_blocks; b0 += BATCH) {
-      const uint32_t nb = (uint32_t)std::min<uint64_t>(BATCH, n_blocks - b0);
-      const double t0 = now_ms();
-      BamwDeflateArgs da{};
-      da.raw = d_raw + b0 * BGZF_RAW;
-      da.raw_len = std::min<uint64_t>(raw_len - b0 * BGZF_RAW, (uint64_t)nb * BGZF_RAW);
-      da.n_blocks = nb;
-      da.first_rec = d_first_rec ? d_first_rec + b0 : nullptr;
-      da.out = d_slots.as<uint8_t>();
-      da.out_size = d_sizes.as<uint32_t>();
-      d_tokens.ensure((size_t)bamw_deflate_grid(nb, ctx->sm_count) * BGZF_RAW * 4);
-      da.tokens = d_tokens.as<uint32_t>();
-      da.crc = ctx->d_crc;
-      da.store_only = store_only ? 1 : 0;
-      CU(launch_bamw_deflate(da, ctx->sm_count, st));
-      CU(cudaMemcpyAsync(sizes.data(), d_sizes.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      uint64_t total = 0;
-      for (uint32_t k = 0; k < nb; k++) {
-        if (sizes[k] < 28 || sizes[k] > BGZF_SLOT) fail("BGZF compression failed on the device");
-        offs[k] = total;
-        total += sizes[k];
-      }
-      CU(cudaMemcpyAsync(d_offsets.p, offs.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-      BwCompactArgs ca{};
-      ca.staging = d_slots.as<uint8_t>();
-      ca.comp_size = d_sizes.as<uint32_t>();
-      ca.offset = d_offsets.as<uint64_t>();
-      ca.n_sections = nb;
-      ca.stride = BGZF_SLOT;
-      ca.blob = d_blob.as<uint8_t>();
-      CU(launch_bw_compact(ca, ctx->sm_count, st));
-      CU(cudaStreamSynchronize(st));
-      compress_ms += now_ms() - t0;
-      const double t1 = now_ms();
-      // the packed blocks leave through the two pinned bounce buffers: the copy of chunk k overlaps the write of chunk k - 1
-      uint64_t pending_len[PinnedBounce::N] = {0, 0};
-      uint64_t k = 0;
-      for (uint64_t off = 0; off < total; off += CH, k++) {
-        const int slot = (int)(k % PinnedBounce::N);
-        const uint64_t len = std::min<uint64_t>(CH, total - off);
-        CU(cudaMemcpyAsync(pb.buf[slot], d_blob.as<uint8_t>() + off, len, cudaMemcpyDeviceToHost, st));
-        CU(cudaEventRecord(pb.ev[slot], st));
-        pending_len[slot] = len;
-        if (k > 0) {
-          const int prev = (int)((k - 1) % PinnedBounce::N);
-          CU(cudaEventSynchronize(pb.ev[prev]));
-          write_all(c, pb.buf[prev], pending_len[prev]);
-        }
-      }
+    uint64_t pending_len[PinnedBounce::N] = {0, 0};
+    uint64_t k = 0;
+    for (uint64_t off = 0; off < total; off += CH, k++) {  // the copy of chunk k overlaps the write of chunk k - 1
+      const int slot = (int)(k % PinnedBounce::N);
+      const uint64_t len = std::min<uint64_t>(CH, total - off);
+      CU(cudaMemcpyAsync(pb.buf[slot], d_src + off, len, cudaMemcpyDeviceToHost, wstream));
+      CU(cudaEventRecord(pb.ev[slot], wstream));
+      pending_len[slot] = len;
       if (k > 0) {
         const int prev = (int)((k - 1) % PinnedBounce::N);
         CU(cudaEventSynchronize(pb.ev[prev]));
         write_all(c, pb.buf[prev], pending_len[prev]);
       }
-      write_ms += now_ms() - t1;
-      c.blocks += nb;
     }
+    if (k > 0) {
+      const int prev = (int)((k - 1) % PinnedBounce::N);
+      CU(cudaEventSynchronize(pb.ev[prev]));
+      write_all(c, pb.buf[prev], pending_len[prev]);
+    }
+  }
+
+  // blocks [0, n_blocks) of a device stream -> compressed, packed, written behind the file's current end.  Batches of BATCH blocks:
+  // while batch k is copied out and written by the writer thread, batch k + 1 is compressed and packed into the other blob.
+  void compress_and_write(ClassStream &c, const uint8_t *d_raw, uint64_t raw_len, const uint32_t *d_first_rec, cudaStream_t st) {
+    const uint64_t n_blocks = (raw_len + BGZF_RAW - 1) / BGZF_RAW;
+    const uint32_t batch = (uint32_t)std::min<uint64_t>(BATCH, std::max<uint64_t>(n_blocks, 1));
+    d_slots.ensure((size_t)batch * BGZF_SLOT);
+    d_sizes.ensure((size_t)batch * 4);
+    d_offsets.ensure((size_t)batch * 8);
+    std::vector<uint32_t> sizes(batch);
+    std::vector<uint64_t> offs(batch);
+    const uint64_t CH = std::max<uint64_t>(env_u64("BND_TEXT_CHUNK_BYTES", 64ull << 20), 1u << 20);
+    ctx->bounce.ensure(CH);
+    if (!wstream) CU(cudaStreamCreateWithFlags(&wstream, cudaStreamNonBlocking));
+    std::thread writer;
+    std::exception_ptr werr;
+    double w_busy = 0;
+    auto join_writer = [&] {
+      if (writer.joinable()) writer.join();
+      if (werr) {
+        std::exception_ptr e = werr;
+        werr = nullptr;
+        std::rethrow_exception(e);
+      }
+    };
+    try {
+      uint32_t which = 0;
+      for (uint64_t b0 = 0; b0 < n_blocks; b0 += batch, which ^= 1u) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, n_blocks - b0);
+        const double t0 = now_ms();
+        BamwDeflateArgs da{};
+        da.raw = d_raw + b0 * BGZF_RAW;
+        da.raw_len = std::min<uint64_t>(raw_len - b0 * BGZF_RAW, (uint64_t)nb * BGZF_RAW);
+        da.n_blocks = nb;
+        da.first_rec = d_first_rec ? d_first_rec + b0 : nullptr;
+        da.out = d_slots.as<uint8_t>();
+        da.out_size = d_sizes.as<uint32_t>();
+        d_tokens.ensure((size_t)bamw_deflate_grid(nb, ctx->sm_count) * BGZF_RAW * 4);
+        da.tokens = d_tokens.as<uint32_t>();
+        da.crc = ctx->d_crc;
+        da.store_only = store_only ? 1 : 0;
+        CU(launch_bamw_deflate(da, ctx->sm_count, st));
+        CU(cudaMemcpyAsync(sizes.data(), d_sizes.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        uint64_t total = 0;
+        for (uint32_t k = 0; k < nb; k++) {
+          if (sizes[k] < 28 || sizes[k] > BGZF_SLOT) fail("BGZF compression failed on the device");
+          offs[k] = total;
+          total += sizes[k];
+        }
+        // the blob about to be overwritten was handed to the writer two batches ago: with one writer at a time it is free once
+        // the previous write has been joined, which also keeps the file offsets in order
+        join_writer();
+        DevBuf &blob = d_blob[which];
+        blob.ensure(total + 64);
+        CU(cudaMemcpyAsync(d_offsets.p, offs.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+        BwCompactArgs ca{};
+        ca.staging = d_slots.as<uint8_t>();
+        ca.comp_size = d_sizes.as<uint32_t>();
+        ca.offset = d_offsets.as<uint64_t>();
+        ca.n_sections = nb;
+        ca.stride = BGZF_SLOT;
+        ca.blob = blob.as<uint8_t>();
+        CU(launch_bw_compact(ca, ctx->sm_count, st));
+        CU(cudaStreamSynchronize(st));
+        compress_ms += now_ms() - t0;
+        const uint8_t *src = blob.as<uint8_t>();
+        writer = std::thread([this, &c, src, total, CH, &werr, &w_busy] {
+          const double t1 = now_ms();
+          try {
+            drain_blob(c, src, total, CH);
+          } catch (...) {
+            werr = std::current_exception();
+          }
+          w_busy += now_ms() - t1;
+        });
+        c.blocks += nb;
+      }
+      join_writer();
+    } catch (...) {
+      if (writer.joinable()) writer.join();
+      throw;
+    }
+    write_ms += w_busy;
     c.raw_bytes += raw_len;
   }
 

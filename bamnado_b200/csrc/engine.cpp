@@ -422,21 +422,38 @@ struct Pileup::TextJob {
 // when the library is unloaded, so no thread of ours outlives the code it runs.
 namespace {
 struct Unmapper {
+  struct Job {
+    std::thread th;
+    std::shared_ptr<std::atomic<bool>> done;
+  };
   std::mutex mu;
-  std::vector<std::thread> threads;
-  void reap() {
-    std::vector<std::thread> t;
+  std::vector<Job> jobs;
+  void reap() {  // waits for every teardown
+    std::vector<Job> t;
     {
       std::lock_guard<std::mutex> g(mu);
-      t.swap(threads);
+      t.swap(jobs);
     }
     for (auto &x : t)
-      if (x.joinable()) x.join();
+      if (x.th.joinable()) x.th.join();
   }
   void submit(char *map, uint64_t len) {
-    reap();  // earlier teardowns finished long ago: their threads are joined here so that none piles up
     std::lock_guard<std::mutex> g(mu);
-    threads.emplace_back([map, len] { munmap(map, len); });
+    // threads that have finished are joined here, without waiting for the others, so that none piles up between reaps
+    for (size_t i = 0; i < jobs.size();) {
+      if (jobs[i].done->load()) {
+        jobs[i].th.join();
+        jobs.erase(jobs.begin() + (long)i);
+      } else {
+        i++;
+      }
+    }
+    auto done = std::make_shared<std::atomic<bool>>(false);
+    jobs.push_back(Job{std::thread([map, len, done] {
+                         munmap(map, len);
+                         done->store(true);
+                       }),
+                       done});
   }
   ~Unmapper() { reap(); }
 } g_unmapper;
