@@ -457,6 +457,39 @@ struct Unmapper {
   }
   ~Unmapper() { reap(); }
 } g_unmapper;
+
+// The read-only mapping of the most recently used BAM is kept for the next handle on the same file (same device, inode, size):
+// setting up and tearing down an 11.5 GB mapping costs ~25 ms of the process's mmap lock per handle, which a caller that asks
+// one BAM for one chromosome after the other (get_signal_for_chromosome) or runs job after job would pay every time.  A shared
+// file mapping always shows the file's current bytes, so only a change of size or identity makes the cached mapping unusable.
+struct MapCache {
+  std::mutex mu;
+  const uint8_t *map = nullptr;
+  uint64_t len = 0;
+  dev_t dev = 0;
+  ino_t ino = 0;
+  bool in_use = false;
+  const uint8_t *take(const struct stat &st) {
+    std::lock_guard<std::mutex> g(mu);
+    if (!map || in_use || st.st_dev != dev || st.st_ino != ino || (uint64_t)st.st_size != len) return nullptr;
+    in_use = true;
+    return map;
+  }
+  // a handle is done with `m`: the cached mapping is released for the next handle, any other mapping takes the cache's place
+  void give(const uint8_t *m, uint64_t n, dev_t d, ino_t i) {
+    std::lock_guard<std::mutex> g(mu);
+    if (m == map) {
+      in_use = false;
+      return;
+    }
+    if (in_use) {
+      g_unmapper.submit((char *)const_cast<uint8_t *>(m), n);
+      return;
+    }
+    if (map) g_unmapper.submit((char *)const_cast<uint8_t *>(map), len);
+    map = m, len = n, dev = d, ino = i;
+  }
+} g_map_cache;
 }  // namespace
 
 // ---- Pileup::Impl: device state of one pileup ------------------------------------------------------------------------
@@ -468,6 +501,8 @@ struct Pileup::Impl {
   int fd = -1;
   const uint8_t *map = nullptr;      // read-only mapping of the BAM (the readers copy out of the page cache through it)
   uint64_t map_len = 0;
+  dev_t map_dev = 0;
+  ino_t map_ino = 0;
   std::vector<uint64_t> cut_points;  // sorted BGZF block starts known from the index
   // geometry + filter tables on the device
   DevBuf d_ref_len, d_first_bin, d_first_chunk;
@@ -497,8 +532,7 @@ struct Pileup::Impl {
     prealloc_stop.store(true);
     if (prealloc_thread.joinable()) prealloc_thread.join();
     const double t1 = now_ms();
-    // the mapping of the BAM is torn down behind the caller's back (20 ms for 11.5 GB of touched pages on the B200 hosts)
-    if (map) g_unmapper.submit((char *)const_cast<uint8_t *>(map), map_len);
+    if (map) g_map_cache.give(map, map_len, map_dev, map_ino);  // kept for the next handle on this file, else torn down in the background
     if (fd >= 0) close(fd);
     const double t2 = now_ms();
     text_job.reset();
@@ -710,10 +744,16 @@ void Pileup::open() {
   if (fstat(im.fd, &st) != 0) fail("cannot stat " + bam_path_);
   file_size_ = (uint64_t)st.st_size;
   if (S_ISREG(st.st_mode) && file_size_ > 0) {
-    void *m = mmap(nullptr, file_size_, PROT_READ, MAP_SHARED, im.fd, 0);
-    if (m != MAP_FAILED) {
-      im.map = (const uint8_t *)m;
+    im.map_dev = st.st_dev, im.map_ino = st.st_ino;
+    if (const uint8_t *cached = g_map_cache.take(st)) {
+      im.map = cached;
       im.map_len = file_size_;
+    } else {
+      void *m = mmap(nullptr, file_size_, PROT_READ, MAP_SHARED, im.fd, 0);
+      if (m != MAP_FAILED) {
+        im.map = (const uint8_t *)m;
+        im.map_len = file_size_;
+      }
     }
   }
   const double t_o0 = now_ms();
