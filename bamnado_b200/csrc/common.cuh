@@ -69,6 +69,7 @@ __device__ __forceinline__ saddr_t smem_addr(const void *p) { return (saddr_t)p;
 __device__ __forceinline__ uint32_t lds_u16(saddr_t a) { return *(const uint16_t *)a; }
 __device__ __forceinline__ uint32_t lds_u32(saddr_t a) { return *(const uint32_t *)a; }
 __device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v) { *(uint32_t *)a = v; }
+__device__ __forceinline__ void sts_u16(saddr_t a, uint32_t v) { *(uint16_t *)a = (uint16_t)v; }
 __device__ __forceinline__ void cp_async_u32(saddr_t dst, const void *src) { *(uint32_t *)dst = *(const uint32_t *)src; }
 __device__ __forceinline__ void cp_async_wait_all() {}
 #else
@@ -85,6 +86,7 @@ __device__ __forceinline__ uint32_t lds_u32(saddr_t a) {
   return v;
 }
 __device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(saddr_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
 // asynchronous 4-byte global -> shared copy (LDGSTS): no register staging, completion awaited with cp_async_wait_all
 __device__ __forceinline__ void cp_async_u32(saddr_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");

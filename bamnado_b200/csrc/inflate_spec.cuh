@@ -41,11 +41,14 @@ struct alignas(16) SpecSmemT {
   HuffCanon dist_canon;
   uint16_t dist_sorted[32];
   uint32_t stage[STAGE_WORDS];  // this round's compressed words
-  // the round's matches in stream order: {output position | (length - 3) << 16, distance}
-  uint2 matches[NT];
-  __device__ __forceinline__ uint16_t *codes() { return reinterpret_cast<uint16_t *>(matches); }     // 320 x u16
-  __device__ __forceinline__ uint8_t *lens() { return reinterpret_cast<uint8_t *>(matches) + 640; }  // 320 x u8
-  static_assert(NT * 8 >= 960, "match list must hold the table-building scratch");
+  // the round's matches in stream order: output position | (length - 3) << 16, and the distance (<= 32768) beside it.  Six bytes
+  // per match instead of eight: the list of a 384-bit round (448 entries) fits where 384 entries of eight bytes were
+  // (profiles/r2_sweeps.md: longer spans pay, a list shorter than ~1.17 matches per span bit does not)
+  uint32_t m_pl[NT];
+  uint16_t m_dist[NT];
+  __device__ __forceinline__ uint16_t *codes() { return reinterpret_cast<uint16_t *>(m_pl); }     // 320 x u16
+  __device__ __forceinline__ uint8_t *lens() { return reinterpret_cast<uint8_t *>(m_pl) + 640; }  // 320 x u8
+  static_assert(NT * 4 >= 960 && NT % 8 == 0, "match list must hold the table-building scratch");
 };
 
 enum : uint32_t { SPAN_OK = 0, SPAN_EOB = 1, SPAN_BAD_SYMBOL = 2, SPAN_BAD_DISTANCE = 3, SPAN_PAST_END = 4 };
@@ -197,6 +200,7 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
   wa += 12;
   int32_t remain = (int32_t)(limit - start);
   uint32_t nm = 0, bytes = 0, flag = SPAN_OK;
+  const saddr_t dadj = STORE ? smem_addr(S.m_dist) - (smem_addr(S.m_pl) >> 1) : 0;  // distance of entry i lives at (address of m_pl[i]) / 2 + dadj
 #pragma unroll 1
   do {
     const uint32_t w = __funnelshift_r(lo, hi, pos);
@@ -261,8 +265,8 @@ __device__ __noinline__ uint2 span_decode(uint32_t start, uint32_t limit, Smem &
           break;
         }
         sts_u32(ml, (opos + bytes) | ((length - 3u) << 16));
-        sts_u32(ml + 4, dist);
-        ml += 8;
+        sts_u16((ml >> 1) + dadj, dist);
+        ml += 4;
       } else {
         out[opos + bytes] = (uint8_t)sym;
       }
@@ -310,7 +314,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
   const uint32_t *base = (const uint32_t *)((uintptr_t)payload & ~(uintptr_t)3);
   uint32_t p0 = (uint32_t)((uintptr_t)payload & 3) * 8;
   const uint32_t end_bit = p0 + (uint32_t)(pend - payload) * 8;
-  const saddr_t ml0 = smem_addr(S.matches), stage0 = smem_addr(S.stage);
+  const saddr_t ml0 = smem_addr(S.m_pl), stage0 = smem_addr(S.stage);
   const uint32_t word_limit = ((end_bit + 31u) >> 5) + 2u;  // words holding payload bits, + 2 inside the block's 8-byte trailer
   // asynchronous copy of one round of input, starting at the word holding bit p: global -> shared, zeros past the payload.
   // (One cp.async.bulk per round with an mbarrier - UBLKCP / SYNCS.PHASECHK in the SASS - was built and measured in round 2:
@@ -456,7 +460,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
       // ---- store pass: literals to out[], matches to the list ----
       bool bad = false;
       if (taken && start < end_bit) {
-        const uint2 r = span_decode<true>(start - sbit0, limit - sbit0, S, T, out, outpos + binc - nbytes, ml0 + 8 * (minc - nm));
+        const uint2 r = span_decode<true>(start - sbit0, limit - sbit0, S, T, out, outpos + binc - nbytes, ml0 + 4 * (minc - nm));
         bad = (r.x & 0xffffffu) + sbit0 != exitb || r.y != cnt;  // only an invalid distance ends the store pass early
         if (bad) flag = r.x >> 24;
       }
@@ -478,7 +482,7 @@ __device__ int inflate_block_spec(const Tile<32> &tile, Smem &S, const SymTables
       // ---- resolve the matches, 32 at a time: lane t owns match mb + t ----
       for (uint32_t mb = 0; mb < nmatch; mb += 32) {
         const bool mine = mb + (uint32_t)lane < nmatch;
-        const uint2 me = mine ? S.matches[mb + lane] : make_uint2(0u, 1u);
+        const uint2 me = mine ? make_uint2(S.m_pl[mb + lane], S.m_dist[mb + lane]) : make_uint2(0u, 1u);
         const uint32_t mypos = me.x & 0xffffu, length = (me.x >> 16) + 3u, dist = me.y;
         const uint32_t src_end = mypos - dist + length;
         uint32_t pend = tile.ballot(mine);

@@ -45,7 +45,7 @@ namespace {
 struct InflateShape {
   int threads, ctas_per_sm;
 };
-const InflateShape kShapes[] = {{320, 3}, {320, 3}, {256, 4}, {32, 30}, {352, 3}, {384, 3}};
+const InflateShape kShapes[] = {{320, 3}, {320, 3}, {256, 4}, {32, 30}, {320, 3}};
 int shape_index() {
   static int v = -1;
   if (v < 0) {
@@ -96,16 +96,15 @@ cudaError_t launch_inflate(const InflateArgs &a, int sm_count, cudaStream_t s) {
     case 1: return launch_inflate_spec_t<320, 3, 9, 8, 256, 384, true>(a, sm_count, v.ctas_per_sm, s);  // round-1 shape: 256-bit spans, ten warps per CTA
     case 2: return launch_inflate_spec_t<256, 4, 9, 8, 256, 256, true>(a, sm_count, v.ctas_per_sm, s);  // short match list (tests)
     case 3: return launch_inflate_spec_t<32, 30, 9, 8, 320, 384, false>(a, sm_count, v.ctas_per_sm, s);  // 30 one-warp CTAs / SM, CRC tables through L1 (A/B: 8 % slower)
-    case 4: return launch_inflate_spec_t<352, 3, 9, 8, 320, 320, true>(a, sm_count, v.ctas_per_sm, s);  // A/B: 33 warps / SM, match list of 320
-    case 5: return launch_inflate_spec_t<384, 3, 9, 8, 320, 256, true>(a, sm_count, v.ctas_per_sm, s);  // A/B: 36 warps / SM, match list of 256 (no registers left beside K1)
-    default: return launch_inflate_spec_t<320, 3, 9, 8, 320, 384, true>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM in three CTAs, 320-bit spans
+    case 4: return launch_inflate_spec_t<320, 3, 9, 8, 320, 384, true>(a, sm_count, v.ctas_per_sm, s);  // 320-bit spans, list of 384 (shipped until the 6-byte list made room: 2.9 % slower)
+    default: return launch_inflate_spec_t<320, 3, 9, 8, 384, 448, true>(a, sm_count, v.ctas_per_sm, s);  // 30 warps / SM in three CTAs, 384-bit spans, 448 matches per round
   }
 }
 
 // zlib streams (BigWig sections): the same walk, Adler-32 instead of CRC-32, sizes reported per stream
 cudaError_t launch_inflate_zlib(const InflateArgs &a, int sm_count, cudaStream_t s) {
   if (a.n_blocks == 0) return cudaSuccess;
-  return launch_inflate_spec_t<320, 3, 9, 8, 320, 384, true, true>(a, sm_count, 3, s);
+  return launch_inflate_spec_t<320, 3, 9, 8, 384, 448, true, true>(a, sm_count, 3, s);
 }
 
 cudaError_t launch_record_index(const RecArgs &a, cudaStream_t s) {

@@ -3,6 +3,4 @@
 set -u
 mkdir -p gpurun_out
 export PAIRS=40000000
-for v in 0 4 5; do BND_INFLATE_VARIANT=$v python scripts/sweep_pipeline.py 2>&1 | tail -1; done | tee gpurun_out/r2_k1_occupancy.log
-BND_SEGMENT_BYTES=150994944 python scripts/sweep_pipeline.py 2>&1 | tail -1 | tee -a gpurun_out/r2_k1_occupancy.log
-BND_SEGMENT_BYTES=201326592 BND_INFLATE_VARIANT=0 python scripts/sweep_pipeline.py 2>&1 | tail -1 | tee -a gpurun_out/r2_k1_occupancy.log
+for v in 0 13 14 15 16; do BND_INFLATE_VARIANT=$v python scripts/sweep_pipeline.py 2>&1 | tail -1; done | tee gpurun_out/r2_k1_ab_run4.log
