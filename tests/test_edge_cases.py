@@ -220,3 +220,32 @@ def test_to_bedgraph_with_background_page_touching(backend, oracle, tmp_path, ma
         with backend.pileup(pile, filt) as h:
             h.to_bedgraph(out)
         assert out.read_bytes() == ref.read_bytes()
+
+
+def test_bam_mapping_cache_follows_the_file(backend, oracle, tmp_path, make_bam):
+    # the read-only mapping of the last BAM is kept for the next handle on the same file (engine.cpp: MapCache): a path whose
+    # file is replaced, rewritten in place or opened twice at once must still give that file's own coverage
+    import shutil
+
+    a = make_bam("cache_a", "--pairs", 3000, "--seed", 11, "--contigs", "chr1:400000,chr2:100000")
+    b = make_bam("cache_b", "--pairs", 4500, "--seed", 12, "--contigs", "chr1:400000,chr2:100000")
+    p = tmp_path / "x.bam"
+
+    def put(src, replace):
+        if replace:  # new inode
+            shutil.copy(src, str(p) + ".tmp")
+            shutil.move(str(p) + ".tmp", p)
+        else:  # same inode, rewritten and truncated in place
+            data = open(src, "rb").read()
+            with open(p, "r+b" if p.exists() else "wb") as f:
+                f.write(data)
+                f.truncate()
+        shutil.copy(src + ".bai", str(p) + ".bai")
+
+    pile, filt = dict(bam_path=str(p), bin_size=25), dict(min_mapq=10)
+    for src, replace in [(a, True), (a, True), (b, True), (a, False), (b, False), (b, False)]:
+        put(src, replace)
+        same(backend, oracle, pile, filt)
+    with backend.pileup(pile, filt) as h1, backend.pileup(pile, filt) as h2:  # two handles on one file at once
+        r1, r2 = h1.runs(), h2.runs()
+    assert (r1 == r2).all() and (r1 == oracle.pileup_runs(pile, filt)[0]).all()
