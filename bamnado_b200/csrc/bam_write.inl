@@ -355,6 +355,18 @@ struct BamWriteJob {
       if (cls[k].ub + bytes > cls[k].cap && !(mode == BAMW_SPLIT_EXOGENOUS && k == 2)) need = true;
     if (!need) return;
     for (auto &s : ctx->sets) CU(cudaStreamSynchronize(s.stream));
+    // the bound counts every inflated byte of every segment; what the filter kept is known on the device: with the exact
+    // lengths most alarms are false (a filter that keeps a third of the reads flushed 23 times for 14 GB at the BASELINE
+    // size), and a flush only happens once a stream is at least half full
+    uint64_t len[BAMW_MAX_CLASSES];
+    CU(cudaMemcpy(len, d_class_len.p, sizeof len, cudaMemcpyDeviceToHost));
+    need = false;
+    for (int k = 0; k < n_classes; k++) {
+      cls[k].ub = len[k];
+      if (mode == BAMW_SPLIT_EXOGENOUS && k == 2) continue;
+      if (len[k] + bytes > cls[k].cap || len[k] > cls[k].cap / 2) need = true;
+    }
+    if (!need) return;
     flush(false);
     for (int k = 0; k < n_classes; k++) {
       ClassStream &s = cls[k];

@@ -308,6 +308,7 @@ struct ReaderPool {
   bool stop = false;
   std::vector<std::thread> threads;
 
+  const bool drop_ptes = env_u64("BND_DROP_PTES", 0) != 0;
   ReaderPool(int fd_, const uint8_t *map_, DeviceCtx &c, const std::vector<Segment> &s, int n_threads) : fd(fd_), map(map_), ctx(c), segs(s) {
     for (int i = 0; i < n_threads; i++) threads.emplace_back([this] { work(); });
   }
@@ -358,10 +359,14 @@ struct ReaderPool {
         if (map) {
           stream_copy(slot.pin + j.off, map + s.begin + j.off, j.len);
           got = j.len;
-          // drop the page-table entries of the pages this piece covers completely (the page cache keeps the data): otherwise
-          // unmapping the whole file at the end costs ~10 ms per GB on the caller's critical path
-          const uintptr_t a0 = ((uintptr_t)(map + s.begin + j.off) + 4095) & ~(uintptr_t)4095, a1 = (uintptr_t)(map + s.begin + j.off + j.len) & ~(uintptr_t)4095;
-          if (a1 > a0) madvise((void *)a0, a1 - a0, MADV_DONTNEED);
+          // BND_DROP_PTES=1: drop the page-table entries of the pages this piece covers completely (the page cache keeps the
+          // data), which made unmapping the file at the end of a job cheap.  Off since the mapping outlives the handle
+          // (MapCache) and is torn down in the background: the entries are then worth keeping, the next pass over the same
+          // file takes no page faults at all.
+          if (drop_ptes) {
+            const uintptr_t a0 = ((uintptr_t)(map + s.begin + j.off) + 4095) & ~(uintptr_t)4095, a1 = (uintptr_t)(map + s.begin + j.off + j.len) & ~(uintptr_t)4095;
+            if (a1 > a0) madvise((void *)a0, a1 - a0, MADV_DONTNEED);
+          }
         }
         while (got < j.len) {
           ssize_t r = pread(fd, slot.pin + j.off + got, j.len - got, (off_t)(s.begin + j.off + got));
