@@ -231,3 +231,21 @@ def test_cli_bam_writers(backend, oracle, tmp_path, make_bam, capfd):
     assert backend.cli_main(["bamnado", "split", "-o", str(out)]) == 2
     assert backend.cli_main(["bamnado", "split", "-i", str(tmp_path / "nope.bam"), "-o", str(out)]) == 1
     capfd.readouterr()
+
+
+def test_long_records_span_bgzf_blocks(backend, oracle, tmp_path, make_bam, monkeypatch):
+    # records of ~75 KB: every record is longer than a BGZF block (65 280 bytes), most blocks hold no record start at all, the
+    # compressor parses them in pieces without a record lag; segments of 256 KiB make nearly every record straddle two segments
+    monkeypatch.setenv("BND_SEGMENT_BYTES", "262144")
+    monkeypatch.setenv("BND_BAM_STREAM_BYTES", str(1 << 20))
+    bam = make_bam("w_long", "--pairs", 60, "--seed", 21, "--read-len", 50000, "--contigs", "chr1:3000000,spike_x:900000")
+    got, want = tmp_path / "l.bam", tmp_path / "l.oracle.bam"
+    st = backend.bam_split(bam, got, dict(min_mapq=1))
+    assert oracle.bam_split(bam, want, dict(min_mapq=1)) == assert_same_bam(got, want) == st["n_written"] > 20
+    assert max(len(r) for r in read_bam(got)[2]) > 0xff00
+    st = backend.bam_split_exogenous(bam, tmp_path / "lx", "spike_", dict())
+    paths = [tmp_path / f"lo.{n}.bam" for n in ("endogenous", "exogenous", "both", "unmapped")]
+    ost = oracle.bam_split_exogenous(bam, paths, "spike_", dict())
+    assert {k: st[k] for k in ost} == ost
+    for n, w in zip(("endogenous", "exogenous", "both", "unmapped"), paths):
+        assert_same_bam(tmp_path / f"lx.{n}.bam", w)
