@@ -48,7 +48,8 @@ struct alignas(16) SpecSmemT {
   uint16_t m_dist[NT];
   __device__ __forceinline__ uint16_t *codes() { return reinterpret_cast<uint16_t *>(m_pl); }     // 320 x u16
   __device__ __forceinline__ uint8_t *lens() { return reinterpret_cast<uint8_t *>(m_pl) + 640; }  // 320 x u8
-  static_assert(NT * 4 >= 960 && NT % 8 == 0, "match list must hold the table-building scratch");
+  __device__ __forceinline__ uint16_t *table_scratch() { return reinterpret_cast<uint16_t *>(m_pl) + 480; }  // 48 x u16 at byte 960
+  static_assert(NT * 6 >= 1056 && NT % 8 == 0, "match list (m_pl and m_dist are adjacent) must hold the table-building scratch");
 };
 
 enum : uint32_t { SPAN_OK = 0, SPAN_EOB = 1, SPAN_BAD_SYMBOL = 2, SPAN_BAD_DISTANCE = 3, SPAN_PAST_END = 4 };
@@ -62,14 +63,22 @@ __device__ bool build_lit_two_level(const Tile<32> &tile, Smem &S) {
   uint16_t *lut = S.lit_lut;
   uint16_t *codes = S.codes();
   const uint8_t *lens = S.lens();
+  // count / first code / next code per length: 48 x u16 behind the code-length scratch (lane 0 kept them in local memory before:
+  // 370 LDL / STL in the SASS of round 2, and 2 x 288 iterations executed by one lane)
+  uint16_t *count = S.table_scratch(), *first = count + 16, *next_code = count + 32;
   for (int i = lane; i < (1 << ROOT) + SUB; i += 32) lut[i] = 0;
+  if (lane < 16) count[lane] = 0;
   tile.sync();
+  // histogram of the 288 code lengths, 32 symbols at a time: the lanes holding the same length elect one of them to add their number
+#pragma unroll 1
+  for (int c = 0; c < 9; c++) {
+    const uint32_t l = lens[c * 32 + lane];
+    const unsigned peers = __match_any_sync(0xffffffffu, l);
+    if (l && lane == __ffs((int)peers) - 1) count[l] = (uint16_t)(count[l] + __popc(peers));
+    tile.sync();
+  }
   bool ok = true;
   if (lane == 0) {
-    uint16_t count[16], first[16], next_code[16];
-    for (int l = 0; l < 16; l++) count[l] = 0;
-    for (int s = 0; s < 288; s++) count[lens[s]]++;
-    count[0] = 0;
     int left = 1;
     uint32_t code = 0;
     first[0] = 0;
@@ -81,11 +90,26 @@ __device__ bool build_lit_two_level(const Tile<32> &tile, Smem &S) {
       next_code[l] = (uint16_t)code;
       first[l] = (uint16_t)code;
     }
-    if (ok) {
-      for (int s = 0; s < 288; s++) {
-        const int l = lens[s];
-        if (l) codes[s] = next_code[l]++;
-      }
+  }
+  ok = tile.shfl((int)ok, 0) != 0;
+  tile.sync();
+  if (!ok) return false;
+  // canonical codes: symbols of one length take consecutive codes in symbol order
+#pragma unroll 1
+  for (int c = 0; c < 9; c++) {
+    const int s = c * 32 + lane;
+    const uint32_t l = lens[s];
+    const unsigned peers = __match_any_sync(0xffffffffu, l);
+    const uint32_t base = next_code[l & 15u];
+    tile.sync();
+    if (l) {
+      codes[s] = (uint16_t)(base + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
+      if (lane == __ffs((int)peers) - 1) next_code[l] = (uint16_t)(base + (uint32_t)__popc(peers));
+    }
+    tile.sync();
+  }
+  if (lane == 0) {
+    {
       // second-level tables, longest codes first: the first code length that reaches a root prefix is its longest
       uint32_t off = 2;  // entries 0, 1 stay zero: "no code"
       for (int l = 15; l > ROOT && ok; l--) {

@@ -166,6 +166,15 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
       if (s[i]) out |= 1u << i;
   return out;
 }
+template <class T>
+inline unsigned __match_any_sync(unsigned mask, T v) {
+  const uint64_t *s = emul::exchange(mask, v);
+  const uint64_t mine = emul::to_bits(v);
+  unsigned out = 0;
+  for (int i = 0; i < 32; i++)
+    if (((mask >> i) & 1u) && s[i] == mine) out |= 1u << i;
+  return out;
+}
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) {
