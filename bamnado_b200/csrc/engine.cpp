@@ -454,8 +454,11 @@ struct Unmapper {
       }
     }
     auto done = std::make_shared<std::atomic<bool>>(false);
+    // piece by piece: munmap holds the process's mmap lock while it runs (≈ 8 ms per GB of touched pages on the B200 hosts), and the
+    // next job's own mmap calls would wait behind one long call (12-18 ms at the start of every other bench step)
     jobs.push_back(Job{std::thread([map, len, done] {
-                         munmap(map, len);
+                         const uint64_t step = 64ull << 20;
+                         for (uint64_t off = 0; off < len; off += step) munmap(map + off, std::min<uint64_t>(step, len - off));
                          done->store(true);
                        }),
                        done});
@@ -2438,6 +2441,7 @@ void Pileup::to_bedgraph(const std::string &path) {
   std::vector<std::thread> touchers;
   char *premap = nullptr;
   uint64_t premap_len = 0;
+  double t_setup = t00;
   auto stop_background = [&] {
     prealloc_stop.store(true);
     if (prealloc_thread.joinable()) prealloc_thread.join();
@@ -2491,6 +2495,7 @@ void Pileup::to_bedgraph(const std::string &path) {
         }
       }
     }
+    t_setup = now_ms();
     ensure_finalized();
   } catch (...) {
     stop_background();
@@ -2498,10 +2503,15 @@ void Pileup::to_bedgraph(const std::string &path) {
     close(fd);
     throw;
   }
+  const double t_fin = now_ms();
   stop_background();
+  const double t_bg = now_ms();
   g_unmapper.reap();  // the previous job's output mapping was torn down while this pile-up ran
   const uint64_t prealloc = prealloc_done.load();
   const double t0 = now_ms();
+  if (env_u64("BND_DEBUG_TIMING", 0))
+    fprintf(stderr, "[bnd] to_bedgraph: open + background start %.2f ms, accumulate + finalize %.2f ms, background stop %.2f ms, unmap reap %.2f ms\n", t_setup - t00,
+            t_fin - t_setup, t_bg - t_fin, t0 - t_bg);
   std::lock_guard<std::mutex> lock(ctx.mu);
   TextJob job;
   uint64_t out_bytes = 0;
