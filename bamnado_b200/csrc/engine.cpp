@@ -433,14 +433,28 @@ struct Unmapper {
   };
   std::mutex mu;
   std::vector<Job> jobs;
+  // A teardown holds the process's mmap lock (≈ 8 ms per GB of touched pages on the B200 hosts).  A job that follows at once sets
+  // up its own mappings and threads in its first millisecond, and would do so behind that lock (12-26 ms measured at the start of
+  // every bench step but the first).  The teardown therefore waits a moment before it starts, unless somebody is waiting for it.
+  std::mutex go_mu;
+  std::condition_variable go_cv;
+  bool hurry = false;
   void reap() {  // waits for every teardown
     std::vector<Job> t;
     {
       std::lock_guard<std::mutex> g(mu);
       t.swap(jobs);
     }
+    if (t.empty()) return;
+    {
+      std::lock_guard<std::mutex> g(go_mu);
+      hurry = true;
+    }
+    go_cv.notify_all();
     for (auto &x : t)
       if (x.th.joinable()) x.th.join();
+    std::lock_guard<std::mutex> g(go_mu);
+    hurry = false;
   }
   void submit(char *map, uint64_t len) {
     std::lock_guard<std::mutex> g(mu);
@@ -454,10 +468,12 @@ struct Unmapper {
       }
     }
     auto done = std::make_shared<std::atomic<bool>>(false);
-    // piece by piece: munmap holds the process's mmap lock while it runs (≈ 8 ms per GB of touched pages on the B200 hosts), and the
-    // next job's own mmap calls would wait behind one long call (12-18 ms at the start of every other bench step)
-    jobs.push_back(Job{std::thread([map, len, done] {
-                         const uint64_t step = 64ull << 20;
+    jobs.push_back(Job{std::thread([this, map, len, done] {
+                         if (len > (256ull << 20)) {
+                           std::unique_lock<std::mutex> lk(go_mu);
+                           go_cv.wait_for(lk, std::chrono::milliseconds(60), [this] { return hurry; });
+                         }
+                         const uint64_t step = 64ull << 20;  // piece by piece: other threads get the lock in between
                          for (uint64_t off = 0; off < len; off += step) munmap(map + off, std::min<uint64_t>(step, len - off));
                          done->store(true);
                        }),
