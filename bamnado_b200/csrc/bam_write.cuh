@@ -11,9 +11,9 @@
 //   bamw_gather     records copied into their class stream (warp-wide word copies), Tn5 fields patched in place
 //                   (pos, bin, mate pos, tlen), first record start of every 65 280-byte block noted for the compressor
 //   bamw_deflate    one CTA per BGZF block: DEFLATE with dynamic Huffman codes built per block (RFC 1951 3.2.7).  The LZ77
-//                   parse is record-parallel: BAM records repeat the previous record field by field, so every record is
-//                   parsed by its own thread against two fixed lags - the distance to the previous record's start and 1 -
-//                   with no hash table and no serial walk; a block scan of the per-record bit counts gives every thread
+//                   parse is record-parallel: BAM records repeat the records before them field by field, so every record is
+//                   parsed by its own thread against the same field (fixed part + name / CIGAR .. qualities / tags) of the
+//                   last eight records and against lag 1, with no hash table and no serial walk; a block scan of the per-record bit counts gives every thread
 //                   its bit offset.  gzip header with the BC field, CRC-32 (warp-interleaved tables of the inflate kernel)
 //                   and ISIZE are written by the same kernel; incompressible blocks fall back to a stored block.
 // All of it is byte / integer work bound by shared-memory and L2 latency; no tensor-core shape.
@@ -27,6 +27,9 @@ constexpr int BAMW_THREADS = 256;
 constexpr uint32_t BAMW_MAX_UNITS = 2048;  // records of one block (>= 36 bytes each) + pieces of long records
 constexpr uint32_t BAMW_PIECE = 1024;      // longer records are parsed in pieces of this many bytes
 constexpr uint32_t BAMW_NONE = 0xffffffffu;
+constexpr uint32_t BAMW_MAX_RECS = 1824;    // >= BGZF_RAW / 36 + 2
+constexpr uint32_t BAMW_NOREC = 0xffffu;
+constexpr int BAMW_BACK = 8;                // previous records whose fields are tried as match sources
 
 // ---- record classes ----------------------------------------------------------------------------------------------------------
 // UCSC binning scheme (SAM spec 5.3), the `bin` field a BAM encoder writes for [beg, end)
@@ -289,10 +292,9 @@ struct DflShared {
   uint16_t lit_code[288], dist_code[32];
   uint8_t lit_len[288], dist_len[32];
   uint16_t unit_start[BAMW_MAX_UNITS + 1];
-  uint16_t unit_lag[BAMW_MAX_UNITS];       // distance to the previous record's start: fixed fields and read name
-  uint16_t unit_lag_mid[BAMW_MAX_UNITS];   // ... to its CIGAR start: CIGAR, sequence, qualities (from unit_mid on)
-  uint16_t unit_lag_aux[BAMW_MAX_UNITS];   // ... to its aux start: the tags (from unit_aux on)
-  uint16_t unit_mid[BAMW_MAX_UNITS], unit_aux[BAMW_MAX_UNITS];
+  uint16_t unit_rec[BAMW_MAX_UNITS];        // record the unit is a piece of (BAMW_NOREC: the tail of a record that started in an earlier block)
+  // per record of the block: where it starts, where its CIGAR starts, where its tags start (BAMW_NOREC: not known / outside the block)
+  uint16_t rec_start[BAMW_MAX_RECS], rec_mid[BAMW_MAX_RECS], rec_aux[BAMW_MAX_RECS];
   uint8_t rle_sym[320], rle_ext[320];
   uint16_t cl_code[19];
   uint8_t cl_len[19];
@@ -435,28 +437,24 @@ __global__ void __launch_bounds__(BAMW_THREADS) bamw_deflate_kernel(BamwDeflateA
     // ---- 2. units (thread 0 follows the record chain of the block) and the CRC-32 (warp 1) ----
     if (tid == 0) {
       uint32_t k = 0;
-      // [s, e) in pieces; lags beyond the DEFLATE window are dropped
-      auto add = [&](uint32_t s, uint32_t e, uint32_t lag, uint32_t lag_mid, uint32_t lag_aux, uint32_t mid, uint32_t aux) {
-        if (lag > 32768u) lag = 0;
-        if (lag_mid > 32768u) lag_mid = 0;
-        if (lag_aux > 32768u) lag_aux = 0;
+      // [s, e) of record r in pieces
+      auto add = [&](uint32_t s, uint32_t e, uint32_t r) {
         while (s < e && k < BAMW_MAX_UNITS - 1) {
           const uint32_t q = k == BAMW_MAX_UNITS - 2 ? e : tmin<uint32_t>(e, s + BAMW_PIECE);
-          S.unit_start[k] = (uint16_t)s, S.unit_lag[k] = (uint16_t)lag, S.unit_lag_mid[k] = (uint16_t)lag_mid, S.unit_lag_aux[k] = (uint16_t)lag_aux;
-          S.unit_mid[k] = (uint16_t)mid, S.unit_aux[k] = (uint16_t)aux;
+          S.unit_start[k] = (uint16_t)s, S.unit_rec[k] = (uint16_t)r;
           k++;
           s = q;
         }
       };
       uint32_t first = a.first_rec ? a.first_rec[b] : BAMW_NONE;
       if (first >= n) first = n;
-      add(0, first, 0, 0, 0, n, n);
-      // Records differ in name, CIGAR and read length, so one lag does not line every field up with the previous record: the
+      add(0, first, BAMW_NOREC);
+      // Records differ in name, CIGAR and read length, so one lag does not line every field up with an earlier record: the
       // fixed fields and the name repeat at the distance of the record starts, CIGAR / sequence / qualities at the distance of
-      // the CIGAR starts, the tags at the distance of the aux starts.
-      uint32_t p = first, prev = BAMW_NONE, prev_mid = BAMW_NONE, prev_aux = BAMW_NONE;
-      while (p < n) {
-        uint32_t q = n, mid = n, aux = n;
+      // the CIGAR starts, the tags at the distance of the aux starts.  The table below lets the parse try the last few records.
+      uint32_t p = first, r = 0;
+      while (p < n && r < BAMW_MAX_RECS) {
+        uint32_t q = n, mid = BAMW_NOREC, aux = BAMW_NOREC;
         if (p + 4 <= n) {
           const uint32_t bs = (uint32_t)raw[p] | ((uint32_t)raw[p + 1] << 8) | ((uint32_t)raw[p + 2] << 16) | ((uint32_t)raw[p + 3] << 24);
           if (bs >= 32 && bs < REC_MAX_SIZE && (uint64_t)p + 4 + bs < (uint64_t)n) q = p + 4 + bs;
@@ -464,15 +462,15 @@ __global__ void __launch_bounds__(BAMW_THREADS) bamw_deflate_kernel(BamwDeflateA
             const uint32_t lrn = raw[p + 12], nc = (uint32_t)raw[p + 16] | ((uint32_t)raw[p + 17] << 8);
             const uint32_t ls = (uint32_t)raw[p + 20] | ((uint32_t)raw[p + 21] << 8) | ((uint32_t)raw[p + 22] << 16) | ((uint32_t)raw[p + 23] << 24);
             const uint64_t m64 = (uint64_t)p + 36 + lrn, a64 = m64 + 4ull * nc + ((uint64_t)ls + 1) / 2 + ls;
-            if (a64 <= (uint64_t)p + 4 + bs) mid = (uint32_t)tmin<uint64_t>(m64, n), aux = (uint32_t)tmin<uint64_t>(a64, n);
+            if (a64 <= (uint64_t)p + 4 + bs && m64 < n) mid = (uint32_t)m64, aux = a64 < n ? (uint32_t)a64 : BAMW_NOREC;
           }
         }
-        const bool have = prev != BAMW_NONE;
-        add(p, q, have ? p - prev : 0u, have && mid < n && prev_mid != BAMW_NONE ? mid - prev_mid : 0u,
-            have && aux < n && prev_aux != BAMW_NONE ? aux - prev_aux : 0u, mid, aux);
-        prev = p, prev_mid = mid < n ? mid : BAMW_NONE, prev_aux = aux < n ? aux : BAMW_NONE;
+        S.rec_start[r] = (uint16_t)p, S.rec_mid[r] = (uint16_t)mid, S.rec_aux[r] = (uint16_t)aux;
+        add(p, q, r);
+        r++;
         p = q;
       }
+      if (p < n) add(p, n, BAMW_NOREC);  // cannot happen (a record is at least 36 bytes); kept so that every byte belongs to a unit
       S.unit_start[k] = (uint16_t)n;
       S.n_units = k;
     }
@@ -485,20 +483,31 @@ __global__ void __launch_bounds__(BAMW_THREADS) bamw_deflate_kernel(BamwDeflateA
     __syncthreads();
     const uint32_t U = S.n_units, K = (U + BAMW_THREADS - 1) / BAMW_THREADS;
     const uint32_t u0 = tmin<uint32_t>(U, (uint32_t)tid * K), u1 = tmin<uint32_t>(U, u0 + K);
-    // ---- 3. greedy parse of every unit against its two lags; tokens to scratch; frequencies ----
+    // ---- 3. greedy parse of every unit against the fields of the records before it and lag 1; tokens to scratch; frequencies ----
     if (!S.stored) {
       for (uint32_t u = u0; u < u1; u++) {
         const uint32_t s = S.unit_start[u], e = S.unit_start[u + 1];
-        const uint32_t lag_a = S.unit_lag[u], lag_m = S.unit_lag_mid[u], lag_x = S.unit_lag_aux[u], mid = S.unit_mid[u], aux = S.unit_aux[u];
+        const uint32_t r = S.unit_rec[u];
+        const uint32_t mid = r == BAMW_NOREC ? BAMW_NOREC : S.rec_mid[r], aux = r == BAMW_NOREC ? BAMW_NOREC : S.rec_aux[r];
         uint32_t p = s, k = 0;
         while (p < e) {
           const uint32_t maxm = tmin<uint32_t>(258u, e - p);
-          const uint32_t lag = p < mid ? lag_a : p < aux ? lag_m : lag_x;
           uint32_t best = 0, bestd = 0;
-          if (lag && p >= lag) {
-            uint32_t m = 0;
-            while (m < maxm && raw[p + m] == raw[p + m - lag]) m++;
-            if (m >= 4) best = m, bestd = lag;
+          if (r != BAMW_NOREC) {
+            // the same field of the last few records: 0 = fixed fields and name, 1 = CIGAR .. qualities, 2 = tags
+            const int field = p < mid ? 0 : p < aux ? 1 : 2;
+            const uint32_t here = field == 0 ? S.rec_start[r] : field == 1 ? mid : aux;
+#pragma unroll 1
+            for (int back = 1; back <= BAMW_BACK && (uint32_t)back <= r; back++) {
+              const uint32_t there = field == 0 ? S.rec_start[r - back] : field == 1 ? S.rec_mid[r - back] : S.rec_aux[r - back];
+              if (there == BAMW_NOREC) continue;
+              const uint32_t lag = here - there;
+              if (lag > 32768u || lag > p) continue;
+              uint32_t m = 0;
+              while (m < maxm && raw[p + m] == raw[p + m - lag]) m++;
+              if (m >= 4 && m > best + (best ? 1u : 0u)) best = m, bestd = lag;  // a farther source pays a longer distance code
+              if (best >= 32) break;  // long enough: the records further back are not asked
+            }
           }
           if (p >= 1 && raw[p] == raw[p - 1]) {
             uint32_t m = 1;
