@@ -417,21 +417,29 @@ __global__ void __launch_bounds__(BAMW_THREADS) bamw_deflate_kernel(BamwDeflateA
   const int tid = (int)threadIdx.x;
   uint32_t *tok = a.tokens + (size_t)blockIdx.x * BGZF_RAW;
   const uint8_t cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  __shared__ __align__(8) unsigned long long s_mbar;
+  const saddr_t mbar = smem_addr(&s_mbar);
+  if (tid == 0) mbar_init(mbar, 1);
+  uint32_t phase = 0;
+  __syncthreads();
   for (uint32_t b = blockIdx.x; b < a.n_blocks; b += gridDim.x) {
     const uint64_t base = (uint64_t)b * BGZF_RAW;
     const uint32_t n = (uint32_t)tmin<uint64_t>(BGZF_RAW, a.raw_len - base);
     uint32_t *img = reinterpret_cast<uint32_t *>(a.out + (size_t)b * BGZF_SLOT);
-    // ---- 1. the block into shared memory; histograms cleared ----
+    // ---- 1. the block into shared memory: one bulk copy by the copy engine (the previous iteration ended with a barrier, nobody
+    //         touches `raw` any more), the last bytes by hand; histograms cleared meanwhile ----
     {
-      const uint4 *g = reinterpret_cast<const uint4 *>(a.raw + base);
-      uint4 *s = reinterpret_cast<uint4 *>(raw);
-      const uint32_t n16 = n / 16;
-      for (uint32_t i = (uint32_t)tid; i < n16; i += BAMW_THREADS) s[i] = g[i];
-      for (uint32_t i = n16 * 16 + (uint32_t)tid; i < n; i += BAMW_THREADS) raw[i] = a.raw[base + i];
+      const uint32_t n16 = n & ~15u;
+      if (tid == 0 && n16) bulk_copy_g2s(smem_addr(raw), a.raw + base, n16, mbar);
+      for (uint32_t i = n16 + (uint32_t)tid; i < n; i += BAMW_THREADS) raw[i] = a.raw[base + i];
       for (int i = tid; i < 288 + 32; i += BAMW_THREADS) S.hist[i] = 0;
       for (int i = tid; i < 288; i += BAMW_THREADS) S.lit_len[i] = 0, S.lit_code[i] = 0;
       if (tid < 32) S.dist_len[tid] = 0, S.dist_code[tid] = 0;
       if (tid == 0) S.n_lit = S.n_dist = 0, S.stored = (uint32_t)a.store_only;
+      if (n16) {
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+      }
     }
     __syncthreads();
     // ---- 2. units (thread 0 follows the record chain of the block) and the CRC-32 (warp 1) ----

@@ -72,6 +72,9 @@ __device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v) { *(uint32_t *)a 
 __device__ __forceinline__ void sts_u16(saddr_t a, uint32_t v) { *(uint16_t *)a = (uint16_t)v; }
 __device__ __forceinline__ void cp_async_u32(saddr_t dst, const void *src) { *(uint32_t *)dst = *(const uint32_t *)src; }
 __device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ void mbar_init(saddr_t, uint32_t) {}
+__device__ __forceinline__ void bulk_copy_g2s(saddr_t dst, const void *src, uint32_t bytes, saddr_t) { memcpy((void *)dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(saddr_t, uint32_t) {}
 #else
 typedef uint32_t saddr_t;
 __device__ __forceinline__ saddr_t smem_addr(const void *p) { return (saddr_t)__cvta_generic_to_shared(p); }
@@ -92,6 +95,27 @@ __device__ __forceinline__ void cp_async_u32(saddr_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// ---- bulk asynchronous copy (TMA engine: UBLKCP in the SASS) completed through an mbarrier ----------------------------------
+// One elected thread hands a whole tile (16-byte aligned source and destination, size a multiple of 16) to the copy engine; the
+// consumers wait on the barrier's phase.  Used where a CTA stages tens of KB at once (the BGZF compressor's 64 KB block); K1's
+// 1.3 KB rounds are better off with per-lane cp.async (profiles/r2_sweeps.md).
+__device__ __forceinline__ void mbar_init(saddr_t mbar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// Caller: every thread that read or wrote the destination through ordinary loads / stores has passed a barrier before this.
+__device__ __forceinline__ void bulk_copy_g2s(saddr_t dst, const void *src, uint32_t bytes, saddr_t mbar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to dst are ordered before the engine's writes
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(saddr_t mbar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  } while (!done);
+}
 #endif
 
 // ---- unaligned little-endian loads (BAM records sit at arbitrary byte offsets) ---------------------------------
