@@ -75,6 +75,8 @@ __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ void mbar_init(saddr_t, uint32_t) {}
 __device__ __forceinline__ void bulk_copy_g2s(saddr_t dst, const void *src, uint32_t bytes, saddr_t) { memcpy((void *)dst, src, bytes); }
 __device__ __forceinline__ void mbar_wait(saddr_t, uint32_t) {}
+__device__ __forceinline__ void bulk_store_fence() {}
+__device__ __forceinline__ void bulk_store_s2g(void *dst, saddr_t src, uint32_t bytes) { memcpy(dst, (const void *)src, bytes); }
 #else
 typedef uint32_t saddr_t;
 __device__ __forceinline__ saddr_t smem_addr(const void *p) { return (saddr_t)__cvta_generic_to_shared(p); }
@@ -115,6 +117,15 @@ __device__ __forceinline__ void mbar_wait(saddr_t mbar, uint32_t parity) {
   do {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
   } while (!done);
+}
+// shared -> global by the copy engine (UBLKCP.G.S): every thread that wrote the tile calls bulk_store_fence() before the barrier
+// that precedes the store; the issuing thread returns once the engine has READ the tile (shared memory reusable), the global
+// writes complete on their own
+__device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_s2g(void *dst, saddr_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 #endif
 

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(THREADS) text_scan_kernel(TextArgs a) {
 }
 
 // A tile's rows (256 x ~43 bytes) are formatted into shared memory, at the same 16-byte phase as their place in the output, and
-// leave as aligned 16-byte stores: the per-thread byte stores of the first version reached 150 GB/s (14 ms for the 2.1 GB of the
+// leave as one bulk store of the copy engine (plus the ragged ends): the per-thread byte stores of the first version reached 150 GB/s (14 ms for the 2.1 GB of the
 // BASELINE run, profiles/r2_launches_bench_10Mpairs_summary.txt).  Tiles longer than the staging buffer take the direct path.
 constexpr uint32_t TEXT_STAGE = 24 * 1024;
 __device__ __forceinline__ void text_format_row(const TextArgs &a, char *p, int32_t ref, uint64_t start, uint64_t stop, uint32_t val) {
@@ -337,14 +337,15 @@ __global__ void __launch_bounds__(TEXT_THREADS) text_write_kernel(TextArgs a) {
       if (gb == tmax<uint64_t>(__ldg(a.g.ref_first_bin + ref), a.g.bin_lo)) a.ref_text_off[ref] = off;  // first row of the reference in this shard
       if (len) text_format_row(a, staged ? stage + phase + (off - tile_off) : a.text + off, ref, start, stop, a.run_val[j]);
     }
+    if (staged) bulk_store_fence();  // the rows written above become visible to the copy engine
     __syncthreads();
     if (staged && total) {
       char *dst = a.text + tile_off - phase;  // 16-byte aligned; stage[k] belongs at dst[k] for k in [phase, phase + total)
       const uint32_t end = phase + (uint32_t)total;
       const uint32_t v0 = phase ? 16u : 0u, v1 = end & ~15u;  // whole 16-byte lines inside the tile
+      // the aligned middle of the tile (~11 KB) leaves as ONE bulk store of the copy engine, the ragged ends by hand
+      if (tid == 0 && v1 > v0) bulk_store_s2g(dst + v0, smem_addr(stage + v0), v1 - v0);
       for (uint32_t k = phase + (uint32_t)tid; k < tmin<uint32_t>(v0, end); k += TEXT_THREADS) dst[k] = stage[k];
-      for (uint32_t k = v0 + 16u * (uint32_t)tid; k + 16u <= v1; k += 16u * TEXT_THREADS)
-        *reinterpret_cast<uint4 *>(dst + k) = *reinterpret_cast<const uint4 *>(stage + k);
       for (uint32_t k = tmax<uint32_t>(v1, v0) + (uint32_t)tid; k < end; k += TEXT_THREADS) dst[k] = stage[k];
     }
     __syncthreads();
