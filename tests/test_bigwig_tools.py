@@ -216,3 +216,31 @@ def test_cli_bigwig_tools(backend, tmp_path, capfd):
     assert backend.cli_main(["bamnado", "bigwig-aggregate", "--bigwigs", str(a), "-o", str(out), "-m", "mode"]) == 2
     assert backend.cli_main(["bamnado", "bigwig-aggregate", "--bigwigs", str(a), str(b), "-o", str(out), "-m", "sum", "--scale-factors", "1"]) == 1
     capfd.readouterr()
+
+
+def test_tools_on_coverage_tracks(backend, tmp_path, make_bam):
+    # end to end: two coverage tracks written by the device BigWig encoder (bam-coverage -o x.bw), then compared and aggregated
+    bams = [make_bam("bwt_a", "--pairs", 4000, "--seed", 31, "--contigs", "chr1:300000,chr2:120000"),
+            make_bam("bwt_b", "--pairs", 6000, "--seed", 32, "--contigs", "chr1:300000,chr2:120000")]
+    tracks, paths, chroms = [], [], None
+    for k, bam in enumerate(bams):
+        p = tmp_path / f"cov{k}.bw"
+        with backend.pileup(dict(bam_path=bam, bin_size=20, norm="cpm"), dict(min_mapq=10)) as h:
+            h.to_bigwig(p)
+        info, per = read_per_chrom(p)
+        chroms = sorted(((n, cid, ln) for n, (cid, ln) in info["chroms"].items()), key=lambda c: c[1])
+        tracks.append({n: [(s, e, float(v)) for s, e, v in ivs] for n, ivs in per.items()})
+        paths.append(str(p))
+    out = tmp_path / "cmp.bw"
+    backend.bigwig_compare(paths[0], paths[1], out, "subtraction", 50, scale_factor_bw2=0.5)
+    _, got = read_per_chrom(out)
+    for name, _, ln in chroms:
+        want = O.merge_bins(O.compare(tracks[0][name], tracks[1][name], ln, 50, "subtraction", scale2=0.5), ln, 50)
+        assert len(got[name]) == len(want) > 10
+        assert all(g[:2] == w[:2] and same_float(g[2], w[2]) for g, w in zip(got[name], want)), name
+    backend.bigwig_aggregate(paths, out, "mean", 100)
+    _, got = read_per_chrom(out)
+    for name, _, ln in chroms:
+        want = O.merge_bins(O.aggregate([t[name] for t in tracks], ln, 100, "mean"), ln, 100)
+        assert len(got[name]) == len(want) > 10
+        assert all(g[:2] == w[:2] and same_float(g[2], w[2]) for g, w in zip(got[name], want)), name
