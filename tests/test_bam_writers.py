@@ -249,3 +249,28 @@ def test_long_records_span_bgzf_blocks(backend, oracle, tmp_path, make_bam, monk
     assert {k: st[k] for k in ost} == ost
     for n, w in zip(("endogenous", "exogenous", "both", "unmapped"), paths):
         assert_same_bam(tmp_path / f"lx.{n}.bam", w)
+
+
+def test_program_group_links_to_the_leaf_of_the_chain(backend, oracle, tmp_path, make_bam):
+    # add_bamnado_program_group (bam_utils.rs:757-780): the new @PG record has id `bamnado`, PN, VN and CL; with programs already in
+    # the header noodles links it to the leaf of every chain (PP).  One chain (the synthetic BAM: synth_bam) -> one record;
+    # test.bam has two leaves (MarkDuplicates and samtools.7) -> `bamnado` and `bamnado-<leaf>`
+    bam = make_bam("w_pg", "--pairs", 200, "--seed", 2, "--contigs", "chr1:100000")
+    got, want = tmp_path / "g.bam", tmp_path / "w.bam"
+    backend.bam_split(bam, got, dict(), command_line="bamnado split -i in.bam -o out.bam")
+    oracle.bam_split(bam, want, dict(), command_line="bamnado split -i in.bam -o out.bam")
+    text = read_bam(got)[0]
+    assert text == read_bam(want)[0]
+    pg = [ln for ln in text.splitlines() if ln.startswith("@PG")]
+    assert len(pg) == 2 and pg[1] == "@PG\tID:bamnado\tPN:bamnado\tVN:0.9.0\tCL:bamnado split -i in.bam -o out.bam\tPP:" + pg[0].split("\t")[1][3:]
+    ref_lines = read_bam_text(TEST_BAM).splitlines()
+    backend.bam_split(TEST_BAM, got, dict(), command_line="x")
+    new = [ln for ln in read_bam(got)[0].splitlines() if ln not in ref_lines]
+    assert [ln.split("\t")[1] for ln in new] == ["ID:bamnado", "ID:bamnado-samtools.7"]  # leaves in header order: MarkDuplicates, samtools.7
+    assert [ln.split("\t")[-1] for ln in new] == ["PP:MarkDuplicates", "PP:samtools.7"]
+    assert all("\tPN:bamnado\tVN:0.9.0\tCL:x\tPP:" in ln for ln in new)
+
+
+def read_bam_text(path):
+    d = gzip.open(path).read(1 << 20)
+    return d[8:8 + struct.unpack_from("<I", d, 4)[0]].decode()
